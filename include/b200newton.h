@@ -1,0 +1,300 @@
+/*
+ * b200newton.h — C ABI of libb200newton.so, the B200-native (sm_100a) Newton iteration core
+ * that sits behind NonlinearSolve.jl's first-order solver plugin points.
+ *
+ * Every entry point is `extern "C"`, takes plain pointers/sizes and returns an int32 status
+ * (0 = B200_OK, negative = infrastructure error, see b200_last_error()).  Numerical outcomes
+ * (converged / max-iters / stalled ...) are NOT errors: they come back in result structs as
+ * retcodes that map 1:1 onto SciMLBase.ReturnCode.
+ *
+ * Reference interface each group replaces (paths relative to the NonlinearSolve.jl tree):
+ *   problems / residual      user f!(du,u,p)      lib/NonlinearSolveBase/src/utils.jl:180-207
+ *                            Brusselator spec     lib/NonlinearSolveFirstOrder/test/sparsity_tests__item1.jl:7-50
+ *   jvp / vjp                JacobianOperator     lib/SciMLJacobianOperators/src/SciMLJacobianOperators.jl:167-182, 238-243, 296-431
+ *   gmres                    LinearSolveJLCache   lib/NonlinearSolveBase/ext/NonlinearSolveBaseLinearSolveExt.jl:16-32
+ *                            (-> LinearSolve.KrylovJL_GMRES -> Krylov.gmres!, external)
+ *   dense jac / LU           JacobianCache        lib/NonlinearSolveBase/src/jacobian.jl:237-258
+ *                            linear cache         lib/NonlinearSolveBase/src/linear_solve.jl:74-147
+ *   sparse pattern/colouring construct_concrete_adtype  lib/NonlinearSolveBase/src/jacobian.jl:286-353
+ *                            colouring choice     lib/NonlinearSolveBase/ext/NonlinearSolveBaseSparseMatrixColoringsExt.jl:13-28
+ *   newton driver            step!                lib/NonlinearSolveFirstOrder/src/solve.jl:325-465
+ *                            termination          lib/NonlinearSolveBase/src/termination_conditions.jl:243-336
+ *                            trust region/dogleg  lib/NonlinearSolveFirstOrder/src/trust_region.jl:396-514,
+ *                                                 lib/NonlinearSolveBase/src/descent/dogleg.jl:86-151
+ *                            forcing              lib/NonlinearSolveFirstOrder/src/eisenstat_walker.jl:42-87
+ *   ensemble                 EnsembleProblem use  test/PolyAlgorithms/core_tests__item6.jl:3-20
+ *
+ * Conventions: all data vectors are Float64 DEVICE pointers unless a parameter name ends in
+ * `_host`; small result structs are HOST pointers.  Work is enqueued on the context's stream;
+ * calls that return a host scalar/struct synchronise that stream.  A context is not thread-safe.
+ * Index arrays are int64 with an explicit `index_base` (Julia: 1).
+ */
+#ifndef B200NEWTON_H
+#define B200NEWTON_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_VERSION 100 /* 0.1.0 */
+
+/* ---------------------------------------------------------------- status codes */
+enum {
+  B200_OK = 0,
+  B200_ERR_CUDA = -1,
+  B200_ERR_INVALID = -2,
+  B200_ERR_NOMEM = -3,
+  B200_ERR_UNSUPPORTED = -4,
+  B200_ERR_CALLBACK = -5,
+  B200_ERR_NO_DEVICE = -6
+};
+
+/* nonlinear-solve return codes; names follow SciMLBase.ReturnCode */
+enum {
+  B200_RC_DEFAULT = 0,
+  B200_RC_SUCCESS = 1,
+  B200_RC_MAXITERS = 2,
+  B200_RC_MAXTIME = 3,
+  B200_RC_STALLED = 4,
+  B200_RC_STALLED_SUCCESS = 5,
+  B200_RC_UNSTABLE = 6,
+  B200_RC_INTERNAL_LINSOLVE_FAILED = 7,
+  B200_RC_INTERNAL_LINESEARCH_FAILED = 8,
+  B200_RC_SHRINK_THRESHOLD_EXCEEDED = 9,
+  B200_RC_INITIAL_FAILURE = 10,
+  B200_RC_FAILURE = 11
+};
+
+/* linear (GMRES) solve status; maps to LinearSolve retcodes (Success / MaxIters / Failure) */
+enum {
+  B200_LS_SOLVED = 1,      /* ||r|| <= atol + rtol*||r0||                    -> ReturnCode.Success  */
+  B200_LS_MAXITERS = 2,    /* itmax reached                                    -> ReturnCode.MaxIters */
+  B200_LS_BREAKDOWN = 3,   /* happy breakdown, solution exact in the subspace  -> ReturnCode.Success  */
+  B200_LS_NONFINITE = 4,   /* NaN/Inf met                                      -> ReturnCode.Failure  */
+  B200_LS_OUT_OF_MEMORY = 5 /* Krylov basis could not grow                     -> ReturnCode.Failure  */
+};
+
+enum { B200_PROB_BRUSS2D = 1, B200_PROB_BRUSS3D = 2, B200_PROB_QUADRATIC = 3, B200_PROB_TRIDIAG_QUAD = 4, B200_PROB_CALLBACK = 5 };
+enum { B200_ORTH_MGS = 0, B200_ORTH_CGS = 1, B200_ORTH_CGS2 = 2 };
+enum { B200_ENGINE_AUTO = 0, B200_ENGINE_MULTIKERNEL = 1, B200_ENGINE_RESIDENT = 2 };
+enum { B200_LINSOLVE_GMRES = 0, B200_LINSOLVE_DENSE_LU = 1, B200_LINSOLVE_SPARSE_GMRES = 2 };
+enum { B200_JVP_EXACT = 0, B200_JVP_FINITE_DIFF = 1 };
+enum { B200_GLOBALIZATION_NONE = 0, B200_GLOBALIZATION_TRUST_REGION = 1 };
+enum { B200_FORCING_NONE = 0, B200_FORCING_EW2 = 1 };
+enum { B200_TERM_ABS_NORM_SAFE_BEST = 0, B200_TERM_ABS_NORM = 1, B200_TERM_ABS_NORM_SAFE = 2 };
+enum { B200_U0_REFERENCE = 0, B200_U0_PERTURBED_Z = 1 };
+enum { B200_ORDER_NATURAL = 0, B200_ORDER_LARGEST_FIRST = 1 };
+
+typedef struct b200_ctx b200_ctx;
+typedef struct b200_problem b200_problem;
+typedef struct b200_linop b200_linop;
+typedef struct b200_gmres b200_gmres;
+typedef struct b200_newton b200_newton;
+typedef struct b200_sparse_jac b200_sparse_jac;
+typedef struct b200_ensemble b200_ensemble;
+
+/* host callbacks invoked between kernels (b1 plug-in point: an arbitrary Julia f!/jvp!/vjp! closure
+ * through @cfunction).  Pointers are device pointers; work must be enqueued on the ctx stream
+ * (b200_ctx_stream) or be complete on return.  Return 0 on success. */
+typedef int32_t (*b200_residual_cb)(void* user, const double* u, double* du);
+typedef int32_t (*b200_jvp_cb)(void* user, const double* u, const double* v, double* Jv);
+typedef int32_t (*b200_matvec_cb)(void* user, const double* x, double* y);
+
+/* ---------------------------------------------------------------- option / result structs */
+typedef struct b200_gmres_opts {
+  int32_t memory;     /* initial basis allocation; Krylov.jl `memory` (LinearSolve passes min(20,n)); grows on demand */
+  int32_t restart;    /* 0 = never restart (KrylovJL_GMRES default gmres_restart=0); k>0 = GMRES(k) */
+  int32_t itmax;      /* 0 => n (LinearSolve default maxiters = length(b)) */
+  int32_t orth;       /* B200_ORTH_* ; MGS = Krylov.jl default (reorthogonalization=false) */
+  int32_t warm_start; /* 0: x0 = 0 ; 1: x_inout holds the initial guess */
+  int32_t engine;     /* B200_ENGINE_* */
+  int32_t check_every;/* host polls the device status every this many Arnoldi iterations (multi-kernel engine); 0 => 8 */
+  int32_t reserved;
+  double atol;
+  double rtol;
+} b200_gmres_opts;
+
+typedef struct b200_gmres_stats {
+  int32_t status;     /* B200_LS_* */
+  int32_t iters;      /* Arnoldi iterations performed */
+  int32_t nmatvec;    /* operator applications (iters + 1 if warm start) */
+  int32_t restarts;
+  double rnorm0;      /* ||b - A x0|| */
+  double rnorm;       /* final residual-norm estimate from the Givens recurrence */
+  double tol;         /* atol + rtol*rnorm0 */
+  double bytes;       /* algorithmic HBM bytes moved by this solve (DESIGN.md accounting) */
+} b200_gmres_stats;
+
+typedef struct b200_newton_opts {
+  double abstol;      /* <=0 => 3e-13 (common_defaults.jl:44-48) */
+  double reltol;      /* <=0 => 3e-13 */
+  int32_t maxiters;   /* <=0 => 1000 (solve.jl:142) */
+  int32_t linsolve;   /* B200_LINSOLVE_* */
+  int32_t jvp_mode;   /* B200_JVP_* */
+  int32_t globalization;
+  int32_t forcing;
+  int32_t termination;
+  int32_t store_trace;
+  int32_t fused_step; /* 1 = fuse u+=du, residual and norms into one kernel (default) ; 0 = separate ops */
+  b200_gmres_opts gmres; /* atol/rtol <= 0 => inherit the nonlinear abstol/reltol (solve.jl:203) */
+  /* Eisenstat-Walker forcing (eisenstat_walker.jl:18-30) */
+  double ew_eta0, ew_eta_max, ew_gamma, ew_alpha, ew_safeguard_threshold;
+  int32_t ew_safeguard;
+  int32_t max_shrink_times; /* trust_region.jl: 32 */
+  /* trust region, RadiusUpdateSchemes.Simple defaults (trust_region.jl:320-384) ; 0 => default */
+  double tr_step_threshold, tr_shrink_threshold, tr_expand_threshold, tr_shrink_factor, tr_expand_factor;
+  double tr_max_trust_radius, tr_initial_trust_radius;
+} b200_newton_opts;
+
+typedef struct b200_newton_result {
+  int32_t retcode;    /* B200_RC_* */
+  int32_t nsteps;     /* NLStats.nsteps */
+  int32_t nf;         /* NLStats.nf   */
+  int32_t njacs;      /* NLStats.njacs */
+  int32_t nfactors;   /* NLStats.nfactors */
+  int32_t nsolve;     /* NLStats.nsolve */
+  int32_t njvp;       /* total Arnoldi operator applications */
+  int32_t ntrace;
+  double resid_inf;   /* ||f(u)||_inf at the returned u */
+  double bytes;       /* algorithmic HBM bytes (DESIGN.md accounting) */
+} b200_newton_result;
+
+typedef struct b200_trace_rec {
+  int32_t iter;
+  int32_t lin_iters;
+  int32_t lin_status;
+  int32_t accepted;   /* trust region: step accepted */
+  double fnorm_inf;   /* ||f(u_iter)||_inf */
+  double step_norm2;  /* ||u_iter - u_{iter-1}||_2 */
+  double lin_rnorm;
+  double trust_radius;
+} b200_trace_rec;
+
+/* ---------------------------------------------------------------- context, memory, events */
+int32_t b200_version(void);
+int32_t b200_device_count(int32_t* count);
+/* stream: an existing cudaStream_t to enqueue on (e.g. torch's current stream), or NULL to create one */
+int32_t b200_ctx_create(int32_t device, void* stream, b200_ctx** ctx);
+int32_t b200_ctx_destroy(b200_ctx* ctx);
+int32_t b200_ctx_sync(b200_ctx* ctx);
+void* b200_ctx_stream(b200_ctx* ctx);
+const char* b200_last_error(b200_ctx* ctx);
+/* number of kernels this library launched on ctx since creation (bench.py's gpu_launches) */
+int32_t b200_ctx_kernel_launches(b200_ctx* ctx, int64_t* count);
+int32_t b200_ctx_sm_count(b200_ctx* ctx, int32_t* count);
+
+int32_t b200_malloc(b200_ctx* ctx, size_t bytes, void** dptr);
+int32_t b200_free(b200_ctx* ctx, void* dptr);
+int32_t b200_host_alloc(b200_ctx* ctx, size_t bytes, void** hptr); /* pinned */
+int32_t b200_host_free(b200_ctx* ctx, void* hptr);
+int32_t b200_memcpy_h2d(b200_ctx* ctx, void* dst, const void* src_host, size_t bytes);
+int32_t b200_memcpy_d2h(b200_ctx* ctx, void* dst_host, const void* src, size_t bytes);
+int32_t b200_memcpy_d2d(b200_ctx* ctx, void* dst, const void* src, size_t bytes);
+int32_t b200_memset(b200_ctx* ctx, void* dst, int32_t byte, size_t bytes);
+int32_t b200_flush_l2(b200_ctx* ctx); /* overwrite a >L2-sized scratch buffer (bench hygiene) */
+
+/* ---------------------------------------------------------------- vector ops (b5: what L2-L4 touch on a device array) */
+int32_t b200_fill(b200_ctx* ctx, int64_t n, double a, double* x);
+int32_t b200_copy(b200_ctx* ctx, int64_t n, const double* x, double* y);
+int32_t b200_scal(b200_ctx* ctx, int64_t n, double a, double* x);
+int32_t b200_axpy(b200_ctx* ctx, int64_t n, double a, const double* x, double* y);             /* y += a x */
+int32_t b200_axpby(b200_ctx* ctx, int64_t n, double a, const double* x, double b, double* y);  /* y = a x + b y */
+int32_t b200_mul(b200_ctx* ctx, int64_t n, const double* x, const double* y, double* z);       /* z = x .* y */
+int32_t b200_dot(b200_ctx* ctx, int64_t n, const double* x, const double* y, double* out_host);
+int32_t b200_nrm2(b200_ctx* ctx, int64_t n, const double* x, double* out_host);
+int32_t b200_norminf(b200_ctx* ctx, int64_t n, const double* x, double* out_host);             /* maximum(abs, x) */
+int32_t b200_diffnrm2(b200_ctx* ctx, int64_t n, const double* x, const double* y, double* out_host); /* ||x-y||_2 */
+int32_t b200_extrema(b200_ctx* ctx, int64_t n, const double* x, double* min_host, double* max_host);
+int32_t b200_equal(b200_ctx* ctx, int64_t n, const double* x, const double* y, int32_t* equal_host);
+
+/* ---------------------------------------------------------------- problems (a1, a2) */
+int32_t b200_problem_create_bruss2d(b200_ctx* ctx, int32_t N, double A, double B, double alpha, b200_problem** prob);
+int32_t b200_problem_create_bruss3d(b200_ctx* ctx, int32_t N, double A, double B, double alpha, b200_problem** prob);
+int32_t b200_problem_create_quadratic(b200_ctx* ctx, int64_t n, double p, b200_problem** prob);          /* f = u.^2 .- p */
+int32_t b200_problem_create_tridiag_quad(b200_ctx* ctx, int64_t n, const double* p_dev, b200_problem** prob); /* rootfind_tests__item20.jl */
+int32_t b200_problem_create_callback(b200_ctx* ctx, int64_t n, b200_residual_cb f, b200_jvp_cb jvp, b200_jvp_cb vjp,
+                                     void* user, b200_problem** prob);
+int32_t b200_problem_destroy(b200_problem* prob);
+int32_t b200_problem_n(b200_problem* prob, int64_t* n);
+int32_t b200_problem_set_AB(b200_problem* prob, double A, double B);     /* remake(prob; p = ...) */
+int32_t b200_problem_u0(b200_problem* prob, int32_t mode, double* u);    /* reference initial condition */
+int32_t b200_residual(b200_problem* prob, const double* u, double* du);
+int32_t b200_jvp(b200_problem* prob, const double* u, const double* v, double* Jv);                      /* exact tangent */
+int32_t b200_residual_jvp(b200_problem* prob, const double* u, const double* v, double* du, double* Jv); /* one halo load */
+int32_t b200_jvp_fd(b200_problem* prob, const double* u, const double* v, double* Jv);                   /* (f(u+eps v)-f(u))/eps, fused */
+int32_t b200_vjp(b200_problem* prob, const double* u, const double* w, double* JTw);
+
+/* ---------------------------------------------------------------- linear operators + GMRES (a3) */
+int32_t b200_linop_from_problem(b200_problem* prob, const double* u, int32_t jvp_mode, b200_linop** op);
+int32_t b200_linop_from_csc(b200_ctx* ctx, int64_t n, const int64_t* colptr_dev, const int64_t* rowval_dev,
+                            const double* nzval_dev, int32_t index_base, b200_linop** op);
+int32_t b200_linop_from_dense(b200_ctx* ctx, int64_t n, const double* A_dev, int64_t ld, b200_linop** op);
+int32_t b200_linop_from_callback(b200_ctx* ctx, int64_t n, b200_matvec_cb mv, void* user, b200_linop** op);
+int32_t b200_linop_apply(b200_linop* op, const double* x, double* y);
+int32_t b200_linop_destroy(b200_linop* op);
+
+void b200_gmres_opts_default(b200_gmres_opts* opts);
+int32_t b200_gmres_create(b200_ctx* ctx, int64_t n, const b200_gmres_opts* opts, b200_gmres** gm);
+int32_t b200_gmres_destroy(b200_gmres* gm);
+int32_t b200_gmres_set_tolerances(b200_gmres* gm, double atol, double rtol); /* LinearSolve.update_tolerances! */
+int32_t b200_gmres_solve(b200_gmres* gm, b200_linop* op, const double* b, double* x_inout, b200_gmres_stats* stats_host);
+
+/* ---------------------------------------------------------------- dense fallback (a5) */
+int32_t b200_dense_jac_fill(b200_problem* prob, const double* u, double* J, int64_t ld); /* column-major n x n */
+int32_t b200_getrf(b200_ctx* ctx, int64_t n, double* A, int64_t ld, int64_t* ipiv_dev, int32_t* info_host); /* LAPACK getrf semantics, 1-based ipiv */
+int32_t b200_getrs(b200_ctx* ctx, int64_t n, int64_t nrhs, const double* A, int64_t ld, const int64_t* ipiv_dev,
+                   double* B, int64_t ldb);
+int32_t b200_gemv(b200_ctx* ctx, int32_t trans, int64_t m, int64_t n, const double* A, int64_t ld, const double* x, double* y);
+
+/* ---------------------------------------------------------------- sparse fallback (a6) */
+int32_t b200_pattern_nnz(b200_problem* prob, int64_t* nnz);
+int32_t b200_pattern(b200_problem* prob, int32_t index_base, int64_t* colptr_host, int64_t* rowval_host); /* CSC, sorted rows */
+int32_t b200_coloring_column(int64_t n, const int64_t* colptr_host, const int64_t* rowval_host, int32_t index_base,
+                             int32_t order, int64_t* colors_host /* 1-based */, int64_t* ncolors_host);
+int32_t b200_sparse_jac_create(b200_problem* prob, const int64_t* colptr_host, const int64_t* rowval_host, int32_t index_base,
+                               const int64_t* colors_host, int64_t ncolors, b200_sparse_jac** sj);
+int32_t b200_sparse_jac_destroy(b200_sparse_jac* sj);
+int32_t b200_sparse_jac_fill(b200_sparse_jac* sj, const double* u, double* nzval_dev); /* ncolors seeded JVP sweeps + scatter */
+int32_t b200_sparse_jac_linop(b200_sparse_jac* sj, const double* nzval_dev, b200_linop** op);
+int32_t b200_spmv(b200_sparse_jac* sj, const double* nzval_dev, const double* x, double* y);   /* y = J x  */
+int32_t b200_spmv_t(b200_sparse_jac* sj, const double* nzval_dev, const double* x, double* y); /* y = J' x */
+
+/* ---------------------------------------------------------------- Newton driver (a4, a7, a8, a9) */
+void b200_newton_opts_default(b200_newton_opts* opts);
+int32_t b200_newton_create(b200_problem* prob, const b200_newton_opts* opts, b200_newton** nw);
+int32_t b200_newton_destroy(b200_newton* nw);
+int32_t b200_newton_reinit(b200_newton* nw, const double* u0_dev);            /* reinit!(cache, u0) */
+int32_t b200_newton_step(b200_newton* nw, int32_t* terminated_host);           /* step!(cache) */
+int32_t b200_newton_solve(b200_newton* nw, b200_newton_result* result_host);   /* solve!(cache) */
+int32_t b200_newton_result_get(b200_newton* nw, b200_newton_result* result_host);
+int32_t b200_newton_u(b200_newton* nw, double** u_dev);
+int32_t b200_newton_fu(b200_newton* nw, double** fu_dev);
+int32_t b200_newton_trace(b200_newton* nw, b200_trace_rec* recs_host, int32_t cap, int32_t* count_host);
+/* whole-solve convenience with HOST buffers (H2D of u0, solve, D2H of u and resid): the e2e call */
+int32_t b200_newton_solve_host(b200_newton* nw, const double* u0_host, double* u_host, double* resid_host,
+                               b200_newton_result* result_host);
+
+/* ---------------------------------------------------------------- ensemble (a11): K independent 2D Brusselators */
+typedef struct b200_ens_result {
+  int32_t nprob;
+  int32_t nsuccess;
+  int32_t max_nsteps;
+  int32_t reserved;
+  int64_t total_nsteps;
+  int64_t total_njvp;
+  double worst_resid_inf;
+} b200_ens_result;
+int32_t b200_ens_create(b200_ctx* ctx, int32_t N, int32_t nprob_local, double alpha, const b200_newton_opts* opts, b200_ensemble** ens);
+int32_t b200_ens_destroy(b200_ensemble* ens);
+/* u0: nprob x n (problem-major, each problem a contiguous (N,N,2) block); A,B: per-problem parameters */
+int32_t b200_ens_solve(b200_ensemble* ens, const double* u0_dev, const double* A_dev, const double* B_dev, double* u_out_dev,
+                       double* resid_inf_dev, int32_t* retcodes_dev, int32_t* nsteps_dev, int32_t* njvp_dev,
+                       b200_ens_result* result_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200NEWTON_H */

@@ -1,0 +1,148 @@
+// common.cuh — internal declarations shared by the translation units of libb200newton.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include "../../include/b200newton.h"
+
+struct b200_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int sm_count = 148;
+  size_t smem_optin = 0;
+  size_t l2_bytes = 0;
+  std::string last_error;
+  int64_t launches = 0;
+  // reduction scratch: per-block partials + a few device scalars mirrored to pinned host memory
+  double* d_partials = nullptr;  // RED_MAX_BLOCKS * 4 doubles
+  double* d_scalars = nullptr;   // 64 doubles
+  double* h_scalars = nullptr;   // pinned, 64 doubles
+  void* l2_flush = nullptr;
+  size_t l2_flush_bytes = 0;
+  int32_t fail(int32_t code, const char* what, const char* file, int line);
+};
+
+#define B200_RED_MAX_BLOCKS 2048
+enum { RED_DOT = 0, RED_SUMSQ = 1, RED_MAXABS = 2, RED_DIFFSQ = 3, RED_MIN = 4, RED_MAX = 5, RED_NEQ = 6 };
+
+#define CUDA_TRY(ctx, expr)                                                             \
+  do {                                                                                  \
+    cudaError_t e__ = (expr);                                                           \
+    if (e__ != cudaSuccess) {                                                           \
+      char buf__[512];                                                                  \
+      snprintf(buf__, sizeof(buf__), "%s -> %s", #expr, cudaGetErrorString(e__));       \
+      return (ctx)->fail(B200_ERR_CUDA, buf__, __FILE__, __LINE__);                     \
+    }                                                                                   \
+  } while (0)
+
+#define B200_TRY(expr)                  \
+  do {                                  \
+    int32_t s__ = (expr);               \
+    if (s__ != B200_OK) return s__;     \
+  } while (0)
+
+#define B200_REQUIRE(ctx, cond, msg)                                                    \
+  do {                                                                                  \
+    if (!(cond)) return (ctx)->fail(B200_ERR_INVALID, msg, __FILE__, __LINE__);         \
+  } while (0)
+
+// Every kernel launch goes through this so that b200_ctx_kernel_launches() is an honest count.
+#define LAUNCH(ctx, kernel, grid, block, smem, ...)                                     \
+  do {                                                                                  \
+    kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                    \
+    (ctx)->launches++;                                                                  \
+  } while (0)
+
+#define CHECK_LAUNCH(ctx) CUDA_TRY(ctx, cudaPeekAtLastError())
+
+// ---------------------------------------------------------------- device helpers
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// block-wide sum; result valid in thread 0 (and warp 0). `red` must hold >= 32 doubles of shared memory.
+__device__ __forceinline__ double block_sum(double v, double* red) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  v = (threadIdx.x < nw) ? red[threadIdx.x] : 0.0;
+  if (wid == 0) v = warp_sum(v);
+  return v;
+}
+__device__ __forceinline__ double block_max(double v, double* red) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  v = (threadIdx.x < nw) ? red[threadIdx.x] : 0.0;
+  if (wid == 0) v = warp_max(v);
+  return v;
+}
+// |x| with non-finite values mapped to +inf so that a max-reduction propagates them (Julia's maximum(abs, x) yields NaN;
+// both are "non-finite" to the termination test at termination_conditions.jl:256).
+__device__ __forceinline__ double abs_nf(double x) {
+  double a = fabs(x);
+  return (a == a) ? a : __longlong_as_double(0x7ff0000000000000LL);
+}
+__device__ __forceinline__ void atomic_max_nonneg(double* addr, double v) {  // v >= 0 or +inf: bit patterns are ordered
+  atomicMax(reinterpret_cast<unsigned long long*>(addr), static_cast<unsigned long long>(__double_as_longlong(v)));
+}
+
+// ---------------------------------------------------------------- internal structs
+struct b200_problem {
+  b200_ctx* ctx;
+  int32_t kind;
+  int32_t N;
+  int64_t n;
+  double A, B, alpha, a;  // a = alpha / dx^2
+  double p;
+  const double* pvec;  // device
+  b200_residual_cb f_cb;
+  b200_jvp_cb jvp_cb, vjp_cb;
+  void* user;
+  double* fd_scratch;  // n doubles, lazily allocated (callback finite differences)
+};
+
+struct b200_sparse_jac;
+
+struct b200_linop {
+  b200_ctx* ctx;
+  int32_t kind;  // 0 problem-jvp, 1 csc, 2 dense, 3 callback, 4 sparse_jac
+  int64_t n;
+  b200_problem* prob;
+  const double* u;
+  int32_t jvp_mode;
+  const int64_t *colptr, *rowval;
+  const double* nzval;
+  int32_t index_base;
+  const double* A;
+  int64_t ld;
+  b200_matvec_cb mv;
+  void* user;
+  b200_sparse_jac* sj;
+};
+enum { LINOP_PROBLEM = 0, LINOP_CSC = 1, LINOP_DENSE = 2, LINOP_CALLBACK = 3, LINOP_SPARSE_JAC = 4 };
+
+// internal (non-ABI) helpers implemented across the .cu files
+int32_t b200i_linop_apply(b200_linop* op, const double* x, double* y);
+int32_t b200i_residual_norm(b200_problem* prob, const double* u, double* du, double* d_norminf /*device, pre-zeroed*/);
+int32_t b200i_axpy_norm(b200_ctx* ctx, int64_t n, double a, const double* x, double* y, double* d_sumsq /*device, pre-zeroed*/);
+int32_t b200i_reduce_sum_dev(b200_ctx* ctx, int64_t n, const double* x, const double* y, int mode, double* d_out);
+int32_t b200i_fetch_scalars(b200_ctx* ctx, int count);  // d_scalars[0..count) -> h_scalars, synchronises

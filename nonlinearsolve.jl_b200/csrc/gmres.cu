@@ -1,0 +1,783 @@
+// gmres.cu — device-resident GMRES (kernels K3/K4), multi-kernel engine.
+//
+// Replaces what the reference reaches through `solve!(cache.lincache)` at
+// lib/NonlinearSolveBase/ext/NonlinearSolveBaseLinearSolveExt.jl:26 (LinearSolve.KrylovJL_GMRES -> Krylov.gmres!):
+// Arnoldi + Gram-Schmidt + Givens reflections, stop at ||r|| <= atol + rtol ||r0||, no restart by default.
+//
+// B200 design: the Krylov basis, the Hessenberg/Givens recurrence, the residual estimate and the stopping decision
+// all live on the device.  An Arnoldi iteration is a fixed sequence of kernels with no host round trip
+// (operator apply -> multi-dot -> update+norm -> givens -> normalise); the host only polls a status word every
+// `check_every` iterations, and kernels enqueued after convergence early-exit on that word.
+//   multi-dot   h = V_k' w   : every CTA owns a contiguous row range, streams JT basis columns at a time with 16-byte
+//                              loads, warp-shuffle + shared-memory block reduction, per-CTA partials summed in fixed
+//                              order (deterministic, no atomics)
+//   update      w -= V_k h   : one pass over the basis with the ||w||^2 partial fused into the epilogue
+//   MGS (reference-parity mode): per basis vector one fused pass  w -= h_i v_i ; h_{i+1} = v_{i+1}.w
+// Orthogonalisation modes: MGS (Krylov.jl default), CGS, CGS2 (classical Gram-Schmidt with reorthogonalisation).
+#include "common.cuh"
+#include <math.h>
+#include <float.h>
+#include <algorithm>
+
+namespace {
+constexpr int GM_THREADS = 256;
+constexpr int JT = 8;  // basis columns streamed together by the multi-dot kernel
+
+struct GmresState {  // device-resident scalars
+  int32_t status;    // 0 = running, else B200_LS_*
+  int32_t k;         // Arnoldi iterations completed in the current cycle
+  int32_t iter_base; // iterations completed in previous restart cycles
+  int32_t itmax;
+  int32_t kmax_cycle;  // restart length (or INT_MAX)
+  int32_t pad;
+  double rnorm0, rnorm, tol, atol, rtol, inv_h, hbis;
+};
+
+__device__ __forceinline__ void sym_givens(double a, double b, double& c, double& s, double& rho) {
+  // Krylov.jl sym_givens (reflection form), restated in oracle/oracle.c the same way
+  if (b == 0.0) {
+    c = (a == 0.0) ? 1.0 : (a > 0 ? 1.0 : -1.0);
+    s = 0.0;
+    rho = fabs(a);
+  } else if (a == 0.0) {
+    c = 0.0;
+    s = (b > 0 ? 1.0 : -1.0);
+    rho = fabs(b);
+  } else if (fabs(b) > fabs(a)) {
+    const double t = a / b;
+    s = (b > 0 ? 1.0 : -1.0) / sqrt(1.0 + t * t);
+    c = s * t;
+    rho = b / s;
+  } else {
+    const double t = b / a;
+    c = (a > 0 ? 1.0 : -1.0) / sqrt(1.0 + t * t);
+    s = c * t;
+    rho = a / c;
+  }
+}
+
+__device__ __forceinline__ void block_rows(int64_t n, int64_t& r0, int64_t& r1) {
+  // contiguous, even-aligned row range of this CTA
+  int64_t chunk = (n + gridDim.x - 1) / gridDim.x;
+  chunk = (chunk + 1) & ~(int64_t)1;
+  r0 = (int64_t)blockIdx.x * chunk;
+  r1 = r0 + chunk;
+  if (r0 > n) r0 = n;
+  if (r1 > n) r1 = n;
+}
+
+// ---- h[c] partials: partial[c * G + blockIdx.x] = sum over this CTA's rows of V[c][r] * w[r]
+__global__ void __launch_bounds__(GM_THREADS) multidot_kernel(const GmresState* __restrict__ st, const double* const* __restrict__ V,
+                                                               int k, const double* __restrict__ w, int64_t n,
+                                                               double* __restrict__ partial) {
+  if (st->status != 0) return;
+  __shared__ double red[GM_THREADS / 32][JT];
+  int64_t r0, r1;
+  block_rows(n, r0, r1);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int G = gridDim.x;
+  for (int c0 = 0; c0 < k; c0 += JT) {
+    const double* vp[JT];
+#pragma unroll
+    for (int c = 0; c < JT; ++c) vp[c] = V[(c0 + c < k) ? (c0 + c) : c0];
+    double acc[JT];
+#pragma unroll
+    for (int c = 0; c < JT; ++c) acc[c] = 0.0;
+    for (int64_t r = r0 + 2 * threadIdx.x; r < r1; r += 2 * GM_THREADS) {
+      if (r + 1 < r1) {
+        const double2 w2 = *reinterpret_cast<const double2*>(w + r);
+        double2 v2[JT];
+#pragma unroll
+        for (int c = 0; c < JT; ++c) v2[c] = __ldcs(reinterpret_cast<const double2*>(vp[c] + r));  // streamed once: evict-first
+#pragma unroll
+        for (int c = 0; c < JT; ++c) acc[c] = fma(v2[c].x, w2.x, fma(v2[c].y, w2.y, acc[c]));
+      } else {
+        const double w1 = w[r];
+#pragma unroll
+        for (int c = 0; c < JT; ++c) acc[c] = fma(vp[c][r], w1, acc[c]);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < JT; ++c) acc[c] = warp_sum(acc[c]);
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+      for (int c = 0; c < JT; ++c) red[wid][c] = acc[c];
+    }
+    __syncthreads();
+    if (threadIdx.x < JT && c0 + threadIdx.x < k) {
+      double s = 0.0;
+#pragma unroll
+      for (int q = 0; q < GM_THREADS / 32; ++q) s += red[q][threadIdx.x];
+      partial[(int64_t)(c0 + threadIdx.x) * G + blockIdx.x] = s;
+    }
+  }
+}
+
+// ---- h[c] = sum_b partial[c*G + b] in fixed order (one warp per column).  accumulate: hacc[c] += h[c] (CGS2 second pass)
+__global__ void __launch_bounds__(GM_THREADS) reduce_h_kernel(const GmresState* __restrict__ st, int k, int G,
+                                                               const double* __restrict__ partial, double* __restrict__ h,
+                                                               double* __restrict__ hacc) {
+  if (st->status != 0) return;
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.x * (GM_THREADS / 32) + (threadIdx.x >> 5);
+  if (c >= k) return;
+  double s = 0.0;
+  for (int b = lane; b < G; b += 32) s += partial[(int64_t)c * G + b];
+  s = warp_sum(s);
+  if (lane == 0) {
+    h[c] = s;
+    if (hacc) hacc[c] += s;
+  }
+}
+
+// ---- w_out = w_in - sum_c coef[c] V[c]  (sign = -1)  or  w_in + sum_c coef[c] V[c] (sign = +1: x += V y);
+//      optional ||w_out||^2 partial per CTA
+__global__ void __launch_bounds__(GM_THREADS) update_kernel(const GmresState* __restrict__ st, int ignore_status,
+                                                             const double* const* __restrict__ V, int k,
+                                                             const double* __restrict__ coef, double sign,
+                                                             const double* w_in, double* w_out, int64_t n,
+                                                             double* __restrict__ norm_partial) {
+  if (!ignore_status && st->status != 0) return;
+  extern __shared__ double sh[];  // k coefficients + 32 reduction slots
+  double* hc = sh;
+  double* red = sh + k;
+  for (int c = threadIdx.x; c < k; c += GM_THREADS) hc[c] = sign * coef[c];
+  __syncthreads();
+  int64_t r0, r1;
+  block_rows(n, r0, r1);
+  double nacc = 0.0;
+  for (int64_t r = r0 + 2 * threadIdx.x; r < r1; r += 2 * GM_THREADS) {
+    if (r + 1 < r1) {
+      double2 w2 = *reinterpret_cast<const double2*>(w_in + r);
+      int c = 0;
+      for (; c + JT <= k; c += JT) {
+        double2 v2[JT];
+#pragma unroll
+        for (int q = 0; q < JT; ++q) v2[q] = __ldcs(reinterpret_cast<const double2*>(V[c + q] + r));
+#pragma unroll
+        for (int q = 0; q < JT; ++q) {
+          w2.x = fma(hc[c + q], v2[q].x, w2.x);
+          w2.y = fma(hc[c + q], v2[q].y, w2.y);
+        }
+      }
+      for (; c < k; ++c) {
+        const double2 v2 = __ldcs(reinterpret_cast<const double2*>(V[c] + r));
+        w2.x = fma(hc[c], v2.x, w2.x);
+        w2.y = fma(hc[c], v2.y, w2.y);
+      }
+      *reinterpret_cast<double2*>(w_out + r) = w2;
+      nacc = fma(w2.x, w2.x, fma(w2.y, w2.y, nacc));
+    } else {
+      double w1 = w_in[r];
+      for (int c = 0; c < k; ++c) w1 = fma(hc[c], V[c][r], w1);
+      w_out[r] = w1;
+      nacc = fma(w1, w1, nacc);
+    }
+  }
+  if (norm_partial) {
+    nacc = block_sum(nacc, red);
+    if (threadIdx.x == 0) norm_partial[blockIdx.x] = nacc;
+  }
+}
+
+// ---- MGS fused pass i:  h_i = sum(partial_in) ; w -= h_i V[i] ; partial_out = (next ? V[next].w : ||w||^2)
+//      i < 0: first pass, only the dot with V[0].
+__global__ void __launch_bounds__(GM_THREADS) mgs_pass_kernel(const GmresState* __restrict__ st, const double* __restrict__ vi,
+                                                               const double* __restrict__ vnext, int i,
+                                                               const double* __restrict__ partial_in, double* __restrict__ partial_out,
+                                                               double* __restrict__ h, double* __restrict__ w, int64_t n) {
+  if (st->status != 0) return;
+  __shared__ double red[32];
+  __shared__ double hs;
+  const int G = gridDim.x;
+  double hi = 0.0;
+  if (i >= 0) {
+    double s = 0.0;
+    for (int b = threadIdx.x; b < G; b += GM_THREADS) s += partial_in[b];
+    s = block_sum(s, red);  // identical in every CTA: fixed summation tree
+    if (threadIdx.x == 0) {
+      hs = s;
+      if (blockIdx.x == 0) h[i] = s;
+    }
+    __syncthreads();
+    hi = hs;
+  }
+  int64_t r0, r1;
+  block_rows(n, r0, r1);
+  double acc = 0.0;
+  for (int64_t r = r0 + 2 * threadIdx.x; r < r1; r += 2 * GM_THREADS) {
+    if (r + 1 < r1) {
+      double2 w2 = *reinterpret_cast<const double2*>(w + r);
+      if (i >= 0) {
+        const double2 v2 = __ldcs(reinterpret_cast<const double2*>(vi + r));
+        w2.x = fma(-hi, v2.x, w2.x);
+        w2.y = fma(-hi, v2.y, w2.y);
+        *reinterpret_cast<double2*>(w + r) = w2;
+      }
+      if (vnext) {
+        const double2 n2 = *reinterpret_cast<const double2*>(vnext + r);
+        acc = fma(n2.x, w2.x, fma(n2.y, w2.y, acc));
+      } else {
+        acc = fma(w2.x, w2.x, fma(w2.y, w2.y, acc));
+      }
+    } else {
+      double w1 = w[r];
+      if (i >= 0) {
+        w1 = fma(-hi, vi[r], w1);
+        w[r] = w1;
+      }
+      acc = vnext ? fma(vnext[r], w1, acc) : fma(w1, w1, acc);
+    }
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) partial_out[blockIdx.x] = acc;
+}
+
+// ---- start of a cycle: beta = sqrt(sum partial) ; tol (first cycle) ; z[0] = beta ; status
+__global__ void __launch_bounds__(GM_THREADS) init_finish_kernel(GmresState* __restrict__ st, int G, const double* __restrict__ norm_partial,
+                                                                  double* __restrict__ z, int first_cycle) {
+  __shared__ double red[32];
+  double s = 0.0;
+  for (int b = threadIdx.x; b < G; b += GM_THREADS) s += norm_partial[b];
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) {
+    const double beta = sqrt(s);
+    if (first_cycle) {
+      st->rnorm0 = beta;
+      st->tol = st->atol + st->rtol * beta;
+      st->iter_base = 0;
+    }
+    st->rnorm = beta;
+    st->k = 0;
+    z[0] = beta;
+    st->inv_h = (beta > 0.0) ? 1.0 / beta : 0.0;
+    if (!(beta == beta) || isinf(beta)) st->status = B200_LS_NONFINITE;
+    else if (beta <= st->tol) st->status = B200_LS_SOLVED;
+    else if (st->iter_base >= st->itmax) st->status = B200_LS_MAXITERS;
+    else st->status = 0;
+  }
+}
+
+// ---- end of Arnoldi step k (1-based): Hbis = sqrt(sum norm partials); apply the previous reflections to column k,
+//      form the new one, update z / residual estimate / status.  R is packed upper triangular: column k at (k-1)k/2.
+__global__ void __launch_bounds__(GM_THREADS) givens_kernel(GmresState* __restrict__ st, int k, int G, const double* __restrict__ norm_partial,
+                                                             const double* __restrict__ h, double* __restrict__ R, double* __restrict__ cs,
+                                                             double* __restrict__ sn, double* __restrict__ z, double* __restrict__ hraw) {
+  if (st->status != 0) return;
+  __shared__ double red[32];
+  double s = 0.0;
+  for (int b = threadIdx.x; b < G; b += GM_THREADS) s += norm_partial[b];
+  s = block_sum(s, red);
+  double* Rk = R + (int64_t)(k - 1) * k / 2;
+  for (int i = threadIdx.x; i < k; i += GM_THREADS) Rk[i] = h[i];
+  if (hraw) {  // raw Hessenberg column for parity tests: k+1 entries at offset (k-1)(k+2)/2
+    double* hr = hraw + (int64_t)(k - 1) * (k + 2) / 2;
+    for (int i = threadIdx.x; i < k; i += GM_THREADS) hr[i] = h[i];
+    if (threadIdx.x == 0) hr[k] = sqrt(s);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const double hbis = sqrt(s);
+    for (int i = 0; i + 1 < k; ++i) {
+      const double rt = cs[i] * Rk[i] + sn[i] * Rk[i + 1];
+      Rk[i + 1] = sn[i] * Rk[i] - cs[i] * Rk[i + 1];
+      Rk[i] = rt;
+    }
+    double c, s_, rho;
+    sym_givens(Rk[k - 1], hbis, c, s_, rho);
+    cs[k - 1] = c;
+    sn[k - 1] = s_;
+    Rk[k - 1] = rho;
+    const double zeta = s_ * z[k - 1];
+    z[k - 1] = c * z[k - 1];
+    z[k] = zeta;
+    const double rnorm = fabs(zeta);
+    st->rnorm = rnorm;
+    st->hbis = hbis;
+    st->k = k;
+    st->inv_h = (hbis > 0.0) ? 1.0 / hbis : 0.0;
+    const double btol = 1.8189894035458565e-12;  // eps(Float64)^(3/4), Krylov.jl breakdown tolerance
+    int status = 0;
+    if (!(rnorm == rnorm) || isinf(rnorm) || !(hbis == hbis) || isinf(hbis)) status = B200_LS_NONFINITE;
+    else if (rnorm <= st->tol) status = B200_LS_SOLVED;
+    else if (st->iter_base + k >= st->itmax) status = B200_LS_MAXITERS;
+    else if (hbis <= btol) status = B200_LS_BREAKDOWN;
+    else if (k >= st->kmax_cycle) status = -1;  // cycle full: restart (host resets)
+    st->status = status;
+  }
+}
+
+// ---- V[k] = w * inv_h
+__global__ void __launch_bounds__(GM_THREADS) normalize_kernel(const GmresState* __restrict__ st, int require_running,
+                                                                const double* __restrict__ w, double* __restrict__ v, int64_t n) {
+  if (require_running && st->status != 0) return;
+  const double s = st->inv_h;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * 2;
+  for (int64_t r = 2 * ((int64_t)blockIdx.x * blockDim.x + threadIdx.x); r < n; r += stride) {
+    if (r + 1 < n) {
+      double2 w2 = *reinterpret_cast<const double2*>(w + r);
+      w2.x *= s;
+      w2.y *= s;
+      *reinterpret_cast<double2*>(v + r) = w2;
+    } else {
+      v[r] = w[r] * s;
+    }
+  }
+}
+
+// ---- y = R^{-1} z for the first k columns (single CTA, column-oriented back substitution)
+__global__ void __launch_bounds__(GM_THREADS) backsolve_kernel(const GmresState* __restrict__ st, const double* __restrict__ R,
+                                                                const double* __restrict__ z, double* __restrict__ y, int kcap) {
+  const int k = st->k;
+  extern __shared__ double zs[];
+  for (int i = threadIdx.x; i < k; i += GM_THREADS) zs[i] = z[i];
+  __syncthreads();
+  for (int i = k - 1; i >= 0; --i) {
+    const double* Ri = R + (int64_t)i * (i + 1) / 2;
+    const double d = Ri[i];
+    const double yi = (d == 0.0) ? 0.0 : zs[i] / d;
+    __syncthreads();
+    if (threadIdx.x == 0) zs[i] = yi;
+    for (int j = threadIdx.x; j < i; j += GM_THREADS) zs[j] -= Ri[j] * yi;
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < kcap; i += GM_THREADS) y[i] = (i < k) ? zs[i] : 0.0;
+}
+
+__global__ void __launch_bounds__(GM_THREADS) residual_init_kernel(int64_t n, const double* __restrict__ b, const double* __restrict__ Ax,
+                                                                    double* __restrict__ r, double* __restrict__ norm_partial) {
+  __shared__ double red[32];
+  double acc = 0.0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const double v = Ax ? b[i] - Ax[i] : b[i];
+    r[i] = v;
+    acc = fma(v, v, acc);
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) norm_partial[blockIdx.x] = acc;
+}
+
+// ---- generic operator kernels (b2/b3 plug-in points): CSC scatter SpMV and dense column-major GEMV
+__global__ void __launch_bounds__(GM_THREADS) csc_spmv_kernel(int64_t n, const int64_t* __restrict__ colptr, const int64_t* __restrict__ rowval,
+                                                               const double* __restrict__ nzval, int base, const double* __restrict__ x,
+                                                               double* __restrict__ y) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  const double xc = x[c];
+  for (int64_t p = colptr[c] - base; p < colptr[c + 1] - base; ++p) atomicAdd(&y[rowval[p] - base], nzval[p] * xc);
+}
+__global__ void __launch_bounds__(GM_THREADS) dense_gemv_kernel(int trans, int64_t m, int64_t n, const double* __restrict__ A, int64_t ld,
+                                                                 const double* __restrict__ x, double* __restrict__ y) {
+  __shared__ double red[32];
+  if (!trans) {  // y = A x: thread per row, coalesced down the column
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    double s = 0.0;
+    for (int64_t c = 0; c < n; ++c) s = fma(A[c * ld + i], x[c], s);
+    y[i] = s;
+  } else {  // y = A' x: CTA per column
+    for (int64_t c = blockIdx.x; c < n; c += gridDim.x) {
+      double s = 0.0;
+      for (int64_t i = threadIdx.x; i < m; i += blockDim.x) s = fma(A[c * ld + i], x[i], s);
+      s = block_sum(s, red);
+      if (threadIdx.x == 0) y[c] = s;
+      __syncthreads();
+    }
+  }
+}
+}  // namespace
+
+struct b200_gmres {
+  b200_ctx* ctx;
+  int64_t n;
+  b200_gmres_opts opts;
+  int G;               // CTAs of the streaming kernels
+  int kcap;            // capacity (columns) of R / cs / sn / z / h / y / partial
+  std::vector<double*> V;      // basis vectors (views into slabs)
+  std::vector<double*> slabs;  // owning allocations
+  double** d_Vptrs;
+  int vptr_cap;
+  double *w, *r0, *d_h, *d_hacc, *d_R, *d_cs, *d_sn, *d_z, *d_y, *d_partial, *d_norm_partial, *d_norm_partial2;
+  double* d_hraw;
+  int64_t hraw_cap;
+  GmresState* d_state;
+  GmresState* h_state;  // pinned
+};
+
+namespace {
+int32_t gm_free_arrays(b200_gmres* gm) {
+  cudaFree(gm->d_h); cudaFree(gm->d_hacc); cudaFree(gm->d_R); cudaFree(gm->d_cs); cudaFree(gm->d_sn);
+  cudaFree(gm->d_z); cudaFree(gm->d_y); cudaFree(gm->d_partial);
+  gm->d_h = gm->d_hacc = gm->d_R = gm->d_cs = gm->d_sn = gm->d_z = gm->d_y = gm->d_partial = nullptr;
+  return B200_OK;
+}
+
+// grow the small Krylov arrays to hold `need` columns (contents preserved)
+int32_t gm_reserve(b200_gmres* gm, int need) {
+  b200_ctx* ctx = gm->ctx;
+  if (need <= gm->kcap) return B200_OK;
+  int ncap = std::max(need, gm->kcap > 0 ? gm->kcap * 2 : 64);
+  const int64_t rsz = (int64_t)ncap * (ncap + 1) / 2;
+  double *nh, *nha, *nR, *ncs, *nsn, *nz, *ny, *npart;
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (cudaMalloc(&nh, sizeof(double) * (ncap + 2)) != cudaSuccess || cudaMalloc(&nha, sizeof(double) * (ncap + 2)) != cudaSuccess ||
+      cudaMalloc(&nR, sizeof(double) * rsz) != cudaSuccess || cudaMalloc(&ncs, sizeof(double) * (ncap + 2)) != cudaSuccess ||
+      cudaMalloc(&nsn, sizeof(double) * (ncap + 2)) != cudaSuccess || cudaMalloc(&nz, sizeof(double) * (ncap + 2)) != cudaSuccess ||
+      cudaMalloc(&ny, sizeof(double) * (ncap + 2)) != cudaSuccess ||
+      cudaMalloc(&npart, sizeof(double) * (int64_t)ncap * gm->G) != cudaSuccess) {
+    cudaGetLastError();
+    return ctx->fail(B200_ERR_NOMEM, "out of device memory growing the Krylov workspace", __FILE__, __LINE__);
+  }
+  if (gm->kcap > 0) {
+    const int oc = gm->kcap;
+    CUDA_TRY(ctx, cudaMemcpy(nR, gm->d_R, sizeof(double) * (int64_t)oc * (oc + 1) / 2, cudaMemcpyDeviceToDevice));
+    CUDA_TRY(ctx, cudaMemcpy(ncs, gm->d_cs, sizeof(double) * (oc + 2), cudaMemcpyDeviceToDevice));
+    CUDA_TRY(ctx, cudaMemcpy(nsn, gm->d_sn, sizeof(double) * (oc + 2), cudaMemcpyDeviceToDevice));
+    CUDA_TRY(ctx, cudaMemcpy(nz, gm->d_z, sizeof(double) * (oc + 2), cudaMemcpyDeviceToDevice));
+    gm_free_arrays(gm);
+  }
+  gm->d_h = nh; gm->d_hacc = nha; gm->d_R = nR; gm->d_cs = ncs; gm->d_sn = nsn; gm->d_z = nz; gm->d_y = ny; gm->d_partial = npart;
+  gm->kcap = ncap;
+  return B200_OK;
+}
+
+// make sure basis vectors 0..idx exist and the device pointer table covers them.  Vectors come in slabs of
+// VSLAB so that growing the basis (Krylov.jl pushes new vectors past `memory` when restart = false) costs one
+// allocation + one pointer-table upload per slab instead of per Arnoldi step.
+constexpr int VSLAB = 16;
+int32_t gm_ensure_vector(b200_gmres* gm, int idx) {
+  b200_ctx* ctx = gm->ctx;
+  bool table_dirty = false;
+  const int64_t npad = (gm->n + 1) & ~(int64_t)1;
+  while ((int)gm->V.size() <= idx) {
+    double* slab = nullptr;
+    int cnt = VSLAB;
+    if ((int64_t)cnt * npad * 8 > ((int64_t)1 << 31)) cnt = (int)std::max<int64_t>(1, ((int64_t)1 << 31) / (npad * 8));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (cudaMalloc(&slab, sizeof(double) * npad * cnt) != cudaSuccess) {
+      cudaGetLastError();
+      cnt = 1;
+      if (cudaMalloc(&slab, sizeof(double) * npad) != cudaSuccess) {
+        cudaGetLastError();
+        return B200_ERR_NOMEM;  // caller turns this into B200_LS_OUT_OF_MEMORY
+      }
+    }
+    gm->slabs.push_back(slab);
+    for (int q = 0; q < cnt; ++q) gm->V.push_back(slab + (int64_t)q * npad);
+    table_dirty = true;
+  }
+  if ((int)gm->V.size() > gm->vptr_cap) {
+    int ncap = std::max((int)gm->V.size() * 2, 64);
+    double** nt = nullptr;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, cudaMalloc(&nt, sizeof(double*) * ncap));
+    if (gm->d_Vptrs) cudaFree(gm->d_Vptrs);
+    gm->d_Vptrs = nt;
+    gm->vptr_cap = ncap;
+    table_dirty = true;
+  }
+  if (table_dirty) {
+    CUDA_TRY(ctx, cudaMemcpyAsync(gm->d_Vptrs, gm->V.data(), sizeof(double*) * gm->V.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return B200_OK;
+}
+
+int32_t gm_fetch_state(b200_gmres* gm) {
+  b200_ctx* ctx = gm->ctx;
+  CUDA_TRY(ctx, cudaMemcpyAsync(gm->h_state, gm->d_state, sizeof(GmresState), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return B200_OK;
+}
+}  // namespace
+
+// ------------------------------------------------------------------ operator application (K2/K3)
+int32_t b200i_linop_apply(b200_linop* op, const double* x, double* y) {
+  b200_ctx* ctx = op->ctx;
+  switch (op->kind) {
+    case LINOP_PROBLEM:
+      return op->jvp_mode == B200_JVP_FINITE_DIFF ? b200_jvp_fd(op->prob, op->u, x, y) : b200_jvp(op->prob, op->u, x, y);
+    case LINOP_CSC: {
+      CUDA_TRY(ctx, cudaMemsetAsync(y, 0, sizeof(double) * op->n, ctx->stream));
+      LAUNCH(ctx, csc_spmv_kernel, (int)((op->n + GM_THREADS - 1) / GM_THREADS), GM_THREADS, 0, op->n, op->colptr, op->rowval, op->nzval,
+             op->index_base, x, y);
+      CHECK_LAUNCH(ctx);
+      return B200_OK;
+    }
+    case LINOP_DENSE:
+      return b200_gemv(ctx, 0, op->n, op->n, op->A, op->ld, x, y);
+    case LINOP_CALLBACK:
+      return op->mv(op->user, x, y) == 0 ? B200_OK : ctx->fail(B200_ERR_CALLBACK, "matvec callback failed", __FILE__, __LINE__);
+    case LINOP_SPARSE_JAC:
+      return b200_spmv(op->sj, op->nzval, x, y);
+  }
+  return ctx->fail(B200_ERR_INVALID, "unknown linop kind", __FILE__, __LINE__);
+}
+
+extern "C" {
+int32_t b200_gemv(b200_ctx* ctx, int32_t trans, int64_t m, int64_t n, const double* A, int64_t ld, const double* x, double* y) {
+  if (!trans) {
+    LAUNCH(ctx, dense_gemv_kernel, (int)((m + GM_THREADS - 1) / GM_THREADS), GM_THREADS, 0, 0, m, n, A, ld, x, y);
+  } else {
+    LAUNCH(ctx, dense_gemv_kernel, (int)std::min<int64_t>(n, 4096), GM_THREADS, 0, 1, m, n, A, ld, x, y);
+  }
+  CHECK_LAUNCH(ctx);
+  return B200_OK;
+}
+
+int32_t b200_linop_from_problem(b200_problem* prob, const double* u, int32_t jvp_mode, b200_linop** out) {
+  b200_linop* op = new b200_linop();
+  memset(op, 0, sizeof(*op));
+  op->ctx = prob->ctx; op->kind = LINOP_PROBLEM; op->n = prob->n; op->prob = prob; op->u = u; op->jvp_mode = jvp_mode;
+  *out = op;
+  return B200_OK;
+}
+int32_t b200_linop_from_csc(b200_ctx* ctx, int64_t n, const int64_t* colptr, const int64_t* rowval, const double* nzval, int32_t base,
+                            b200_linop** out) {
+  b200_linop* op = new b200_linop();
+  memset(op, 0, sizeof(*op));
+  op->ctx = ctx; op->kind = LINOP_CSC; op->n = n; op->colptr = colptr; op->rowval = rowval; op->nzval = nzval; op->index_base = base;
+  *out = op;
+  return B200_OK;
+}
+int32_t b200_linop_from_dense(b200_ctx* ctx, int64_t n, const double* A, int64_t ld, b200_linop** out) {
+  b200_linop* op = new b200_linop();
+  memset(op, 0, sizeof(*op));
+  op->ctx = ctx; op->kind = LINOP_DENSE; op->n = n; op->A = A; op->ld = ld;
+  *out = op;
+  return B200_OK;
+}
+int32_t b200_linop_from_callback(b200_ctx* ctx, int64_t n, b200_matvec_cb mv, void* user, b200_linop** out) {
+  b200_linop* op = new b200_linop();
+  memset(op, 0, sizeof(*op));
+  op->ctx = ctx; op->kind = LINOP_CALLBACK; op->n = n; op->mv = mv; op->user = user;
+  *out = op;
+  return B200_OK;
+}
+int32_t b200_linop_apply(b200_linop* op, const double* x, double* y) { return b200i_linop_apply(op, x, y); }
+int32_t b200_linop_destroy(b200_linop* op) { delete op; return B200_OK; }
+
+void b200_gmres_opts_default(b200_gmres_opts* o) {
+  memset(o, 0, sizeof(*o));
+  o->memory = 20;        // Krylov.jl default `memory`; LinearSolve passes min(20, n)
+  o->restart = 0;        // KrylovJL_GMRES(gmres_restart = 0): no restart
+  o->itmax = 0;          // => n
+  o->orth = B200_ORTH_CGS2;
+  o->warm_start = 0;
+  o->engine = B200_ENGINE_AUTO;
+  o->check_every = 8;
+  o->atol = 0.0;
+  o->rtol = 1.4901161193847656e-08;  // sqrt(eps): Krylov.jl default rtol
+}
+
+int32_t b200_gmres_create(b200_ctx* ctx, int64_t n, const b200_gmres_opts* opts, b200_gmres** out) {
+  B200_REQUIRE(ctx, n > 0 && opts && out, "gmres_create: bad arguments");
+  b200_gmres* gm = new b200_gmres();
+  gm->ctx = ctx; gm->n = n; gm->opts = *opts;
+  gm->kcap = 0; gm->d_Vptrs = nullptr; gm->vptr_cap = 0;
+  gm->d_h = gm->d_hacc = gm->d_R = gm->d_cs = gm->d_sn = gm->d_z = gm->d_y = gm->d_partial = nullptr;
+  gm->d_hraw = nullptr; gm->hraw_cap = 0;
+  // streaming grid: 4 CTAs of 256 threads per SM, fewer for small n (at least 512 rows per CTA)
+  int64_t g = std::min<int64_t>((int64_t)ctx->sm_count * 4, std::max<int64_t>(1, n / 512));
+  gm->G = (int)g;
+  const int64_t npad = (n + 1) & ~(int64_t)1;
+  CUDA_TRY(ctx, cudaMalloc(&gm->w, sizeof(double) * npad));
+  CUDA_TRY(ctx, cudaMalloc(&gm->r0, sizeof(double) * npad));
+  CUDA_TRY(ctx, cudaMalloc(&gm->d_norm_partial, sizeof(double) * std::max(gm->G, B200_RED_MAX_BLOCKS)));
+  CUDA_TRY(ctx, cudaMalloc(&gm->d_norm_partial2, sizeof(double) * std::max(gm->G, B200_RED_MAX_BLOCKS)));
+  CUDA_TRY(ctx, cudaMalloc(&gm->d_state, sizeof(GmresState)));
+  CUDA_TRY(ctx, cudaMallocHost(&gm->h_state, sizeof(GmresState)));
+  int mem = opts->restart > 0 ? opts->restart : (opts->memory > 0 ? opts->memory : 20);
+  if (mem > n) mem = (int)n;
+  int32_t s = gm_reserve(gm, std::max(mem + 1, 32));
+  if (s != B200_OK) { b200_gmres_destroy(gm); return s; }
+  *out = gm;
+  return B200_OK;
+}
+
+int32_t b200_gmres_destroy(b200_gmres* gm) {
+  if (!gm) return B200_OK;
+  cudaStreamSynchronize(gm->ctx->stream);
+  for (double* v : gm->slabs) cudaFree(v);
+  if (gm->d_Vptrs) cudaFree(gm->d_Vptrs);
+  cudaFree(gm->w); cudaFree(gm->r0); cudaFree(gm->d_norm_partial); cudaFree(gm->d_norm_partial2); cudaFree(gm->d_state);
+  if (gm->d_hraw) cudaFree(gm->d_hraw);
+  cudaFreeHost(gm->h_state);
+  gm_free_arrays(gm);
+  delete gm;
+  return B200_OK;
+}
+
+int32_t b200_gmres_set_tolerances(b200_gmres* gm, double atol, double rtol) {
+  if (atol >= 0) gm->opts.atol = atol;
+  if (rtol >= 0) gm->opts.rtol = rtol;
+  return B200_OK;
+}
+
+// test hook: keep the raw Hessenberg columns of the next solve (k+1 entries per column)
+int32_t b200_gmres_keep_hessenberg(b200_gmres* gm, int64_t capacity) {
+  b200_ctx* ctx = gm->ctx;
+  if (gm->d_hraw) { cudaFree(gm->d_hraw); gm->d_hraw = nullptr; }
+  gm->hraw_cap = capacity;
+  if (capacity > 0) CUDA_TRY(ctx, cudaMalloc(&gm->d_hraw, sizeof(double) * capacity));
+  return B200_OK;
+}
+int32_t b200_gmres_get_hessenberg(b200_gmres* gm, double* out_host, int64_t count) {
+  b200_ctx* ctx = gm->ctx;
+  if (!gm->d_hraw || count > gm->hraw_cap) return ctx->fail(B200_ERR_INVALID, "hessenberg capture not enabled / too small", __FILE__, __LINE__);
+  return b200_memcpy_d2h(ctx, out_host, gm->d_hraw, sizeof(double) * count);
+}
+
+int32_t b200_gmres_solve(b200_gmres* gm, b200_linop* op, const double* b, double* x, b200_gmres_stats* stats) {
+  b200_ctx* ctx = gm->ctx;
+  B200_REQUIRE(ctx, op && op->n == gm->n && b && x, "gmres_solve: bad arguments");
+  B200_REQUIRE(ctx, (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(b) & 7) == 0,
+               "gmres_solve: x must be 16-byte aligned (vectorised loads)");
+  const int64_t n = gm->n;
+  const b200_gmres_opts& o = gm->opts;
+  const int G = gm->G;
+  const int orth = o.orth;
+  const int check_every = o.check_every > 0 ? o.check_every : 8;
+  const int64_t itmax = o.itmax > 0 ? o.itmax : n;
+  const int restart_len = o.restart > 0 ? (int)std::min<int64_t>(o.restart, n) : 0;
+  const int ew_grid = (int)std::min<int64_t>((n + GM_THREADS * 2 - 1) / (GM_THREADS * 2), (int64_t)ctx->sm_count * 8);
+  b200_gmres_stats st_local;
+  memset(&st_local, 0, sizeof(st_local));
+  double bytes = 0.0;
+  const double Bv = 8.0 * (double)n;
+
+  // ---- initial state
+  GmresState init;
+  memset(&init, 0, sizeof(init));
+  init.itmax = (int32_t)std::min<int64_t>(itmax, INT32_MAX);
+  init.kmax_cycle = restart_len > 0 ? restart_len : INT32_MAX;
+  init.atol = o.atol;
+  init.rtol = o.rtol;
+  *gm->h_state = init;
+  CUDA_TRY(ctx, cudaMemcpyAsync(gm->d_state, gm->h_state, sizeof(GmresState), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // h_state is reused as the read-back buffer below
+
+  int32_t rc = gm_ensure_vector(gm, 1);
+  if (rc == B200_ERR_NOMEM) return ctx->fail(B200_ERR_NOMEM, "cannot allocate the first Krylov vectors", __FILE__, __LINE__);
+  B200_TRY(rc);
+
+  int nmatvec = 0, restarts = 0;
+  int64_t iters_total = 0;
+  bool first_cycle = true;
+  bool have_x = o.warm_start != 0;
+  if (!have_x) CUDA_TRY(ctx, cudaMemsetAsync(x, 0, sizeof(double) * n, ctx->stream));
+  int final_status = 0;
+  int oom = 0;
+
+  for (;;) {
+    // r0 = b - A x (or b), beta, V[0] = r0 / beta
+    const double* Ax = nullptr;
+    if (have_x) {
+      B200_TRY(b200i_linop_apply(op, x, gm->w));
+      ++nmatvec;
+      Ax = gm->w;
+      bytes += 3 * Bv;
+    }
+    LAUNCH(ctx, residual_init_kernel, std::min(G, B200_RED_MAX_BLOCKS), GM_THREADS, 0, n, b, Ax, gm->r0, gm->d_norm_partial);
+    LAUNCH(ctx, init_finish_kernel, 1, GM_THREADS, 0, gm->d_state, std::min(G, B200_RED_MAX_BLOCKS), gm->d_norm_partial, gm->d_z,
+           first_cycle ? 1 : 0);
+    LAUNCH(ctx, normalize_kernel, ew_grid, GM_THREADS, 0, gm->d_state, 0, gm->r0, gm->V[0], n);
+    CHECK_LAUNCH(ctx);
+    bytes += (Ax ? 3 : 2) * Bv + 2 * Bv;
+    first_cycle = false;
+
+    int k = 0;
+    int cycle_status = 0;
+    for (;;) {
+      ++k;
+      B200_TRY(gm_reserve(gm, k + 1));
+      rc = gm_ensure_vector(gm, k);
+      if (rc == B200_ERR_NOMEM || k + 40 > 6000) { oom = 1; --k; break; }  // 48 KB of coefficients in shared memory
+      B200_TRY(rc);
+      // w = A v_k
+      B200_TRY(b200i_linop_apply(op, gm->V[k - 1], gm->w));
+      if (orth == B200_ORTH_MGS) {
+        double* pin = gm->d_norm_partial;
+        double* pout = gm->d_norm_partial2;
+        LAUNCH(ctx, mgs_pass_kernel, G, GM_THREADS, 0, gm->d_state, (const double*)nullptr, (const double*)gm->V[0], -1, pin, pout, gm->d_h,
+               gm->w, n);
+        for (int i = 0; i < k; ++i) {
+          std::swap(pin, pout);
+          LAUNCH(ctx, mgs_pass_kernel, G, GM_THREADS, 0, gm->d_state, (const double*)gm->V[i],
+                 (const double*)(i + 1 < k ? gm->V[i + 1] : nullptr), i, pin, pout, gm->d_h, gm->w, n);
+        }
+        LAUNCH(ctx, givens_kernel, 1, GM_THREADS, 0, gm->d_state, k, G, pout, gm->d_h, gm->d_R, gm->d_cs, gm->d_sn, gm->d_z,
+               (gm->d_hraw && (int64_t)k * (k + 3) / 2 <= gm->hraw_cap) ? gm->d_hraw : nullptr);
+      } else {
+        const size_t shm = sizeof(double) * (k + 32);
+        LAUNCH(ctx, multidot_kernel, G, GM_THREADS, 0, gm->d_state, (const double* const*)gm->d_Vptrs, k, gm->w, n, gm->d_partial);
+        LAUNCH(ctx, reduce_h_kernel, (k + 7) / 8, GM_THREADS, 0, gm->d_state, k, G, gm->d_partial, gm->d_h, (double*)nullptr);
+        LAUNCH(ctx, update_kernel, G, GM_THREADS, shm, gm->d_state, 0, (const double* const*)gm->d_Vptrs, k, gm->d_h, -1.0, gm->w, gm->w, n,
+               gm->d_norm_partial);
+        if (orth == B200_ORTH_CGS2) {
+          LAUNCH(ctx, multidot_kernel, G, GM_THREADS, 0, gm->d_state, (const double* const*)gm->d_Vptrs, k, gm->w, n, gm->d_partial);
+          LAUNCH(ctx, reduce_h_kernel, (k + 7) / 8, GM_THREADS, 0, gm->d_state, k, G, gm->d_partial, gm->d_hacc, gm->d_h);
+          LAUNCH(ctx, update_kernel, G, GM_THREADS, shm, gm->d_state, 0, (const double* const*)gm->d_Vptrs, k, gm->d_hacc, -1.0, gm->w,
+                 gm->w, n, gm->d_norm_partial);
+        }
+        LAUNCH(ctx, givens_kernel, 1, GM_THREADS, 0, gm->d_state, k, G, gm->d_norm_partial, gm->d_h, gm->d_R, gm->d_cs, gm->d_sn, gm->d_z,
+               (gm->d_hraw && (int64_t)k * (k + 3) / 2 <= gm->hraw_cap) ? gm->d_hraw : nullptr);
+      }
+      LAUNCH(ctx, normalize_kernel, ew_grid, GM_THREADS, 0, gm->d_state, 1, gm->w, gm->V[k], n);
+      CHECK_LAUNCH(ctx);
+      const bool must_check = (k % check_every == 0) || (iters_total + k >= itmax) || (restart_len > 0 && k >= restart_len);
+      if (must_check) {
+        B200_TRY(gm_fetch_state(gm));
+        if (gm->h_state->status != 0) { cycle_status = gm->h_state->status; k = gm->h_state->k; break; }
+      }
+    }
+    if (oom) {
+      B200_TRY(gm_fetch_state(gm));
+      if (gm->h_state->status != 0) { cycle_status = gm->h_state->status; k = gm->h_state->k; oom = 0; }
+      else { cycle_status = B200_LS_OUT_OF_MEMORY; }
+    }
+    nmatvec += k;
+    iters_total += k;
+    // algorithmic bytes of this cycle: per Arnoldi step j: operator 3 Bv, normalise 2 Bv and
+    //   CGS (2j+2) Bv | CGS2 (4j+4) Bv | MGS (3j+1) Bv (dot pass reads v_{i+1}, update pass reads v_i, w read+written)
+    for (int j = 1; j <= k; ++j) {
+      double orthb = (orth == B200_ORTH_CGS) ? (2.0 * j + 2.0) : (orth == B200_ORTH_CGS2) ? (4.0 * j + 4.0) : (3.0 * j + 1.0);
+      bytes += (3.0 + 2.0 + orthb) * Bv;
+    }
+    // x += V_k y
+    if (k > 0 && cycle_status != B200_LS_NONFINITE) {
+      LAUNCH(ctx, backsolve_kernel, 1, GM_THREADS, sizeof(double) * (k + 1), gm->d_state, gm->d_R, gm->d_z, gm->d_y, gm->kcap);
+      LAUNCH(ctx, update_kernel, G, GM_THREADS, sizeof(double) * (k + 32), gm->d_state, 1, (const double* const*)gm->d_Vptrs, k, gm->d_y, 1.0,
+             x, x, n, (double*)nullptr);
+      CHECK_LAUNCH(ctx);
+      bytes += (k + 2.0) * Bv;
+      have_x = true;
+    }
+    if (cycle_status == -1) {  // restart: next cycle starts from the current x
+      ++restarts;
+      GmresState* hs = gm->h_state;
+      hs->iter_base = (int32_t)iters_total;
+      hs->status = 0;
+      hs->k = 0;
+      CUDA_TRY(ctx, cudaMemcpyAsync(gm->d_state, hs, sizeof(GmresState), cudaMemcpyHostToDevice, ctx->stream));
+      CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+      continue;
+    }
+    final_status = cycle_status;
+    break;
+  }
+  B200_TRY(gm_fetch_state(gm));
+  st_local.status = final_status;
+  st_local.iters = (int32_t)iters_total;
+  st_local.nmatvec = nmatvec;
+  st_local.restarts = restarts;
+  st_local.rnorm0 = gm->h_state->rnorm0;
+  st_local.rnorm = gm->h_state->rnorm;
+  st_local.tol = gm->h_state->tol;
+  st_local.bytes = bytes;
+  if (stats) *stats = st_local;
+  return B200_OK;
+}
+}  // extern "C"

@@ -1,0 +1,475 @@
+// newton.cu — the first-order nonlinear driver on the device (kernels K5/K6).
+//
+// Mirrors GeneralizedFirstOrderAlgorithm: __init (lib/NonlinearSolveFirstOrder/src/solve.jl:140-301), step! (:325-465),
+// the driver loop (lib/NonlinearSolveBase/src/solve.jl:360-387, 835-858), NewtonDescent (descent/newton.jl:97-141),
+// Dogleg (descent/dogleg.jl:86-151), GenericTrustRegionScheme / RadiusUpdateSchemes.Simple (trust_region.jl:204-258,
+// 320-384, 396-430, 511-513), EisenstatWalkerForcing2 (eisenstat_walker.jl:42-87) and the default termination mode
+// AbsNormSafeBestTerminationMode (termination_conditions.jl:134-179, 243-336, 376-393, 414-453).
+//
+// All n-vectors stay in HBM for the whole solve; per step the host reads back one small record of scalars
+// (||f||_inf, ||du||_2^2) produced by the epilogues of the update / residual kernels, and takes the (scalar) control
+// decisions of the reference on the host.
+#include "common.cuh"
+#include <math.h>
+#include <algorithm>
+
+extern "C" int32_t b200_gmres_keep_hessenberg(b200_gmres* gm, int64_t capacity);
+
+namespace {
+struct TermCache {  // NonlinearTerminationModeCache (termination_conditions.jl:60-98)
+  int mode;
+  double abstol, best, initial;
+  int nsteps;
+  int retcode;
+  double obj_trace[100];
+  double step_trace[32];
+};
+}  // namespace
+
+struct b200_newton {
+  b200_ctx* ctx;
+  b200_problem* prob;
+  b200_newton_opts o;
+  int64_t n;
+  double abstol, reltol;
+  int maxiters;
+  double *u, *fu, *u_cache, *du, *xlin, *best_u;
+  double *u_trial, *fu_trial, *Jdu, *JTfu, *du_c, *c1, *c2;
+  b200_gmres* gm;
+  b200_linop op;
+  // dense
+  double* Jdense;
+  int64_t* ipiv;
+  // sparse
+  b200_sparse_jac* sj;
+  double* nzval;
+  // state
+  TermCache tc;
+  b200_newton_result res;
+  std::vector<b200_trace_rec> trace;
+  int retcode, force_stop, make_new_jacobian, nsteps, have_factor, initialised;
+  double trust_region, max_tr;
+  int shrink_counter;
+  double eta, rnorm, rnorm_prev;
+  double fnorm_inf;  // ||f(u)||_inf of the current iterate
+  double bytes;
+};
+
+namespace {
+// ||x||_2 on the host (synchronising)
+int32_t h_nrm2(b200_newton* nw, const double* x, double* out) { return b200_nrm2(nw->ctx, nw->n, x, out); }
+int32_t h_dot(b200_newton* nw, const double* x, const double* y, double* out) { return b200_dot(nw->ctx, nw->n, x, y, out); }
+
+// termination_conditions.jl:243-336 for the AbsNorm* modes; `objective` = ||fu||_inf, `du_norm` = ||u - uprev||_2
+int term_check(b200_newton* nw, double objective, double du_norm, bool* new_best) {
+  TermCache& tc = nw->tc;
+  *new_best = false;
+  if (tc.mode == B200_TERM_ABS_NORM) {
+    if (objective <= tc.abstol) { tc.retcode = B200_RC_SUCCESS; return 1; }
+    return 0;
+  }
+  if (!std::isfinite(objective)) { tc.retcode = B200_RC_UNSTABLE; return 1; }
+  if (tc.mode == B200_TERM_ABS_NORM_SAFE_BEST && objective < tc.best) { tc.best = objective; *new_best = true; }
+  if (objective <= tc.abstol) { tc.retcode = B200_RC_SUCCESS; return 1; }
+  tc.nsteps += 1;
+  tc.obj_trace[(tc.nsteps - 1) % 100] = objective;
+  if (objective <= 3.0 * tc.abstol && tc.nsteps > 100) {
+    double mn = INFINITY, mx = -INFINITY;
+    for (int i = 0; i < 100; ++i) { mn = std::min(mn, tc.obj_trace[i]); mx = std::max(mx, tc.obj_trace[i]); }
+    if (mn < 1.3 * mx) { tc.retcode = B200_RC_STALLED; return 1; }
+  }
+  tc.step_trace[(tc.nsteps - 1) % 32] = du_norm;
+  if (tc.nsteps > 32) {
+    double mx = 0.0;
+    for (int i = 0; i < 32; ++i) mx = std::max(mx, tc.step_trace[i]);
+    if (mx <= tc.abstol) { tc.retcode = B200_RC_STALLED; return 1; }
+  }
+  tc.retcode = B200_RC_FAILURE;
+  return 0;
+}
+
+int32_t alloc_vec(b200_ctx* ctx, int64_t n, double** p) {
+  CUDA_TRY(ctx, cudaMalloc(p, sizeof(double) * ((n + 1) & ~(int64_t)1)));
+  return B200_OK;
+}
+}  // namespace
+
+extern "C" {
+void b200_newton_opts_default(b200_newton_opts* o) {
+  memset(o, 0, sizeof(*o));
+  o->abstol = 0.0;  // => 3e-13
+  o->reltol = 0.0;
+  o->maxiters = 1000;
+  o->linsolve = B200_LINSOLVE_GMRES;
+  o->jvp_mode = B200_JVP_EXACT;
+  o->globalization = B200_GLOBALIZATION_NONE;
+  o->forcing = B200_FORCING_NONE;
+  o->termination = B200_TERM_ABS_NORM_SAFE_BEST;
+  o->store_trace = 1;
+  o->fused_step = 1;
+  b200_gmres_opts_default(&o->gmres);
+  o->gmres.atol = 0.0;  // inherit the nonlinear tolerances (solve.jl:203)
+  o->gmres.rtol = 0.0;
+  o->ew_eta0 = 0.5; o->ew_eta_max = 0.9; o->ew_gamma = 0.9; o->ew_alpha = 2.0; o->ew_safeguard_threshold = 0.1; o->ew_safeguard = 1;
+  o->max_shrink_times = 32;
+}
+
+int32_t b200_newton_destroy(b200_newton* nw) {
+  if (!nw) return B200_OK;
+  b200_ctx* ctx = nw->ctx;
+  cudaStreamSynchronize(ctx->stream);
+  double* vecs[] = {nw->u, nw->fu, nw->u_cache, nw->du, nw->xlin, nw->best_u, nw->u_trial, nw->fu_trial, nw->Jdu, nw->JTfu, nw->du_c, nw->c1, nw->c2,
+                    nw->Jdense, nw->nzval};
+  for (double* v : vecs) if (v) cudaFree(v);
+  if (nw->ipiv) cudaFree(nw->ipiv);
+  if (nw->gm) b200_gmres_destroy(nw->gm);
+  if (nw->sj) b200_sparse_jac_destroy(nw->sj);
+  delete nw;
+  return B200_OK;
+}
+
+int32_t b200_newton_create(b200_problem* prob, const b200_newton_opts* opts, b200_newton** out) {
+  b200_ctx* ctx = prob->ctx;
+  B200_REQUIRE(ctx, opts && out, "newton_create: bad arguments");
+  b200_newton* nw = new b200_newton();
+  nw->ctx = ctx; nw->prob = prob; nw->o = *opts; nw->n = prob->n;
+  nw->abstol = opts->abstol > 0 ? opts->abstol : 3.0e-13;  // common_defaults.jl:44-48
+  nw->reltol = opts->reltol > 0 ? opts->reltol : 3.0e-13;
+  nw->maxiters = opts->maxiters > 0 ? opts->maxiters : 1000;
+  nw->u = nw->fu = nw->u_cache = nw->du = nw->xlin = nw->best_u = nullptr;
+  nw->u_trial = nw->fu_trial = nw->Jdu = nw->JTfu = nw->du_c = nw->c1 = nw->c2 = nullptr;
+  nw->gm = nullptr; nw->Jdense = nullptr; nw->ipiv = nullptr; nw->sj = nullptr; nw->nzval = nullptr;
+  nw->initialised = 0;
+  const int64_t n = nw->n;
+  int32_t s = B200_OK;
+  auto A = [&](double** p) { if (s == B200_OK) s = alloc_vec(ctx, n, p); };
+  A(&nw->u); A(&nw->fu); A(&nw->u_cache); A(&nw->du); A(&nw->xlin);
+  if (opts->termination == B200_TERM_ABS_NORM_SAFE_BEST) A(&nw->best_u);
+  if (opts->globalization == B200_GLOBALIZATION_TRUST_REGION) {
+    A(&nw->u_trial); A(&nw->fu_trial); A(&nw->Jdu); A(&nw->JTfu); A(&nw->du_c); A(&nw->c1); A(&nw->c2);
+  }
+  if (s != B200_OK) { b200_newton_destroy(nw); return s; }
+  memset(&nw->op, 0, sizeof(nw->op));
+  nw->op.ctx = ctx; nw->op.n = n;
+  if (opts->linsolve == B200_LINSOLVE_GMRES || opts->linsolve == B200_LINSOLVE_SPARSE_GMRES) {
+    b200_gmres_opts g = opts->gmres;
+    if (g.atol <= 0) g.atol = nw->abstol;  // linsolve_kwargs = (; abstol, reltol)   solve.jl:203
+    if (g.rtol <= 0) g.rtol = nw->reltol;
+    nw->o.gmres = g;
+    s = b200_gmres_create(ctx, n, &g, &nw->gm);
+    if (s != B200_OK) { b200_newton_destroy(nw); return s; }
+  }
+  if (opts->linsolve == B200_LINSOLVE_GMRES) {
+    nw->op.kind = LINOP_PROBLEM; nw->op.prob = prob; nw->op.u = nw->u; nw->op.jvp_mode = opts->jvp_mode;
+  } else if (opts->linsolve == B200_LINSOLVE_DENSE_LU) {
+    if (cudaMalloc(&nw->Jdense, sizeof(double) * n * n) != cudaSuccess || cudaMalloc(&nw->ipiv, sizeof(int64_t) * n) != cudaSuccess) {
+      cudaGetLastError();
+      b200_newton_destroy(nw);
+      return ctx->fail(B200_ERR_NOMEM, "dense Jacobian does not fit in device memory", __FILE__, __LINE__);
+    }
+  } else if (opts->linsolve == B200_LINSOLVE_SPARSE_GMRES) {
+    // jac_prototype + colouring once at init (jacobian.jl:286-353; colouring ext :13-28)
+    int64_t nnz = 0;
+    s = b200_pattern_nnz(prob, &nnz);
+    std::vector<int64_t> colptr(n + 1), rowval(nnz), colors(n);
+    int64_t ncolors = 0;
+    if (s == B200_OK) s = b200_pattern(prob, 1, colptr.data(), rowval.data());
+    if (s == B200_OK) s = b200_coloring_column(n, colptr.data(), rowval.data(), 1, B200_ORDER_LARGEST_FIRST, colors.data(), &ncolors);
+    if (s == B200_OK) s = b200_sparse_jac_create(prob, colptr.data(), rowval.data(), 1, colors.data(), ncolors, &nw->sj);
+    if (s == B200_OK && cudaMalloc(&nw->nzval, sizeof(double) * nnz) != cudaSuccess) { cudaGetLastError(); s = B200_ERR_NOMEM; }
+    if (s != B200_OK) { b200_newton_destroy(nw); return s; }
+    nw->op.kind = LINOP_SPARSE_JAC; nw->op.sj = nw->sj; nw->op.nzval = nw->nzval;
+  } else {
+    b200_newton_destroy(nw);
+    return ctx->fail(B200_ERR_INVALID, "unknown linsolve kind", __FILE__, __LINE__);
+  }
+  *out = nw;
+  return B200_OK;
+}
+
+// reinit!(cache, u0): everything __init computes from u0 (solve.jl:191-284; termination_conditions.jl:134-179)
+int32_t b200_newton_reinit(b200_newton* nw, const double* u0_dev) {
+  b200_ctx* ctx = nw->ctx;
+  const int64_t n = nw->n;
+  const b200_newton_opts& o = nw->o;
+  if (u0_dev != nw->u) CUDA_TRY(ctx, cudaMemcpyAsync(nw->u, u0_dev, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_scalars, 0, sizeof(double) * 4, ctx->stream));
+  B200_TRY(b200i_residual_norm(nw->prob, nw->u, nw->fu, ctx->d_scalars));  // evaluate_f(prob,u): nf is NOT bumped (solve.jl:194)
+  CUDA_TRY(ctx, cudaMemcpyAsync(nw->u_cache, nw->u, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaMemsetAsync(nw->du, 0, sizeof(double) * n, ctx->stream));  // descent caches start with a defined du
+  if (nw->best_u) CUDA_TRY(ctx, cudaMemcpyAsync(nw->best_u, nw->u, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+  B200_TRY(b200i_fetch_scalars(ctx, 1));
+  nw->fnorm_inf = ctx->h_scalars[0];
+  memset(&nw->tc, 0, sizeof(nw->tc));
+  nw->tc.mode = o.termination;
+  nw->tc.abstol = nw->abstol;
+  nw->tc.initial = nw->fnorm_inf;
+  nw->tc.best = (o.termination == B200_TERM_ABS_NORM) ? INFINITY : nw->fnorm_inf;
+  memset(&nw->res, 0, sizeof(nw->res));
+  nw->trace.clear();
+  nw->retcode = B200_RC_DEFAULT; nw->force_stop = 0; nw->make_new_jacobian = 1; nw->nsteps = 0; nw->have_factor = 0;
+  nw->shrink_counter = 0; nw->bytes = 2.0 * 8.0 * n;
+  if (o.linsolve == B200_LINSOLVE_DENSE_LU) nw->res.njacs += 1;  // jac_prototype === nothing: DI.jacobian at init (jacobian.jl:103-117)
+  if (o.globalization == B200_GLOBALIZATION_TRUST_REGION) {  // trust_region.jl:204-258, 330-346 (Simple scheme)
+    double fu_norm, umin, umax;
+    B200_TRY(h_nrm2(nw, nw->fu, &fu_norm));
+    B200_TRY(b200_extrema(ctx, n, nw->u, &umin, &umax));
+    nw->max_tr = o.tr_max_trust_radius > 0 ? o.tr_max_trust_radius : std::max(fu_norm, umax - umin);
+    nw->trust_region = o.tr_initial_trust_radius > 0 ? o.tr_initial_trust_radius : nw->max_tr / 11.0;
+  }
+  nw->eta = o.ew_eta0;
+  if (o.forcing == B200_FORCING_EW2) {
+    B200_TRY(h_nrm2(nw, nw->fu, &nw->rnorm));
+    nw->rnorm_prev = nw->rnorm;
+  }
+  nw->initialised = 1;
+  return B200_OK;
+}
+
+static int32_t newton_step_inner(b200_newton* nw) {
+  b200_ctx* ctx = nw->ctx;
+  const int64_t n = nw->n;
+  const b200_newton_opts& o = nw->o;
+  const double Bv = 8.0 * (double)n;
+  const bool tr_on = o.globalization == B200_GLOBALIZATION_TRUST_REGION;
+  const bool krylov = o.linsolve != B200_LINSOLVE_DENSE_LU;
+  const double step_thr = o.tr_step_threshold > 0 ? o.tr_step_threshold : 1.0 / 10000;
+  const double shrink_thr = o.tr_shrink_threshold > 0 ? o.tr_shrink_threshold : 0.25;
+  const double expand_thr = o.tr_expand_threshold > 0 ? o.tr_expand_threshold : 0.75;
+  const double shrink_fac = o.tr_shrink_factor > 0 ? o.tr_shrink_factor : 0.25;
+  const double expand_fac = o.tr_expand_factor > 0 ? o.tr_expand_factor : 2.0;
+  const int max_shrink = o.max_shrink_times > 0 ? o.max_shrink_times : 32;
+
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    int new_jacobian;
+    if (nw->make_new_jacobian) {  // J = cache.jac_cache(u)   solve.jl:338-344
+      new_jacobian = 1;
+      if (o.linsolve == B200_LINSOLVE_DENSE_LU) {
+        nw->res.njacs += 1;
+        B200_TRY(b200_dense_jac_fill(nw->prob, nw->u, nw->Jdense, n));  // written straight into the LU workspace (K10: no copyto!)
+        nw->have_factor = 0;
+      } else if (o.linsolve == B200_LINSOLVE_SPARSE_GMRES) {
+        nw->res.njacs += 1;
+        B200_TRY(b200_sparse_jac_fill(nw->sj, nw->u, nw->nzval));
+      }
+    } else {
+      new_jacobian = 0;
+    }
+    if (o.forcing == B200_FORCING_EW2 && krylov) {  // pre_step_forcing!   eisenstat_walker.jl:42-80
+      if (nw->nsteps == 0) {
+        nw->eta = o.ew_eta0;
+        B200_TRY(h_nrm2(nw, nw->fu, &nw->rnorm));
+        nw->rnorm_prev = nw->rnorm;
+      } else {
+        const double eta_prev = nw->eta;
+        nw->eta = o.ew_gamma * pow(nw->rnorm / nw->rnorm_prev, o.ew_alpha);
+        if (o.ew_safeguard) {
+          const double sg = o.ew_gamma * pow(eta_prev, o.ew_alpha);
+          if (sg > o.ew_safeguard_threshold && sg > nw->eta) nw->eta = sg;
+        }
+        nw->eta = std::min(std::max(nw->eta, 0.0), o.ew_eta_max);
+      }
+      B200_TRY(b200_gmres_set_tolerances(nw->gm, -1.0, nw->eta));  // LinearSolve.update_tolerances!(lincache; reltol = eta)
+    }
+    // ---- descent: J x = fu ; du = -x   (newton.jl:97-141)
+    int lin_success = 1;
+    b200_gmres_stats gs;
+    memset(&gs, 0, sizeof(gs));
+    nw->res.nsolve += 1;
+    if (!krylov) {
+      if (!nw->have_factor) {  // update_A! for a factorisation on a fresh A (…LinearSolveExt.jl:81-86)
+        nw->res.nfactors += 1;
+        int32_t info = 0;
+        B200_TRY(b200_getrf(ctx, n, nw->Jdense, n, nw->ipiv, &info));
+        nw->have_factor = 1;
+        if (info != 0) lin_success = 0;
+      }
+      CUDA_TRY(ctx, cudaMemcpyAsync(nw->xlin, nw->fu, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+      if (lin_success) B200_TRY(b200_getrs(ctx, n, 1, nw->Jdense, n, nw->ipiv, nw->xlin, n));
+    } else {
+      // `linu` aliases the du buffer: it is the initial guess only when warm_start is requested
+      if (o.gmres.warm_start) CUDA_TRY(ctx, cudaMemcpyAsync(nw->xlin, nw->du, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+      B200_TRY(b200_gmres_solve(nw->gm, &nw->op, nw->fu, nw->xlin, &gs));
+      nw->res.njvp += gs.nmatvec;
+      nw->bytes += gs.bytes;
+      if (gs.status == B200_LS_NONFINITE || gs.status == B200_LS_OUT_OF_MEMORY) lin_success = 0;  // LinearSolve retcode Failure
+    }
+    if (!lin_success) {  // solve.jl:367-382
+      if (new_jacobian) { nw->retcode = B200_RC_INTERNAL_LINSOLVE_FAILED; nw->force_stop = 1; return B200_OK; }
+      nw->make_new_jacobian = 1;
+      continue;  // retry once with a fresh Jacobian
+    }
+    // du = -x   (@. du *= -1, newton.jl:138)
+    B200_TRY(b200_axpby(ctx, n, -1.0, nw->xlin, 0.0, nw->du));
+
+    double dJJd = NAN;
+    if (tr_on) {  // Dogleg   dogleg.jl:86-151
+      double nrm_newton;
+      B200_TRY(h_nrm2(nw, nw->du, &nrm_newton));
+      if (!(nrm_newton <= nw->trust_region)) {
+        B200_TRY(b200_vjp(nw->prob, nw->u, nw->fu, nw->du_c));  // du_c = -J' fu  (steepest.jl:60-80)
+        B200_TRY(b200_scal(ctx, n, -1.0, nw->du_c));
+        double l_grad, quad;
+        B200_TRY(h_nrm2(nw, nw->du_c, &l_grad));
+        B200_TRY(b200_jvp(nw->prob, nw->u, nw->du_c, nw->Jdu));
+        B200_TRY(h_dot(nw, nw->Jdu, nw->Jdu, &quad));
+        const double d_cauchy = (l_grad * l_grad * l_grad) / quad;
+        if (d_cauchy >= nw->trust_region) {
+          const double lam = nw->trust_region / l_grad;
+          B200_TRY(b200_axpby(ctx, n, lam, nw->du_c, 0.0, nw->du));
+          dJJd = lam * lam * quad;
+        } else {
+          B200_TRY(b200_axpby(ctx, n, d_cauchy / l_grad, nw->du_c, 0.0, nw->c1));  // c1 = (d_cauchy/l_grad) du_c
+          B200_TRY(b200_copy(ctx, n, nw->du, nw->c2));
+          B200_TRY(b200_axpy(ctx, n, -1.0, nw->c1, nw->c2));                         // c2 = du_newton - c1
+          double a, b2;
+          B200_TRY(h_dot(nw, nw->c2, nw->c2, &a));
+          B200_TRY(h_dot(nw, nw->c1, nw->c2, &b2));
+          const double b = 2.0 * b2, c = d_cauchy * d_cauchy - nw->trust_region * nw->trust_region;
+          const double aux = std::max(0.0, b * b - 4.0 * a * c);
+          const double tau = (-b + sqrt(aux)) / (2.0 * a);
+          B200_TRY(b200_copy(ctx, n, nw->c1, nw->du));
+          B200_TRY(b200_axpy(ctx, n, tau, nw->c2, nw->du));
+        }
+      }
+    }
+    if (o.forcing == B200_FORCING_EW2 && krylov) {  // post_step_forcing!  eisenstat_walker.jl:83-87 (fu is still the old residual)
+      nw->rnorm_prev = nw->rnorm;
+      B200_TRY(h_nrm2(nw, nw->fu, &nw->rnorm));
+    }
+    nw->make_new_jacobian = 1;
+    int accepted = 1;
+    double objective, du_norm;
+    if (!tr_on) {  // solve.jl:436-445 : u += du ; fu = f(u) ; with ||du||^2 and ||fu||_inf produced by the kernels' epilogues
+      CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_scalars, 0, sizeof(double) * 2, ctx->stream));
+      B200_TRY(b200i_axpy_norm(ctx, n, 1.0, nw->du, nw->u, ctx->d_scalars + 1));
+      B200_TRY(b200i_residual_norm(nw->prob, nw->u, nw->fu, ctx->d_scalars));
+      nw->res.nf += 1;
+      B200_TRY(b200i_fetch_scalars(ctx, 2));
+      objective = ctx->h_scalars[0];
+      du_norm = sqrt(ctx->h_scalars[1]);
+      nw->bytes += 5.0 * Bv;
+    } else {  // GenericTrustRegionScheme solve!   trust_region.jl:396-430, 511-513
+      B200_TRY(b200_copy(ctx, n, nw->u, nw->u_trial));
+      B200_TRY(b200_axpy(ctx, n, 1.0, nw->du, nw->u_trial));
+      CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_scalars, 0, sizeof(double) * 2, ctx->stream));
+      B200_TRY(b200i_residual_norm(nw->prob, nw->u_trial, nw->fu_trial, ctx->d_scalars));
+      nw->res.nf += 1;
+      B200_TRY(b200i_fetch_scalars(ctx, 1));
+      const double trial_inf = ctx->h_scalars[0];
+      if (dJJd != dJJd) {
+        B200_TRY(b200_jvp(nw->prob, nw->u, nw->du, nw->Jdu));
+        B200_TRY(h_dot(nw, nw->Jdu, nw->Jdu, &dJJd));
+      }
+      B200_TRY(b200_vjp(nw->prob, nw->u, nw->fu, nw->JTfu));
+      double nt, nc, dg;
+      B200_TRY(h_nrm2(nw, nw->fu_trial, &nt));
+      B200_TRY(h_nrm2(nw, nw->fu, &nc));
+      B200_TRY(h_dot(nw, nw->du, nw->JTfu, &dg));
+      const double num = (nt * nt - nc * nc) / 2.0;
+      const double denom = dg + dJJd / 2.0;
+      const double rho = num / denom;
+      accepted = rho > step_thr;
+      if (rho < shrink_thr) { nw->trust_region *= shrink_fac; nw->shrink_counter += 1; }
+      else { nw->shrink_counter = 0; if (rho > expand_thr && rho > step_thr) nw->trust_region = expand_fac * nw->trust_region; }
+      nw->trust_region = std::min(nw->trust_region, nw->max_tr);
+      if (accepted) {
+        B200_TRY(h_nrm2(nw, nw->du, &du_norm));
+        std::swap(nw->u, nw->u_trial);      // copyto!(cache.u, u_new) as a pointer swap
+        std::swap(nw->fu, nw->fu_trial);
+        nw->op.u = nw->u;
+        objective = trial_inf;
+      } else {
+        nw->make_new_jacobian = 0;
+        objective = nw->fnorm_inf;
+        du_norm = 0.0;
+      }
+      if (nw->shrink_counter > max_shrink) { nw->retcode = B200_RC_SHRINK_THRESHOLD_EXCEEDED; nw->force_stop = 1; }
+    }
+    nw->fnorm_inf = objective;
+    bool new_best = false;
+    if (term_check(nw, objective, du_norm, &new_best)) { nw->retcode = nw->tc.retcode; nw->force_stop = 1; }  // check_and_update!
+    if (new_best && nw->best_u) CUDA_TRY(ctx, cudaMemcpyAsync(nw->best_u, nw->u, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (o.store_trace) {
+      b200_trace_rec t;
+      t.iter = nw->nsteps + 1; t.lin_iters = gs.iters; t.lin_status = gs.status; t.accepted = accepted;
+      t.fnorm_inf = objective; t.step_norm2 = du_norm; t.lin_rnorm = gs.rnorm; t.trust_radius = nw->trust_region;
+      nw->trace.push_back(t);
+    }
+    // copyto!(u_cache, u) (solve.jl:460) is only ever read back as `uprev` for the stall norm, which the update kernel
+    // already produced; the copy is skipped.
+    return B200_OK;
+  }
+  return B200_OK;
+}
+
+int32_t b200_newton_step(b200_newton* nw, int32_t* terminated_host) {
+  b200_ctx* ctx = nw->ctx;
+  B200_REQUIRE(ctx, nw->initialised, "newton_step before newton_reinit");
+  if (!(nw->force_stop || nw->nsteps >= nw->maxiters)) {  // not_terminated  abstract_types.jl:722-724
+    B200_TRY(newton_step_inner(nw));
+    nw->res.nsteps += 1;  // CommonSolve.step!  NonlinearSolveBase/src/solve.jl:835-858
+    nw->nsteps += 1;
+  }
+  if (terminated_host) *terminated_host = (nw->force_stop || nw->nsteps >= nw->maxiters) ? 1 : 0;
+  return B200_OK;
+}
+
+int32_t b200_newton_result_get(b200_newton* nw, b200_newton_result* r) {
+  *r = nw->res;
+  r->retcode = nw->retcode;
+  r->resid_inf = nw->fnorm_inf;
+  r->ntrace = (int32_t)nw->trace.size();
+  r->bytes = nw->bytes;
+  return B200_OK;
+}
+
+int32_t b200_newton_solve(b200_newton* nw, b200_newton_result* result) {
+  b200_ctx* ctx = nw->ctx;
+  B200_REQUIRE(ctx, nw->initialised, "newton_solve before newton_reinit");
+  while (!nw->force_stop && nw->nsteps < nw->maxiters) {
+    B200_TRY(newton_step_inner(nw));
+    nw->res.nsteps += 1;
+    nw->nsteps += 1;
+  }
+  if (nw->retcode == B200_RC_DEFAULT) nw->retcode = (nw->nsteps >= nw->maxiters) ? B200_RC_MAXITERS : B200_RC_SUCCESS;  // solve.jl:372-376
+  // update_from_termination_cache! for Best modes: roll back to the best iterate (termination_conditions.jl:440-453)
+  if (nw->best_u) {
+    int32_t same = 1;
+    B200_TRY(b200_equal(ctx, nw->n, nw->u, nw->best_u, &same));
+    if (!same) {
+      CUDA_TRY(ctx, cudaMemcpyAsync(nw->u, nw->best_u, sizeof(double) * nw->n, cudaMemcpyDeviceToDevice, ctx->stream));
+      CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_scalars, 0, sizeof(double), ctx->stream));
+      B200_TRY(b200i_residual_norm(nw->prob, nw->u, nw->fu, ctx->d_scalars));
+      nw->res.nf += 1;
+      B200_TRY(b200i_fetch_scalars(ctx, 1));
+      nw->fnorm_inf = ctx->h_scalars[0];
+    }
+  }
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (result) B200_TRY(b200_newton_result_get(nw, result));
+  return B200_OK;
+}
+
+int32_t b200_newton_u(b200_newton* nw, double** u_dev) { *u_dev = nw->u; return B200_OK; }
+int32_t b200_newton_fu(b200_newton* nw, double** fu_dev) { *fu_dev = nw->fu; return B200_OK; }
+
+int32_t b200_newton_trace(b200_newton* nw, b200_trace_rec* recs, int32_t cap, int32_t* count) {
+  int32_t m = (int32_t)std::min<size_t>(nw->trace.size(), (size_t)std::max(cap, 0));
+  for (int32_t i = 0; i < m; ++i) recs[i] = nw->trace[i];
+  if (count) *count = m;
+  return B200_OK;
+}
+
+int32_t b200_newton_solve_host(b200_newton* nw, const double* u0_host, double* u_host, double* resid_host, b200_newton_result* result) {
+  b200_ctx* ctx = nw->ctx;
+  const size_t bytes = sizeof(double) * nw->n;
+  CUDA_TRY(ctx, cudaMemcpyAsync(nw->u, u0_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  B200_TRY(b200_newton_reinit(nw, nw->u));
+  B200_TRY(b200_newton_solve(nw, result));
+  if (u_host) CUDA_TRY(ctx, cudaMemcpyAsync(u_host, nw->u, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  if (resid_host) CUDA_TRY(ctx, cudaMemcpyAsync(resid_host, nw->fu, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return B200_OK;
+}
+}  // extern "C"

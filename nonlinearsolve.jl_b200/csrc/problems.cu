@@ -1,0 +1,445 @@
+// problems.cu — residual f(u), exact-tangent JVP J(u)v, VJP J(u)'w and the fused finite-difference JVP for the
+// built-in problems (kernels K1, K2).
+//
+//   2D/3D Brusselator  : lib/NonlinearSolveFirstOrder/test/sparsity_tests__item1.jl:7-50 (3D extension: SURVEY.md §A.2)
+//   quadratic u.^2 .- p: common/common_rootfind_testing.jl:15
+//   tridiagonal quad.  : lib/NonlinearSolveFirstOrder/test/rootfind_tests__item20.jl:6-29
+//   callback           : NonlinearFunction{true}(f!; jvp = jvp!)  (SciMLJacobianOperators.jl:366-431 takes f.jvp verbatim)
+//
+// Layout: species-planar, i fastest: idx(i,j[,k],s) = i + N j [+ N^2 k] + N^dim s  (Julia column-major (N,N[,N],2)).
+// The JVP is the exact tangent of the residual expression (what DI.pushforward! with ForwardDiff computes,
+// SciMLJacobianOperators.jl:396-414), not a finite difference; b200_jvp_fd is the AutoFiniteDiff analogue.
+#include "common.cuh"
+#include <math.h>
+#include <float.h>
+
+namespace {
+constexpr int PB_THREADS = 256;
+
+enum { M_RESID = 1, M_JVP = 2, M_VJP = 4, M_NORM = 8, M_FD = 16 };
+
+struct BrussParams {
+  int N;
+  double a, A, B;
+};
+
+__device__ __forceinline__ void bruss_react(double uc, double vc, double A, double& j00, double& j01, double& j10, double& j11) {
+  const double uv2 = 2.0 * uc * vc, uu = uc * uc;
+  j00 = uv2 - (A + 1.0);
+  j01 = uu;
+  j10 = A - uv2;
+  j11 = -uu;
+}
+
+// ---- 2D: one thread per cell.  n is small for every 2D configuration (N<=128 -> 256 KB), so the whole state is
+// L2/L1 resident and a halo tile buys nothing; the 3D kernel below is the bandwidth-critical one.
+template <int MODE>
+__global__ void __launch_bounds__(PB_THREADS) bruss2d_kernel(BrussParams P, const double* __restrict__ u, const double* __restrict__ d,
+                                                              const double* __restrict__ forcing, double* __restrict__ du,
+                                                              double* __restrict__ Jd, double* __restrict__ norm_out,
+                                                              const double* __restrict__ eps_ptr) {
+  __shared__ double red[32];
+  const int N = P.N;
+  const int NC = N * N;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  double nrm = 0.0;
+  if (c < NC) {
+    const int i = c % N, j = c / N;
+    const int ip = (i + 1 == N) ? 0 : i + 1, im = (i == 0) ? N - 1 : i - 1;
+    const int jp = (j + 1 == N) ? 0 : j + 1, jm = (j == 0) ? N - 1 : j - 1;
+    const int cim = im + N * j, cip = ip + N * j, cjp = i + N * jp, cjm = i + N * jm;
+    const double uc = u[c], vc = u[c + NC];
+    if (MODE & M_RESID) {
+      const double lapu = u[cim] + u[cip] + u[cjp] + u[cjm] - 4.0 * uc;
+      const double lapv = u[cim + NC] + u[cip + NC] + u[cjp + NC] + u[cjm + NC] - 4.0 * vc;
+      const double uuv = uc * uc * vc;
+      const double f0 = P.a * lapu + P.B + uuv - (P.A + 1.0) * uc + forcing[c];
+      const double f1 = P.a * lapv + P.A * uc - uuv;
+      du[c] = f0;
+      du[c + NC] = f1;
+      if (MODE & M_NORM) nrm = fmax(abs_nf(f0), abs_nf(f1));
+    }
+    if (MODE & (M_JVP | M_VJP)) {
+      const double dc = d[c], ec = d[c + NC];
+      const double lapd = d[cim] + d[cip] + d[cjp] + d[cjm] - 4.0 * dc;
+      const double lape = d[cim + NC] + d[cip + NC] + d[cjp + NC] + d[cjm + NC] - 4.0 * ec;
+      double j00, j01, j10, j11;
+      bruss_react(uc, vc, P.A, j00, j01, j10, j11);
+      if (MODE & M_JVP) {
+        Jd[c] = P.a * lapd + j00 * dc + j01 * ec;
+        Jd[c + NC] = P.a * lape + j10 * dc + j11 * ec;
+      } else {
+        Jd[c] = P.a * lapd + j00 * dc + j10 * ec;
+        Jd[c + NC] = P.a * lape + j01 * dc + j11 * ec;
+      }
+    }
+    if (MODE & M_FD) {  // (f(u + eps d) - f(u)) / eps evaluated in one pass over the shared neighbourhood
+      const double eps = *eps_ptr;
+      const double dc = d[c], ec = d[c + NC];
+      const double lapu = u[cim] + u[cip] + u[cjp] + u[cjm] - 4.0 * uc;
+      const double lapv = u[cim + NC] + u[cip + NC] + u[cjp + NC] + u[cjm + NC] - 4.0 * vc;
+      const double up = uc + eps * dc, vp = vc + eps * ec;
+      const double lapup = (u[cim] + eps * d[cim]) + (u[cip] + eps * d[cip]) + (u[cjp] + eps * d[cjp]) + (u[cjm] + eps * d[cjm]) - 4.0 * up;
+      const double lapvp = (u[cim + NC] + eps * d[cim + NC]) + (u[cip + NC] + eps * d[cip + NC]) + (u[cjp + NC] + eps * d[cjp + NC]) +
+                           (u[cjm + NC] + eps * d[cjm + NC]) - 4.0 * vp;
+      const double fo = forcing[c];
+      const double f0 = P.a * lapu + P.B + uc * uc * vc - (P.A + 1.0) * uc + fo;
+      const double f1 = P.a * lapv + P.A * uc - uc * uc * vc;
+      const double g0 = P.a * lapup + P.B + up * up * vp - (P.A + 1.0) * up + fo;
+      const double g1 = P.a * lapvp + P.A * up - up * up * vp;
+      Jd[c] = (g0 - f0) / eps;
+      Jd[c + NC] = (g1 - f1) / eps;
+    }
+  }
+  if (MODE & M_NORM) {
+    nrm = block_max(nrm, red);
+    if (threadIdx.x == 0) atomic_max_nonneg(norm_out, nrm);
+  }
+}
+
+// ---- 3D: thread per cell, i fastest -> the centre loads/stores of a warp are one contiguous 256-byte segment per
+// species; i+-1 neighbours hit the same lines in L1, j+-1 / k+-1 neighbours are re-reads served by L1/L2 (the whole
+// 32 MB state of the N=100 case sits in the 126 MB L2), so HBM traffic stays at the algorithmic 2/3/4 Bv.
+template <int MODE>
+__global__ void __launch_bounds__(PB_THREADS) bruss3d_kernel(BrussParams P, const double* __restrict__ u, const double* __restrict__ d,
+                                                              const double* __restrict__ forcing, double* __restrict__ du,
+                                                              double* __restrict__ Jd, double* __restrict__ norm_out,
+                                                              const double* __restrict__ eps_ptr) {
+  __shared__ double red[32];
+  const int N = P.N;
+  const int N2 = N * N;
+  const int64_t NC = (int64_t)N2 * N;
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double nrm = 0.0;
+  if (c < NC) {
+    const int k = (int)(c / N2);
+    const int r = (int)(c - (int64_t)k * N2);
+    const int j = r / N, i = r - j * N;
+    const int64_t cim = c + ((i == 0) ? (N - 1) : -1), cip = c + ((i + 1 == N) ? -(N - 1) : 1);
+    const int64_t cjm = c + ((j == 0) ? (int64_t)(N - 1) * N : -N), cjp = c + ((j + 1 == N) ? -(int64_t)(N - 1) * N : N);
+    const int64_t ckm = c + ((k == 0) ? (int64_t)(N - 1) * N2 : -N2), ckp = c + ((k + 1 == N) ? -(int64_t)(N - 1) * N2 : N2);
+    const double uc = u[c], vc = u[c + NC];
+    if (MODE & M_RESID) {
+      const double lapu = (u[cim] + u[cip] + u[cjp] + u[cjm] - 4.0 * uc) + (u[ckp] + u[ckm] - 2.0 * uc);
+      const double lapv = (u[cim + NC] + u[cip + NC] + u[cjp + NC] + u[cjm + NC] - 4.0 * vc) + (u[ckp + NC] + u[ckm + NC] - 2.0 * vc);
+      const double uuv = uc * uc * vc;
+      const double f0 = P.a * lapu + P.B + uuv - (P.A + 1.0) * uc + forcing[r];
+      const double f1 = P.a * lapv + P.A * uc - uuv;
+      du[c] = f0;
+      du[c + NC] = f1;
+      if (MODE & M_NORM) nrm = fmax(abs_nf(f0), abs_nf(f1));
+    }
+    if (MODE & (M_JVP | M_VJP)) {
+      const double dc = d[c], ec = d[c + NC];
+      const double lapd = (d[cim] + d[cip] + d[cjp] + d[cjm] - 4.0 * dc) + (d[ckp] + d[ckm] - 2.0 * dc);
+      const double lape = (d[cim + NC] + d[cip + NC] + d[cjp + NC] + d[cjm + NC] - 4.0 * ec) + (d[ckp + NC] + d[ckm + NC] - 2.0 * ec);
+      double j00, j01, j10, j11;
+      bruss_react(uc, vc, P.A, j00, j01, j10, j11);
+      if (MODE & M_JVP) {
+        Jd[c] = P.a * lapd + j00 * dc + j01 * ec;
+        Jd[c + NC] = P.a * lape + j10 * dc + j11 * ec;
+      } else {
+        Jd[c] = P.a * lapd + j00 * dc + j10 * ec;
+        Jd[c + NC] = P.a * lape + j01 * dc + j11 * ec;
+      }
+    }
+    if (MODE & M_FD) {
+      const double eps = *eps_ptr;
+      const double dc = d[c], ec = d[c + NC];
+      const double up = uc + eps * dc, vp = vc + eps * ec;
+      const double lapu = (u[cim] + u[cip] + u[cjp] + u[cjm] - 4.0 * uc) + (u[ckp] + u[ckm] - 2.0 * uc);
+      const double lapv = (u[cim + NC] + u[cip + NC] + u[cjp + NC] + u[cjm + NC] - 4.0 * vc) + (u[ckp + NC] + u[ckm + NC] - 2.0 * vc);
+#define PU(x) (u[x] + eps * d[x])
+      const double lapup = (PU(cim) + PU(cip) + PU(cjp) + PU(cjm) - 4.0 * up) + (PU(ckp) + PU(ckm) - 2.0 * up);
+      const double lapvp = (PU(cim + NC) + PU(cip + NC) + PU(cjp + NC) + PU(cjm + NC) - 4.0 * vp) + (PU(ckp + NC) + PU(ckm + NC) - 2.0 * vp);
+#undef PU
+      const double fo = forcing[r];
+      const double f0 = P.a * lapu + P.B + uc * uc * vc - (P.A + 1.0) * uc + fo;
+      const double f1 = P.a * lapv + P.A * uc - uc * uc * vc;
+      const double g0 = P.a * lapup + P.B + up * up * vp - (P.A + 1.0) * up + fo;
+      const double g1 = P.a * lapvp + P.A * up - up * up * vp;
+      Jd[c] = (g0 - f0) / eps;
+      Jd[c + NC] = (g1 - f1) / eps;
+    }
+  }
+  if (MODE & M_NORM) {
+    nrm = block_max(nrm, red);
+    if (threadIdx.x == 0) atomic_max_nonneg(norm_out, nrm);
+  }
+}
+
+// ---- small analytic test problems
+__device__ __forceinline__ double tri_apply(int64_t n, const double* x, int64_t i) {
+  double s = 2.0 * x[i];
+  if (i > 0) s -= x[i - 1];
+  if (i + 1 < n) s -= x[i + 1];
+  return s;
+}
+// kind: 0 quadratic, 1 tridiag.  what: M_RESID / M_JVP / M_VJP
+__global__ void __launch_bounds__(PB_THREADS) small_problem_kernel(int kind, int what, int64_t n, double p, const double* __restrict__ pvec,
+                                                                    const double* __restrict__ u, const double* __restrict__ d,
+                                                                    double* __restrict__ out, double* __restrict__ norm_out) {
+  __shared__ double red[32];
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double nrm = 0.0;
+  if (i < n) {
+    double r;
+    if (kind == 0) {
+      if (what & M_RESID) r = u[i] * u[i] - p;
+      else r = 2.0 * u[i] * d[i];
+    } else {
+      if (what & M_RESID) r = u[i] + 0.1 * u[i] * tri_apply(n, u, i) - pvec[i];
+      else if (what & M_JVP) r = d[i] + 0.1 * (u[i] * tri_apply(n, d, i) + d[i] * tri_apply(n, u, i));
+      else {  // J'w = w + 0.1 (T(u.*w) + (T u).*w)
+        double t = 2.0 * u[i] * d[i];
+        if (i > 0) t -= u[i - 1] * d[i - 1];
+        if (i + 1 < n) t -= u[i + 1] * d[i + 1];
+        r = d[i] + 0.1 * (t + tri_apply(n, u, i) * d[i]);
+      }
+    }
+    out[i] = r;
+    nrm = abs_nf(r);
+  }
+  if (what & M_NORM) {
+    nrm = block_max(nrm, red);
+    if (threadIdx.x == 0) atomic_max_nonneg(norm_out, nrm);
+  }
+}
+
+__global__ void fd_eps_kernel(const double* dot_uv, double* eps_out) {
+  // FiniteDiff.jl finite_difference_jvp!: eps = max(relstep * sqrt|x.v|, absstep), relstep = absstep = sqrt(eps(Float64))
+  const double relstep = 1.4901161193847656e-08;
+  *eps_out = fmax(relstep * sqrt(fabs(*dot_uv)), relstep);
+}
+__global__ void __launch_bounds__(PB_THREADS) fd_combine_kernel(int64_t n, const double* __restrict__ eps_ptr, const double* f1,
+                                                                 const double* __restrict__ f0, double* out) {
+  const double eps = *eps_ptr;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = (f1[i] - f0[i]) / eps;
+}
+__global__ void __launch_bounds__(PB_THREADS) fd_perturb_kernel(int64_t n, const double* __restrict__ eps_ptr, const double* __restrict__ u,
+                                                                 const double* __restrict__ v, double* __restrict__ out) {
+  const double eps = *eps_ptr;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = u[i] + eps * v[i];
+}
+
+__global__ void __launch_bounds__(PB_THREADS) bruss_u0_kernel(int dim, int N, int mode, double* __restrict__ u) {
+  const int64_t NC = (dim == 2) ? (int64_t)N * N : (int64_t)N * N * N;
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= NC) return;
+  const int i = (int)(c % N), j = (int)((c / N) % N), k = (int)(c / ((int64_t)N * N));
+  const double x = (double)i / (double)(N - 1), y = (double)j / (double)(N - 1);
+  double fac = 1.0;
+  if (dim == 3 && mode == B200_U0_PERTURBED_Z) {
+    const double z = (double)k / (double)(N - 1);
+    fac = 1.0 + 0.01 * sin(2.0 * 3.14159265358979323846 * z);
+  }
+  u[c] = 22.0 * pow(y * (1.0 - y), 1.5) * fac;
+  u[c + NC] = 27.0 * pow(x * (1.0 - x), 1.5) * fac;
+}
+
+inline int grid_for(int64_t n) { return (int)((n + PB_THREADS - 1) / PB_THREADS); }
+
+template <int MODE>
+int32_t launch_bruss(b200_problem* p, const double* u, const double* d, double* du, double* Jd, double* norm_out, const double* eps) {
+  b200_ctx* ctx = p->ctx;
+  BrussParams P{p->N, p->a, p->A, p->B};
+  const double* forcing = p->pvec;
+  if (p->kind == B200_PROB_BRUSS2D) {
+    LAUNCH(ctx, (bruss2d_kernel<MODE>), grid_for((int64_t)p->N * p->N), PB_THREADS, 0, P, u, d, forcing, du, Jd, norm_out, eps);
+  } else {
+    LAUNCH(ctx, (bruss3d_kernel<MODE>), grid_for((int64_t)p->N * p->N * p->N), PB_THREADS, 0, P, u, d, forcing, du, Jd, norm_out, eps);
+  }
+  CHECK_LAUNCH(ctx);
+  return B200_OK;
+}
+
+int32_t create_common(b200_ctx* ctx, b200_problem** out, int32_t kind, int32_t N, int64_t n) {
+  if (!ctx || !out) return B200_ERR_INVALID;
+  b200_problem* p = new b200_problem();
+  memset(p, 0, sizeof(*p));
+  p->ctx = ctx;
+  p->kind = kind;
+  p->N = N;
+  p->n = n;
+  *out = p;
+  return B200_OK;
+}
+
+int32_t create_bruss(b200_ctx* ctx, int dim, int32_t N, double A, double B, double alpha, b200_problem** out) {
+  B200_REQUIRE(ctx, N >= 3 && (dim == 2 ? N <= 16384 : N <= 1024), "Brusselator grid size out of range (3 <= N)");
+  const int64_t NC = (dim == 2) ? (int64_t)N * N : (int64_t)N * N * N;
+  B200_TRY(create_common(ctx, out, dim == 2 ? B200_PROB_BRUSS2D : B200_PROB_BRUSS3D, N, 2 * NC));
+  b200_problem* p = *out;
+  p->A = A;
+  p->B = B;
+  p->alpha = alpha;
+  const double dx = 1.0 / (double)(N - 1);  // step(range(0, stop = 1, length = N))
+  p->a = alpha / (dx * dx);                 // alpha = alpha / dx^2   (sparsity_tests__item1.jl:15)
+  // forcing plane brusselator_f(x_i, y_j) (sparsity_tests__item1.jl:10), z-independent; evaluated once on the host in
+  // strict IEEE double with the reference's expression so that the mask is bit-identical to the reference's.
+  std::vector<double> forcing((size_t)N * N);
+  const double r2 = 0.1 * 0.1;
+  for (int j = 0; j < N; ++j)
+    for (int i = 0; i < N; ++i) {
+      volatile double x = (double)i / (double)(N - 1), y = (double)j / (double)(N - 1);
+      volatile double dx2 = (x - 0.3) * (x - 0.3), dy2 = (y - 0.6) * (y - 0.6);
+      volatile double s = dx2 + dy2;
+      forcing[(size_t)i + (size_t)N * j] = (s <= r2) ? 5.0 : 0.0;
+    }
+  double* dptr = nullptr;
+  CUDA_TRY(ctx, cudaMalloc(&dptr, sizeof(double) * forcing.size()));
+  CUDA_TRY(ctx, cudaMemcpyAsync(dptr, forcing.data(), sizeof(double) * forcing.size(), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  p->pvec = dptr;
+  return B200_OK;
+}
+
+int32_t ensure_fd_scratch(b200_problem* p, int copies) {
+  if (!p->fd_scratch) CUDA_TRY(p->ctx, cudaMalloc(&p->fd_scratch, sizeof(double) * p->n * 2));
+  (void)copies;
+  return B200_OK;
+}
+}  // namespace
+
+extern "C" {
+int32_t b200_problem_create_bruss2d(b200_ctx* ctx, int32_t N, double A, double B, double alpha, b200_problem** prob) {
+  return create_bruss(ctx, 2, N, A, B, alpha, prob);
+}
+int32_t b200_problem_create_bruss3d(b200_ctx* ctx, int32_t N, double A, double B, double alpha, b200_problem** prob) {
+  return create_bruss(ctx, 3, N, A, B, alpha, prob);
+}
+int32_t b200_problem_create_quadratic(b200_ctx* ctx, int64_t n, double p, b200_problem** prob) {
+  B200_REQUIRE(ctx, n > 0, "n must be positive");
+  B200_TRY(create_common(ctx, prob, B200_PROB_QUADRATIC, 0, n));
+  (*prob)->p = p;
+  return B200_OK;
+}
+int32_t b200_problem_create_tridiag_quad(b200_ctx* ctx, int64_t n, const double* p_dev, b200_problem** prob) {
+  B200_REQUIRE(ctx, n > 0 && p_dev, "n must be positive and p_dev non-null");
+  B200_TRY(create_common(ctx, prob, B200_PROB_TRIDIAG_QUAD, 0, n));
+  double* copy = nullptr;
+  CUDA_TRY(ctx, cudaMalloc(&copy, sizeof(double) * n));
+  CUDA_TRY(ctx, cudaMemcpyAsync(copy, p_dev, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+  (*prob)->pvec = copy;
+  return B200_OK;
+}
+int32_t b200_problem_create_callback(b200_ctx* ctx, int64_t n, b200_residual_cb f, b200_jvp_cb jvp, b200_jvp_cb vjp, void* user,
+                                     b200_problem** prob) {
+  B200_REQUIRE(ctx, n > 0 && f, "callback problem needs n > 0 and a residual callback");
+  B200_TRY(create_common(ctx, prob, B200_PROB_CALLBACK, 0, n));
+  (*prob)->f_cb = f;
+  (*prob)->jvp_cb = jvp;
+  (*prob)->vjp_cb = vjp;
+  (*prob)->user = user;
+  return B200_OK;
+}
+int32_t b200_problem_destroy(b200_problem* p) {
+  if (!p) return B200_OK;
+  cudaStreamSynchronize(p->ctx->stream);
+  if (p->kind != B200_PROB_CALLBACK && p->pvec) cudaFree(const_cast<double*>(p->pvec));
+  if (p->fd_scratch) cudaFree(p->fd_scratch);
+  delete p;
+  return B200_OK;
+}
+int32_t b200_problem_n(b200_problem* p, int64_t* n) { *n = p->n; return B200_OK; }
+int32_t b200_problem_set_AB(b200_problem* p, double A, double B) { p->A = A; p->B = B; return B200_OK; }
+
+int32_t b200_problem_u0(b200_problem* p, int32_t mode, double* u) {
+  b200_ctx* ctx = p->ctx;
+  if (p->kind == B200_PROB_BRUSS2D || p->kind == B200_PROB_BRUSS3D) {
+    const int dim = p->kind == B200_PROB_BRUSS2D ? 2 : 3;
+    LAUNCH(ctx, bruss_u0_kernel, grid_for(p->n / 2), PB_THREADS, 0, dim, p->N, mode, u);
+    CHECK_LAUNCH(ctx);
+    return B200_OK;
+  }
+  return b200_fill(ctx, p->n, 1.0, u);
+}
+
+int32_t b200_residual(b200_problem* p, const double* u, double* du) { return b200i_residual_norm(p, u, du, nullptr); }
+
+int32_t b200_jvp(b200_problem* p, const double* u, const double* v, double* Jv) {
+  b200_ctx* ctx = p->ctx;
+  switch (p->kind) {
+    case B200_PROB_BRUSS2D:
+    case B200_PROB_BRUSS3D: return launch_bruss<M_JVP>(p, u, v, nullptr, Jv, nullptr, nullptr);
+    case B200_PROB_QUADRATIC:
+    case B200_PROB_TRIDIAG_QUAD:
+      LAUNCH(ctx, small_problem_kernel, grid_for(p->n), PB_THREADS, 0, p->kind == B200_PROB_QUADRATIC ? 0 : 1, (int)M_JVP, p->n, p->p,
+             p->pvec, u, v, Jv, nullptr);
+      CHECK_LAUNCH(ctx);
+      return B200_OK;
+    case B200_PROB_CALLBACK:
+      if (p->jvp_cb) return p->jvp_cb(p->user, u, v, Jv) == 0 ? B200_OK : ctx->fail(B200_ERR_CALLBACK, "jvp callback failed", __FILE__, __LINE__);
+      return b200_jvp_fd(p, u, v, Jv);  // no jvp supplied: AutoFiniteDiff fallback (autodiff.jl:52-84 last resort)
+  }
+  return ctx->fail(B200_ERR_INVALID, "unknown problem kind", __FILE__, __LINE__);
+}
+
+int32_t b200_vjp(b200_problem* p, const double* u, const double* w, double* JTw) {
+  b200_ctx* ctx = p->ctx;
+  switch (p->kind) {
+    case B200_PROB_BRUSS2D:
+    case B200_PROB_BRUSS3D: return launch_bruss<M_VJP>(p, u, w, nullptr, JTw, nullptr, nullptr);
+    case B200_PROB_QUADRATIC:
+    case B200_PROB_TRIDIAG_QUAD:
+      LAUNCH(ctx, small_problem_kernel, grid_for(p->n), PB_THREADS, 0, p->kind == B200_PROB_QUADRATIC ? 0 : 1, (int)M_VJP, p->n, p->p,
+             p->pvec, u, w, JTw, nullptr);
+      CHECK_LAUNCH(ctx);
+      return B200_OK;
+    case B200_PROB_CALLBACK:
+      if (p->vjp_cb) return p->vjp_cb(p->user, u, w, JTw) == 0 ? B200_OK : ctx->fail(B200_ERR_CALLBACK, "vjp callback failed", __FILE__, __LINE__);
+      return ctx->fail(B200_ERR_UNSUPPORTED, "callback problem has no vjp", __FILE__, __LINE__);
+  }
+  return ctx->fail(B200_ERR_INVALID, "unknown problem kind", __FILE__, __LINE__);
+}
+
+int32_t b200_residual_jvp(b200_problem* p, const double* u, const double* v, double* du, double* Jv) {
+  if (p->kind == B200_PROB_BRUSS2D || p->kind == B200_PROB_BRUSS3D) return launch_bruss<M_RESID | M_JVP>(p, u, v, du, Jv, nullptr, nullptr);
+  B200_TRY(b200_residual(p, u, du));
+  return b200_jvp(p, u, v, Jv);
+}
+
+// (f(u + eps v) - f(u)) / eps with FiniteDiff.jl's forward step; for the stencils both evaluations share one neighbourhood load.
+int32_t b200_jvp_fd(b200_problem* p, const double* u, const double* v, double* Jv) {
+  b200_ctx* ctx = p->ctx;
+  double* d_dot = ctx->d_scalars + 8;
+  double* d_eps = ctx->d_scalars + 9;
+  B200_TRY(b200i_reduce_sum_dev(ctx, p->n, u, v, RED_DOT, d_dot));
+  LAUNCH(ctx, fd_eps_kernel, 1, 1, 0, d_dot, d_eps);
+  if (p->kind == B200_PROB_BRUSS2D || p->kind == B200_PROB_BRUSS3D) return launch_bruss<M_FD>(p, u, v, nullptr, Jv, nullptr, d_eps);
+  B200_TRY(ensure_fd_scratch(p, 2));
+  double* x1 = p->fd_scratch;
+  double* f0 = p->fd_scratch + p->n;
+  const int g = grid_for(p->n) > 2048 ? 2048 : grid_for(p->n);
+  LAUNCH(ctx, fd_perturb_kernel, g, PB_THREADS, 0, p->n, d_eps, u, v, x1);
+  B200_TRY(b200_residual(p, u, f0));
+  B200_TRY(b200_residual(p, x1, Jv));
+  LAUNCH(ctx, fd_combine_kernel, g, PB_THREADS, 0, p->n, d_eps, Jv, f0, Jv);
+  CHECK_LAUNCH(ctx);
+  return B200_OK;
+}
+}  // extern "C"
+
+// residual with the ||f||_inf epilogue fused (K1 + K6: `evaluate_f!` utils.jl:200-207 + `maximum(abs, fu)` common_defaults.jl:37)
+int32_t b200i_residual_norm(b200_problem* p, const double* u, double* du, double* d_norminf) {
+  b200_ctx* ctx = p->ctx;
+  switch (p->kind) {
+    case B200_PROB_BRUSS2D:
+    case B200_PROB_BRUSS3D:
+      return d_norminf ? launch_bruss<M_RESID | M_NORM>(p, u, nullptr, du, nullptr, d_norminf, nullptr)
+                       : launch_bruss<M_RESID>(p, u, nullptr, du, nullptr, nullptr, nullptr);
+    case B200_PROB_QUADRATIC:
+    case B200_PROB_TRIDIAG_QUAD:
+      LAUNCH(ctx, small_problem_kernel, grid_for(p->n), PB_THREADS, 0, p->kind == B200_PROB_QUADRATIC ? 0 : 1,
+             (int)(M_RESID | (d_norminf ? M_NORM : 0)), p->n, p->p, p->pvec, u, (const double*)nullptr, du, d_norminf);
+      CHECK_LAUNCH(ctx);
+      return B200_OK;
+    case B200_PROB_CALLBACK:
+      if (p->f_cb(p->user, u, du) != 0) return ctx->fail(B200_ERR_CALLBACK, "residual callback failed", __FILE__, __LINE__);
+      if (d_norminf) return b200i_reduce_sum_dev(ctx, p->n, du, nullptr, RED_MAXABS, d_norminf);
+      return B200_OK;
+  }
+  return ctx->fail(B200_ERR_INVALID, "unknown problem kind", __FILE__, __LINE__);
+}

@@ -1,0 +1,43 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with `-m gpu`)")
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built():
+    """Build the CUDA library and the oracle once per session (no-ops when up to date)."""
+    import __graft_entry__ as g
+    g.build()
+
+
+@pytest.fixture(scope="session")
+def golden():
+    return dict(np.load(os.path.join(ROOT, "tests", "golden", "brusselator_golden.npz")))
+
+
+@pytest.fixture(scope="session")
+def po():
+    from oracle import pyoracle
+    return pyoracle
+
+
+@pytest.fixture(scope="session")
+def nls():
+    import nonlinearsolve_jl_b200 as m
+    return m
+
+
+@pytest.fixture(scope="session")
+def ctx(nls):
+    """A library context on cuda:0; GPU tests only.  Raises (never falls back) when there is no device."""
+    return nls.Context(0)
