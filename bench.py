@@ -1,0 +1,296 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200 Newton iteration core.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--N 100]
+
+Workload (BASELINE.json configs[2], the configuration the metric is quoted on): 3D Brusselator N=100 (10^6 cells, 2*10^6
+unknowns), NewtonRaphson(linsolve = KrylovJL_GMRES()) with the matrix-free exact JVP, abstol = 1e-8 (the reference
+test's value, sparsity_tests__item1.jl:54), GMRES tolerances inherited from the nonlinear solve (solve.jl:203).
+One "step" = one complete Newton solve from the synthetic initial condition (3 Newton iterations, ~2000 Arnoldi
+iterations): a fixed, deterministic amount of hot-path work.  `value` = GMRES JVPs (Arnoldi iterations) per second with
+inputs resident in HBM; `e2e` = the same through the host-buffer call (H2D of u0, solve, D2H of u and resid inside the
+timed region).  N > 1: the single large system does not shard ("replicas only"): every rank solves its own
+replica, value = total JVPs of all ranks / max-over-ranks time ("weak").
+
+The JSON line also carries `roofline` (dominant kernel family, live CUDA-event timing inside the timed region),
+`cpu_baseline` (the CPU oracle timed on the host cores on a bounded sample) and `clocks`.
+`--impl reference` times the CPU restatement of the reference (oracle/, "port": the Julia reference cannot run here).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "gmres_jvps_per_s"
+UNIT = "JVP/s"
+MEAN_BASIS = {100: 345, 64: 217, 32: 107}  # mean Krylov basis size over one solve (measured)
+
+
+def workload_name(N):
+    return "bruss3d_N%d_newtonraphson_gmres_jfnk_abstol1e-8" % N
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+            "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for nm, val in zip(names, r[4:8]):
+                    if val.lower().startswith("active"):
+                        reasons.add(nm)
+            except (ValueError, IndexError):
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def host_cpus():
+    """Usable host cores: scheduler affinity capped by the cgroup CPU quota."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = max(1, min(n, int(float(q) / float(p))))
+    except (OSError, ValueError):
+        pass
+    return n
+
+
+_CPU_THREADS = {}
+
+
+def cpu_sample(N, steps, count):
+    """Time the CPU oracle on a bounded sample of the workload: `count` Arnoldi iterations (exact JVP + CGS2
+    orthogonalisation, the same arithmetic as the GPU arm) at the workload's mean Krylov basis size, using the thread
+    count (all usable cores, or half / a quarter of them when SMT or memory-bandwidth saturation makes that faster)
+    that a one-iteration calibration finds best."""
+    os.environ.setdefault("OMP_WAIT_POLICY", "passive")
+    os.environ.setdefault("OMP_PROC_BIND", "false")
+    from oracle import pyoracle as po
+    po.build()
+    P = po.OracleProblem.bruss3d(N)
+    u = P.u0(1)
+    k0 = MEAN_BASIS.get(N, max(8, int(3.45 * N)))
+    if N not in _CPU_THREADS:
+        T = host_cpus()
+        best = None
+        for cand in sorted({T, max(1, T // 2), max(1, T // 4)}, reverse=True):
+            po.set_threads(cand)
+            t = po.arnoldi_sample(P, u, k0, 1, po.ORTH_CGS2)
+            if best is None or t < best[0]:
+                best = (t, cand)
+        _CPU_THREADS[N] = best[1]
+    po.set_threads(_CPU_THREADS[N])
+    times = []
+    for _ in range(steps):
+        times.append(po.arnoldi_sample(P, u, k0, count, po.ORTH_CGS2))
+    cores = _CPU_THREADS[N]
+    sample = "%d Arnoldi iterations (exact JVP + CGS2 Gram-Schmidt + normalise) at the solve's mean basis size k=%d, N=%d, %d OpenMP threads" % (
+        count, k0, N, cores)
+    return times, cores, sample, k0
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port), bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    count = 4
+    for _ in range(min(args.warmup, 1)):
+        cpu_sample(args.N, 1, 1)
+    times, cores, sample, k0 = cpu_sample(args.N, args.steps, count)
+    total = sum(times)
+    val = args.steps * count / total
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": {"workload": workload_name(args.N), "unknowns": 2 * args.N ** 3},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "CPU restatement of the reference NewtonRaphson+GMRES inner loop (oracle/oracle.c); the Julia reference cannot run in this image"}
+    print(json.dumps(line))
+
+
+def run_b200(args):
+    import numpy as np
+    import torch
+    import nonlinearsolve_jl_b200 as nls
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    stream = torch.cuda.current_stream()
+    ctx = nls.Context(local_rank, stream=stream.cuda_stream)
+    N = args.N
+    f = nls.Brusselator3D(N)
+    n = f.n()
+    dp = nls._DeviceProblem(ctx, nls.NonlinearProblem(f, None, (3.4, 1.0, 10.0), ctx=ctx))
+    u0_dev = dp.u0(nls.abi.U0_PERTURBED_Z)  # synthetic, deterministic
+    u0_pinned = ctx.pinned_empty(n)
+    u0_pinned[:] = u0_dev.to_host()
+    u_out, r_out = ctx.pinned_empty(n), ctx.pinned_empty(n)
+    prob = nls.NonlinearProblem(f, u0_dev, (3.4, 1.0, 10.0), ctx=ctx)
+    alg = nls.NewtonRaphson(linsolve=nls.KrylovJL_GMRES())
+    cache = nls.init(prob, alg, abstol=1e-8, store_trace=True)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step():
+        cache.reinit(u0_dev)
+        return cache.solve(to_host=False)
+
+    for _ in range(args.warmup):
+        sol = one_step()
+    # ---- device-resident timed region
+    clocks = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        clocks.start()
+    ctx.profile(True)
+    l0 = ctx.kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    njvp = nsteps = 0
+    bytes_moved = 0.0
+    for _ in range(args.steps):
+        sol = one_step()
+        njvp += sol.stats.njvp
+        nsteps += sol.stats.nsteps
+        bytes_moved += sol.bytes_moved
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    ms_local = ms
+    launches = ctx.kernel_launches() - l0
+    prof = ctx.profile_report()
+    ctx.profile(False, reset=False)
+    clk = clocks.stop() if rank == 0 else None
+    assert sol.retcode == nls.ReturnCode.Success and sol.resid_inf < 1e-8, (sol.retcode, sol.resid_inf)
+    # ---- end-to-end timed region: host buffers, H2D + D2H inside
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record(stream)
+    njvp_e2e = 0
+    for _ in range(args.steps):
+        s2 = cache.solve_host(u0_pinned, u_out, r_out)
+        njvp_e2e += s2.stats.njvp
+    e3.record(stream)
+    barrier()
+    ms_e2e = e2.elapsed_time(e3)
+    assert np.abs(r_out).max() < 1e-8
+    # ---- max over ranks, totals over ranks
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
+    c = torch.tensor([njvp, nsteps, njvp_e2e, launches], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+    ms, ms_e2e = t.tolist()
+    njvp_all, nsteps_all, njvp_e2e_all, launches_all = c.tolist()
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = peaks()
+    # dominant kernel family = the Gram-Schmidt streaming pair (multi-dot + update), timed live with CUDA events
+    dom_ms = sum(prof[k]["ms"] for k in ("multidot", "update") if k in prof)
+    dom_bytes = sum(prof[k]["bytes"] for k in ("multidot", "update") if k in prof)
+    dom_launches = sum(prof[k]["launches"] for k in ("multidot", "update") if k in prof)
+    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "gmres CGS2 orthogonalisation: multidot_kernel + update_kernel", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+                "bytes_per_launch": dom_bytes / max(dom_launches, 1), "ms_per_launch": dom_ms / max(dom_launches, 1),
+                "share_of_step": dom_ms / (ms_local if ms_local > 0 else 1.0),
+                "whole_step_gbs": bytes_moved / (ms * 1e-3) / 1e9,
+                "families": {k: {"gbs": round(v["gbs"], 1), "ms": round(v["ms"], 2), "launches": v["launches"]} for k, v in prof.items()}}
+    count = 4
+    times, cores, sample, k0 = cpu_sample(N, 1, count)
+    cpu_val = count / sum(times)
+    value = njvp_all / (ms * 1e-3)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": workload_name(N), "unknowns": n, "cells": N ** 3, "step": "one full Newton solve (%d Newton iterations, %d Arnoldi iterations)" % (
+                nsteps // args.steps, njvp // args.steps), "orth": "cgs2", "parallelism": "replicas x%d (single system does not shard)" % world,
+                "l2": "inputs_exceed_l2 (Krylov basis %.1f GB per solve)" % (max(t_.lin_iters for t_ in sol.trace) * 8.0 * n / 1e9)},
+            "newton_steps_per_s": nsteps_all / (ms * 1e-3),
+            "e2e": {"value": njvp_e2e_all / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 16 * n,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches_all),
+            "roofline": roofline,
+            "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "clocks": clk,
+            "resid_inf": sol.resid_inf, "retcode": nls.ReturnCode.name(sol.retcode)}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--N", type=int, default=100)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -28,6 +28,7 @@ FORCING_NONE, FORCING_EW2 = 0, 1
 TERM_ABS_NORM_SAFE_BEST, TERM_ABS_NORM, TERM_ABS_NORM_SAFE = 0, 1, 2
 U0_REFERENCE, U0_PERTURBED_Z = 0, 1
 ORDER_NATURAL, ORDER_LARGEST_FIRST = 0, 1
+KID_NAMES = ["jvp", "multidot", "update", "mgs", "normalize", "residual", "givens", "resident"]
 
 
 class GmresOpts(C.Structure):
@@ -88,6 +89,9 @@ SIGNATURES = {
     "b200_last_error": (C.c_char_p, [P]),
     "b200_ctx_kernel_launches": (I32, [P, PI64]),
     "b200_ctx_sm_count": (I32, [P, PI32]),
+    "b200_ctx_profile_enable": (I32, [P, I32]),
+    "b200_ctx_profile_reset": (I32, [P]),
+    "b200_ctx_profile_get": (I32, [P, I32, PF64, PF64, PI64]),
     "b200_malloc": (I32, [P, SZ, PP]),
     "b200_free": (I32, [P, P]),
     "b200_host_alloc": (I32, [P, SZ, PP]),

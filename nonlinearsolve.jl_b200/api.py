@@ -62,6 +62,34 @@ class Context:
     def flush_l2(self):
         check(self._h, lib().b200_flush_l2(self._h))
 
+    def profile(self, on=True, reset=True):
+        """Enable/disable per-kernel-family CUDA-event timing on the context stream."""
+        if reset:
+            check(self._h, lib().b200_ctx_profile_reset(self._h))
+        check(self._h, lib().b200_ctx_profile_enable(self._h, 1 if on else 0))
+
+    def profile_report(self):
+        """{family: {"ms", "bytes", "launches", "gbs"}} accumulated since the last reset."""
+        out = {}
+        for kid, name in enumerate(abi.KID_NAMES):
+            ms, by, ln = C.c_double(), C.c_double(), C.c_int64()
+            check(self._h, lib().b200_ctx_profile_get(self._h, kid, C.byref(ms), C.byref(by), C.byref(ln)))
+            if ln.value:
+                out[name] = {"ms": ms.value, "bytes": by.value, "launches": ln.value,
+                             "gbs": (by.value / (ms.value * 1e-3) / 1e9) if ms.value > 0 else 0.0}
+        return out
+
+    def pinned_empty(self, n, dtype=np.float64):
+        """A NumPy view of pinned host memory (b200_host_alloc) for the end-to-end host-buffer path."""
+        dt = np.dtype(dtype)
+        p = C.c_void_p()
+        check(self._h, lib().b200_host_alloc(self._h, int(n) * dt.itemsize, C.byref(p)))
+        buf = (C.c_char * (int(n) * dt.itemsize)).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=dt)
+        self._pinned = getattr(self, "_pinned", [])
+        self._pinned.append((p, buf))
+        return arr
+
     # memory
     def empty(self, n, dtype=np.float64):
         return DeviceVector(self, int(n), dtype)

@@ -22,8 +22,26 @@ struct b200_ctx {
   double* h_scalars = nullptr;   // pinned, 64 doubles
   void* l2_flush = nullptr;
   size_t l2_flush_bytes = 0;
+  // optional per-kernel-family event timing (b200_ctx_profile_*)
+  bool prof_on = false;
+  struct ProfSlot { double ms = 0, bytes = 0; int64_t launches = 0; } prof[B200_KID_COUNT];
+  struct ProfPending { int kid; double bytes; cudaEvent_t a, b; };
+  std::vector<ProfPending> prof_pending;
+  std::vector<cudaEvent_t> prof_free;
+  void prof_begin(int kid, double bytes);
+  void prof_end();
+  void prof_collect();
   int32_t fail(int32_t code, const char* what, const char* file, int line);
 };
+
+// timed launch: like LAUNCH, bracketed by events when profiling is on
+#define PLAUNCH(ctx, kid, bytes, kernel, grid, block, smem, ...)                        \
+  do {                                                                                  \
+    if ((ctx)->prof_on) (ctx)->prof_begin((kid), (bytes));                              \
+    kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                    \
+    (ctx)->launches++;                                                                  \
+    if ((ctx)->prof_on) (ctx)->prof_end();                                              \
+  } while (0)
 
 #define B200_RED_MAX_BLOCKS 2048
 enum { RED_DOT = 0, RED_SUMSQ = 1, RED_MAXABS = 2, RED_DIFFSQ = 3, RED_MIN = 4, RED_MAX = 5, RED_NEQ = 6 };

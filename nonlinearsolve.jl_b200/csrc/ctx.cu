@@ -10,9 +10,59 @@ int32_t b200_ctx::fail(int32_t code, const char* what, const char* file, int lin
   return code;
 }
 
+void b200_ctx::prof_begin(int kid, double bytes) {
+  ProfPending p;
+  p.kid = kid;
+  p.bytes = bytes;
+  for (cudaEvent_t* e : {&p.a, &p.b}) {
+    if (!prof_free.empty()) { *e = prof_free.back(); prof_free.pop_back(); }
+    else cudaEventCreate(e);
+  }
+  cudaEventRecord(p.a, stream);
+  prof_pending.push_back(p);
+}
+void b200_ctx::prof_end() {
+  cudaEventRecord(prof_pending.back().b, stream);
+  if (prof_pending.size() >= 32768) prof_collect();
+}
+void b200_ctx::prof_collect() {
+  if (prof_pending.empty()) return;
+  cudaStreamSynchronize(stream);
+  for (ProfPending& p : prof_pending) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+      prof[p.kid].ms += ms;
+      prof[p.kid].bytes += p.bytes;
+      prof[p.kid].launches += 1;
+    }
+    prof_free.push_back(p.a);
+    prof_free.push_back(p.b);
+  }
+  prof_pending.clear();
+}
+
 extern "C" {
 
 int32_t b200_version(void) { return B200_VERSION; }
+
+int32_t b200_ctx_profile_enable(b200_ctx* ctx, int32_t on) {
+  ctx->prof_collect();
+  ctx->prof_on = on != 0;
+  return B200_OK;
+}
+int32_t b200_ctx_profile_reset(b200_ctx* ctx) {
+  ctx->prof_collect();
+  for (auto& s : ctx->prof) s = b200_ctx::ProfSlot();
+  return B200_OK;
+}
+int32_t b200_ctx_profile_get(b200_ctx* ctx, int32_t kid, double* ms, double* bytes, int64_t* launches) {
+  if (kid < 0 || kid >= B200_KID_COUNT) return ctx->fail(B200_ERR_INVALID, "bad kernel id", __FILE__, __LINE__);
+  ctx->prof_collect();
+  if (ms) *ms = ctx->prof[kid].ms;
+  if (bytes) *bytes = ctx->prof[kid].bytes;
+  if (launches) *launches = ctx->prof[kid].launches;
+  return B200_OK;
+}
 
 int32_t b200_device_count(int32_t* count) {
   int c = 0;

@@ -701,31 +701,31 @@ int32_t b200_gmres_solve(b200_gmres* gm, b200_linop* op, const double* b, double
       if (orth == B200_ORTH_MGS) {
         double* pin = gm->d_norm_partial;
         double* pout = gm->d_norm_partial2;
-        LAUNCH(ctx, mgs_pass_kernel, G, GM_THREADS, 0, gm->d_state, (const double*)nullptr, (const double*)gm->V[0], -1, pin, pout, gm->d_h,
+        PLAUNCH(ctx, B200_KID_MGS, 2.0 * Bv, mgs_pass_kernel, G, GM_THREADS, 0, gm->d_state, (const double*)nullptr, (const double*)gm->V[0], -1, pin, pout, gm->d_h,
                gm->w, n);
         for (int i = 0; i < k; ++i) {
           std::swap(pin, pout);
-          LAUNCH(ctx, mgs_pass_kernel, G, GM_THREADS, 0, gm->d_state, (const double*)gm->V[i],
+          PLAUNCH(ctx, B200_KID_MGS, 4.0 * Bv, mgs_pass_kernel, G, GM_THREADS, 0, gm->d_state, (const double*)gm->V[i],
                  (const double*)(i + 1 < k ? gm->V[i + 1] : nullptr), i, pin, pout, gm->d_h, gm->w, n);
         }
-        LAUNCH(ctx, givens_kernel, 1, GM_THREADS, 0, gm->d_state, k, G, pout, gm->d_h, gm->d_R, gm->d_cs, gm->d_sn, gm->d_z,
+        PLAUNCH(ctx, B200_KID_GIVENS, 0.0, givens_kernel, 1, GM_THREADS, 0, gm->d_state, k, G, pout, gm->d_h, gm->d_R, gm->d_cs, gm->d_sn, gm->d_z,
                (gm->d_hraw && (int64_t)k * (k + 3) / 2 <= gm->hraw_cap) ? gm->d_hraw : nullptr);
       } else {
         const size_t shm = sizeof(double) * (k + 32);
-        LAUNCH(ctx, multidot_kernel, G, GM_THREADS, 0, gm->d_state, (const double* const*)gm->d_Vptrs, k, gm->w, n, gm->d_partial);
+        PLAUNCH(ctx, B200_KID_MULTIDOT, (k + 1.0) * Bv, multidot_kernel, G, GM_THREADS, 0, gm->d_state, (const double* const*)gm->d_Vptrs, k, gm->w, n, gm->d_partial);
         LAUNCH(ctx, reduce_h_kernel, (k + 7) / 8, GM_THREADS, 0, gm->d_state, k, G, gm->d_partial, gm->d_h, (double*)nullptr);
-        LAUNCH(ctx, update_kernel, G, GM_THREADS, shm, gm->d_state, 0, (const double* const*)gm->d_Vptrs, k, gm->d_h, -1.0, gm->w, gm->w, n,
+        PLAUNCH(ctx, B200_KID_UPDATE, (k + 2.0) * Bv, update_kernel, G, GM_THREADS, shm, gm->d_state, 0, (const double* const*)gm->d_Vptrs, k, gm->d_h, -1.0, gm->w, gm->w, n,
                gm->d_norm_partial);
         if (orth == B200_ORTH_CGS2) {
-          LAUNCH(ctx, multidot_kernel, G, GM_THREADS, 0, gm->d_state, (const double* const*)gm->d_Vptrs, k, gm->w, n, gm->d_partial);
+          PLAUNCH(ctx, B200_KID_MULTIDOT, (k + 1.0) * Bv, multidot_kernel, G, GM_THREADS, 0, gm->d_state, (const double* const*)gm->d_Vptrs, k, gm->w, n, gm->d_partial);
           LAUNCH(ctx, reduce_h_kernel, (k + 7) / 8, GM_THREADS, 0, gm->d_state, k, G, gm->d_partial, gm->d_hacc, gm->d_h);
-          LAUNCH(ctx, update_kernel, G, GM_THREADS, shm, gm->d_state, 0, (const double* const*)gm->d_Vptrs, k, gm->d_hacc, -1.0, gm->w,
+          PLAUNCH(ctx, B200_KID_UPDATE, (k + 2.0) * Bv, update_kernel, G, GM_THREADS, shm, gm->d_state, 0, (const double* const*)gm->d_Vptrs, k, gm->d_hacc, -1.0, gm->w,
                  gm->w, n, gm->d_norm_partial);
         }
-        LAUNCH(ctx, givens_kernel, 1, GM_THREADS, 0, gm->d_state, k, G, gm->d_norm_partial, gm->d_h, gm->d_R, gm->d_cs, gm->d_sn, gm->d_z,
+        PLAUNCH(ctx, B200_KID_GIVENS, 0.0, givens_kernel, 1, GM_THREADS, 0, gm->d_state, k, G, gm->d_norm_partial, gm->d_h, gm->d_R, gm->d_cs, gm->d_sn, gm->d_z,
                (gm->d_hraw && (int64_t)k * (k + 3) / 2 <= gm->hraw_cap) ? gm->d_hraw : nullptr);
       }
-      LAUNCH(ctx, normalize_kernel, ew_grid, GM_THREADS, 0, gm->d_state, 1, gm->w, gm->V[k], n);
+      PLAUNCH(ctx, B200_KID_NORMALIZE, 2.0 * Bv, normalize_kernel, ew_grid, GM_THREADS, 0, gm->d_state, 1, gm->w, gm->V[k], n);
       CHECK_LAUNCH(ctx);
       const bool must_check = (k % check_every == 0) || (iters_total + k >= itmax) || (restart_len > 0 && k >= restart_len);
       if (must_check) {
@@ -749,7 +749,7 @@ int32_t b200_gmres_solve(b200_gmres* gm, b200_linop* op, const double* b, double
     // x += V_k y
     if (k > 0 && cycle_status != B200_LS_NONFINITE) {
       LAUNCH(ctx, backsolve_kernel, 1, GM_THREADS, sizeof(double) * (k + 1), gm->d_state, gm->d_R, gm->d_z, gm->d_y, gm->kcap);
-      LAUNCH(ctx, update_kernel, G, GM_THREADS, sizeof(double) * (k + 32), gm->d_state, 1, (const double* const*)gm->d_Vptrs, k, gm->d_y, 1.0,
+      PLAUNCH(ctx, B200_KID_UPDATE, (k + 2.0) * Bv, update_kernel, G, GM_THREADS, sizeof(double) * (k + 32), gm->d_state, 1, (const double* const*)gm->d_Vptrs, k, gm->d_y, 1.0,
              x, x, n, (double*)nullptr);
       CHECK_LAUNCH(ctx);
       bytes += (k + 2.0) * Bv;

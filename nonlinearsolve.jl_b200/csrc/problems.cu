@@ -246,10 +246,13 @@ int32_t launch_bruss(b200_problem* p, const double* u, const double* d, double* 
   b200_ctx* ctx = p->ctx;
   BrussParams P{p->N, p->a, p->A, p->B};
   const double* forcing = p->pvec;
+  // algorithmic bytes: residual 2 Bv, JVP/VJP/FD-JVP 3 Bv, fused residual+JVP 4 Bv
+  const int kid = (MODE & M_RESID) && !(MODE & (M_JVP | M_VJP)) ? B200_KID_RESIDUAL : B200_KID_JVP;
+  const double pbytes = 8.0 * (double)p->n * (((MODE & M_RESID) ? 2.0 : 0.0) + ((MODE & (M_JVP | M_VJP | M_FD)) ? ((MODE & M_RESID) ? 2.0 : 3.0) : 0.0));
   if (p->kind == B200_PROB_BRUSS2D) {
-    LAUNCH(ctx, (bruss2d_kernel<MODE>), grid_for((int64_t)p->N * p->N), PB_THREADS, 0, P, u, d, forcing, du, Jd, norm_out, eps);
+    PLAUNCH(ctx, kid, pbytes, (bruss2d_kernel<MODE>), grid_for((int64_t)p->N * p->N), PB_THREADS, 0, P, u, d, forcing, du, Jd, norm_out, eps);
   } else {
-    LAUNCH(ctx, (bruss3d_kernel<MODE>), grid_for((int64_t)p->N * p->N * p->N), PB_THREADS, 0, P, u, d, forcing, du, Jd, norm_out, eps);
+    PLAUNCH(ctx, kid, pbytes, (bruss3d_kernel<MODE>), grid_for((int64_t)p->N * p->N * p->N), PB_THREADS, 0, P, u, d, forcing, du, Jd, norm_out, eps);
   }
   CHECK_LAUNCH(ctx);
   return B200_OK;

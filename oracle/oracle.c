@@ -982,3 +982,60 @@ void orc_ensemble_solve(int32_t N, int32_t nprob, double alpha, const double* u0
     }
   }
 }
+
+/* ------------------------------------------------------------------ timed CPU sample for bench.py (cpu_baseline / --impl reference)
+ * `count` Arnoldi iterations of the reference's inner loop (operator apply + Gram-Schmidt against the current basis +
+ * normalise + append) starting from a basis of k0 vectors.  The k0 start vectors are pseudo-random unit vectors rather than
+ * a true Krylov basis: the arithmetic and memory traffic per iteration are identical, which is all a throughput sample
+ * needs, and it avoids spending minutes of CPU time building the first k0 Krylov vectors.  Returns seconds in *seconds. */
+int32_t orc_arnoldi_sample(const orc_problem* p, const double* u, int32_t k0, int32_t count, int32_t orth, double* seconds) {
+  const int64_t n = p->n;
+  const int64_t kmax = (int64_t)k0 + count + 1;
+  double** V = (double**)calloc((size_t)kmax, sizeof(double*));
+  double* w = (double*)malloc((size_t)n * 8);
+  double* h = (double*)malloc((size_t)kmax * 8);
+  if (!V || !w || !h) return -1;
+  for (int64_t c = 0; c <= k0; ++c) {
+    V[c] = (double*)malloc((size_t)n * 8);
+    if (!V[c]) return -1;
+    const double s = 1.0 / sqrt((double)n / 3.0);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+      uint64_t x = (uint64_t)(i + 1) * 0x9E3779B97F4A7C15ull + (uint64_t)(c + 1) * 0xBF58476D1CE4E5B9ull;
+      x ^= x >> 31; x *= 0x94D049BB133111EBull; x ^= x >> 29;
+      V[c][i] = (((double)(x >> 11) / 9007199254740992.0) * 2.0 - 1.0) * s;
+    }
+  }
+#ifdef _OPENMP
+  double t0 = omp_get_wtime();
+#else
+  double t0 = 0.0;
+#endif
+  for (int32_t it = 0; it < count; ++it) {
+    const int64_t k = (int64_t)k0 + it + 1; /* basis vectors V[0..k-1] */
+    orc_jvp(p, u, V[k - 1], w);
+    if (orth == B200_ORTH_MGS) {
+      for (int64_t i = 0; i < k; ++i) { h[i] = v_dot(n, V[i], w); v_axpy(n, -h[i], V[i], w); }
+    } else {
+      const int passes = (orth == B200_ORTH_CGS2) ? 2 : 1;
+      for (int ps = 0; ps < passes; ++ps) {
+        for (int64_t i = 0; i < k; ++i) h[i] = v_dot(n, V[i], w);
+        for (int64_t i = 0; i < k; ++i) v_axpy(n, -h[i], V[i], w);
+      }
+    }
+    const double nw = v_nrm2(n, w);
+    V[k] = (double*)malloc((size_t)n * 8);
+    if (!V[k]) return -1;
+    const double inv = nw > 0 ? 1.0 / nw : 0.0;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) V[k][i] = w[i] * inv;
+  }
+#ifdef _OPENMP
+  *seconds = omp_get_wtime() - t0;
+#else
+  *seconds = 0.0;
+#endif
+  for (int64_t c = 0; c < kmax; ++c) free(V[c]);
+  free(V); free(w); free(h);
+  return 0;
+}

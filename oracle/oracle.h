@@ -91,6 +91,9 @@ void orc_ensemble_solve(int32_t N, int32_t nprob, double alpha, const double* u0
                         const b200_newton_opts* opts, double* u_out, double* resid_inf, int32_t* retcodes, int32_t* nsteps,
                         int32_t* njvp, b200_ens_result* result);
 
+/* bench helper: time `count` Arnoldi iterations starting from a k0-vector basis (see oracle.c) */
+int32_t orc_arnoldi_sample(const orc_problem* p, const double* u, int32_t k0, int32_t count, int32_t orth, double* seconds);
+
 #ifdef __cplusplus
 }
 #endif

@@ -226,6 +226,16 @@ class OracleProblem:
         return u, fu, res, [tr[i] for i in range(res.ntrace)]
 
 
+def arnoldi_sample(prob, u, k0, count, orth=ORTH_CGS2):
+    """Seconds for `count` Arnoldi iterations at basis size k0 (bench.py's CPU baseline sample)."""
+    u = _f64(u)
+    sec = C.c_double()
+    rc = lib().orc_arnoldi_sample(C.byref(prob.c), _p(u), C.c_int32(k0), C.c_int32(count), C.c_int32(orth), C.byref(sec))
+    if rc != 0:
+        raise MemoryError("orc_arnoldi_sample: allocation failed")
+    return sec.value
+
+
 def coloring_column(n, colptr, rowval, index_base=1, order=ORDER_LARGEST_FIRST):
     colors = np.empty(n, dtype=np.int64)
     nc = C.c_int64(0)
