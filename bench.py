@@ -155,6 +155,62 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def ensemble_params(K):
+    """BASELINE config 5 / SURVEY.md §8d: trajectory m is the 2D N=32 Brusselator with its own (A_m, B_m)."""
+    import numpy as np
+    m = np.arange(K)
+    return 3.4 + 0.1 * (m % 64) / 64.0, 1.0 + 0.05 * (m // 64) / 128.0
+
+
+def run_ensemble(nls, torch, dist, ctx, rank, world, K_total=8192, N=32, reps=2):
+    """Config 5: ensemble of K_total independent 2D Brusselator problems, contiguous blocks sharded over the ranks
+    (strong scaling, no data-path collective during the solve); after the solve one all-gather of the solutions and one
+    all-reduce of the status counters over NCCL, both inside the timed region."""
+    import numpy as np
+    n = 2 * N * N
+    lo, hi = nls.shard_range(K_total, rank, world)
+    K = hi - lo
+    A, B = ensemble_params(K_total)
+    dp = nls._DeviceProblem(ctx, nls.NonlinearProblem(nls.Brusselator2D(N), None, (3.4, 1.0, 10.0), ctx=ctx))
+    u0 = np.tile(dp.u0().to_host(), K)
+    d_u0, d_A, d_B = ctx.to_device(u0), ctx.to_device(A[lo:hi]), ctx.to_device(B[lo:hi])
+    alg = nls.NewtonRaphson(linsolve=nls.KrylovJL_GMRES(orth="cgs2"))
+    cache = nls.EnsembleCache(ctx, N, K, 10.0, alg, abstol=1e-8)
+    gathered = torch.empty(K_total * n if world > 1 else 0, dtype=torch.float64, device="cuda")
+    u_loc = torch.as_tensor(cache.u_out, device="cuda")
+    stream = torch.cuda.current_stream()
+    times = []
+    res = None
+    for it in range(1 + reps):
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        res = cache.solve(d_u0, d_A, d_B)
+        stats = torch.tensor([res.nsuccess, res.total_nsteps, res.total_njvp, res.worst_resid_inf], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            if K_total % world == 0:
+                dist.all_gather_into_tensor(gathered, u_loc)
+            succ = stats[:3].clone()
+            dist.all_reduce(succ, op=dist.ReduceOp.SUM)
+            worst = stats[3:].clone()
+            dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+            stats = torch.cat([succ, worst])
+        e1.record(stream)
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if it > 0:
+            times.append(t.item())
+    ms = sum(times) / len(times)
+    nsucc, tot_steps, tot_jvp, worst = stats.tolist()
+    return {"workload": "ensemble_%d_x_bruss2d_N%d_newtonraphson_gmres" % (K_total, N), "n_problems": K_total, "scaling": "strong",
+            "problems_per_s": K_total / (ms * 1e-3), "ms": ms, "n_success": int(nsucc), "newton_steps": int(tot_steps), "gmres_jvps": int(tot_jvp),
+            "jvps_per_s": tot_jvp / (ms * 1e-3), "worst_resid_inf": worst, "collectives": "all_gather(u) + all_reduce(stats) via NCCL" if dist is not None else "none (1 rank)"}
+
+
 def run_b200(args):
     import numpy as np
     import torch
@@ -239,6 +295,10 @@ def run_b200(args):
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
     ms, ms_e2e = t.tolist()
     njvp_all, nsteps_all, njvp_e2e_all, launches_all = c.tolist()
+    ens = None
+    if not args.no_ensemble:
+        del cache  # release the Krylov basis before the ensemble workspaces are allocated
+        ens = run_ensemble(nls, torch, dist, ctx, rank, world)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -272,6 +332,7 @@ def run_b200(args):
             "roofline": roofline,
             "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "clocks": clk,
+            "ensemble": ens,
             "resid_inf": sol.resid_inf, "retcode": nls.ReturnCode.name(sol.retcode)}
     print(json.dumps(line))
     if dist is not None:
@@ -285,6 +346,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--N", type=int, default=100)
+    ap.add_argument("--no-ensemble", dest="no_ensemble", action="store_true", help="skip the config-5 ensemble leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -380,6 +380,32 @@ def test_sparse_pattern_coloring_fill(nls, ctx, po, golden, kind, N):
 
 
 # ----------------------------------------------------------------------------- ensemble (a11)
+@pytest.mark.parametrize("N,K,orth", [(32, 40, "cgs2"), (32, 7, "mgs"), (16, 300, "cgs2"), (9, 5, "cgs2")])
+def test_ensemble_batched_vs_oracle(nls, ctx, po, N, K, orth):
+    # BASELINE config 5 at test size: the one-CTA-per-trajectory engine against per-trajectory oracle solves
+    import bench
+    P = po.OracleProblem.bruss2d(N)
+    A, B = bench.ensemble_params(K)
+    u0 = np.tile(P.u0(), (K, 1))
+    u0 *= (1.0 + 0.01 * np.arange(K))[:, None]  # distinct initial conditions too
+    alg = nls.NewtonRaphson(linsolve=nls.KrylovJL_GMRES(orth=orth))
+    cache = nls.EnsembleCache(ctx, N, K, 10.0, alg, abstol=1e-8)
+    res = cache.solve(ctx.to_device(u0.ravel()), ctx.to_device(A), ctx.to_device(B))
+    ocode = po.ORTH_MGS if orth == "mgs" else po.ORTH_CGS2
+    uo, ro, rco, nso, njo, reso = po.ensemble_solve(N, u0, A, B, opts=po.default_newton_opts(abstol=1e-8, gmres_orth=ocode))
+    u = cache.u_out.to_host().reshape(K, -1)
+    assert res.nsuccess == K == reso.nsuccess
+    assert np.array_equal(cache.rc.to_host(), rco) and np.array_equal(cache.ns.to_host(), nso)
+    assert np.abs(u - uo).max() <= RTOL_ROOT * np.abs(uo).max()
+    assert cache.resid.to_host().max() < 1e-8
+    # iteration counts: same algorithm family, reduction order differs -> within a few Arnoldi steps per solve
+    assert np.abs(cache.nj.to_host() - njo).max() <= 6 * nso.max()
+    # residual reported == residual of the returned iterate
+    m = K // 2
+    Pm = po.OracleProblem.bruss2d(N, A=A[m], B=B[m])
+    assert abs(np.abs(Pm.residual(u[m])).max() - cache.resid.to_host()[m]) <= 1e-12 + 1e-6 * cache.resid.to_host()[m]
+
+
 def test_ensemble_small(nls, ctx, po):
     N, K = 8, 6
     P = po.OracleProblem.bruss2d(N)
