@@ -160,7 +160,7 @@ end
 
 # ------------------------------------------------------------------ option structs (bit-compatible with the header)
 struct GmresOpts
-    memory::Int32; restart::Int32; itmax::Int32; orth::Int32; warm_start::Int32; engine::Int32; check_every::Int32; reserved::Int32
+    memory::Int32; restart::Int32; itmax::Int32; orth::Int32; warm_start::Int32; engine::Int32; check_every::Int32; block::Int32
     atol::Float64; rtol::Float64
 end
 struct GmresStats

@@ -33,7 +33,7 @@ KID_NAMES = ["jvp", "multidot", "update", "mgs", "normalize", "residual", "given
 
 class GmresOpts(C.Structure):
     _fields_ = [("memory", C.c_int32), ("restart", C.c_int32), ("itmax", C.c_int32), ("orth", C.c_int32),
-                ("warm_start", C.c_int32), ("engine", C.c_int32), ("check_every", C.c_int32), ("reserved", C.c_int32),
+                ("warm_start", C.c_int32), ("engine", C.c_int32), ("check_every", C.c_int32), ("block", C.c_int32),
                 ("atol", C.c_double), ("rtol", C.c_double)]
 
 

@@ -326,7 +326,8 @@ class KrylovJL_GMRES:
     needs_concrete_A = False
 
     def __init__(self, gmres_restart=0, memory=20, itmax=0, orth="cgs2", warm_start=False, atol=None, rtol=None, check_every=8,
-                 engine="auto"):
+                 engine="auto", block=0):
+        self.block = block  # Gram-Schmidt in L2-sized blocks of this many basis vectors (0: whole basis, -1: automatic)
         self.gmres_restart, self.memory, self.itmax, self.orth = gmres_restart, memory, itmax, orth
         self.warm_start, self.atol, self.rtol, self.check_every, self.engine = warm_start, atol, rtol, check_every, engine
 
@@ -336,6 +337,7 @@ class KrylovJL_GMRES:
         g.warm_start = 1 if self.warm_start else 0
         g.engine = {"auto": abi.ENGINE_AUTO, "multikernel": abi.ENGINE_MULTIKERNEL, "resident": abi.ENGINE_RESIDENT}[self.engine]
         g.check_every = int(self.check_every)
+        g.block = int(self.block)
         g.atol = float(self.atol) if self.atol is not None else 0.0
         g.rtol = float(self.rtol) if self.rtol is not None else 0.0
 

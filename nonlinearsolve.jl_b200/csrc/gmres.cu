@@ -67,6 +67,8 @@ __device__ __forceinline__ void block_rows(int64_t n, int64_t& r0, int64_t& r1) 
 }
 
 // ---- h[c] partials: partial[c * G + blockIdx.x] = sum over this CTA's rows of V[c][r] * w[r]
+//      KEEP = true: the columns are loaded with the default policy so that they stay in L2 for the blocked update sweep.
+template <bool KEEP>
 __global__ void __launch_bounds__(GM_THREADS) multidot_kernel(const GmresState* __restrict__ st, const double* const* __restrict__ V,
                                                                int k, const double* __restrict__ w, int64_t n,
                                                                double* __restrict__ partial) {
@@ -88,7 +90,14 @@ __global__ void __launch_bounds__(GM_THREADS) multidot_kernel(const GmresState* 
         const double2 w2 = *reinterpret_cast<const double2*>(w + r);
         double2 v2[JT];
 #pragma unroll
-        for (int c = 0; c < JT; ++c) v2[c] = __ldcs(reinterpret_cast<const double2*>(vp[c] + r));  // streamed once: evict-first
+        for (int c = 0; c < JT; ++c) {
+          if (KEEP) {
+            if (c0 + c < k) v2[c] = *reinterpret_cast<const double2*>(vp[c] + r);
+            else v2[c] = make_double2(0.0, 0.0);
+          } else {
+            v2[c] = __ldcs(reinterpret_cast<const double2*>(vp[c] + r));  // streamed once: evict-first
+          }
+        }
 #pragma unroll
         for (int c = 0; c < JT; ++c) acc[c] = fma(v2[c].x, w2.x, fma(v2[c].y, w2.y, acc[c]));
       } else {
@@ -172,6 +181,66 @@ __global__ void __launch_bounds__(GM_THREADS) update_kernel(const GmresState* __
       double w1 = w_in[r];
       for (int c = 0; c < k; ++c) w1 = fma(hc[c], V[c][r], w1);
       w_out[r] = w1;
+      nacc = fma(w1, w1, nacc);
+    }
+  }
+  if (norm_partial) {
+    nacc = block_sum(nacc, red);
+    if (threadIdx.x == 0) norm_partial[blockIdx.x] = nacc;
+  }
+}
+
+// ---- blocked Gram-Schmidt update: coefficients of the kb (<= JT) columns of this block are reduced in-kernel from the
+//      multi-dot partials (every CTA sums the same G partials in the same order: deterministic, no extra launch), then
+//      w -= sum_c coef[c] V[c].  CTA 0 publishes the coefficients: h[c] = coef (first pass) or h[c] += coef (second pass).
+//      The block's vectors were just streamed by the multi-dot sweep and are re-read here from L2, so the basis crosses
+//      HBM once per Gram-Schmidt pass instead of twice.
+__global__ void __launch_bounds__(GM_THREADS) update_block_kernel(const GmresState* __restrict__ st, const double* const* __restrict__ V,
+                                                                   int kb, const double* __restrict__ partial, int accumulate,
+                                                                   double* __restrict__ h, double* w, int64_t n,
+                                                                   double* __restrict__ norm_partial) {
+  if (st->status != 0) return;
+  __shared__ double hc[JT];
+  __shared__ double red[32];
+  const int G = gridDim.x;
+  {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (wid < kb) {
+      double s = 0.0;
+      for (int b = lane; b < G; b += 32) s += partial[(int64_t)wid * G + b];
+      s = warp_sum(s);
+      if (lane == 0) {
+        hc[wid] = s;
+        if (blockIdx.x == 0) h[wid] = accumulate ? h[wid] + s : s;
+      }
+    }
+  }
+  __syncthreads();
+  int64_t r0, r1;
+  block_rows(n, r0, r1);
+  double nacc = 0.0;
+  const double* vp[JT];
+#pragma unroll
+  for (int c = 0; c < JT; ++c) vp[c] = V[c < kb ? c : 0];
+  for (int64_t r = r0 + 2 * threadIdx.x; r < r1; r += 2 * GM_THREADS) {
+    if (r + 1 < r1) {
+      double2 w2 = *reinterpret_cast<const double2*>(w + r);
+      double2 v2[JT];
+#pragma unroll
+      for (int c = 0; c < JT; ++c)
+        if (c < kb) v2[c] = __ldcs(reinterpret_cast<const double2*>(vp[c] + r));  // last use of the block: evict first
+#pragma unroll
+      for (int c = 0; c < JT; ++c)
+        if (c < kb) {
+          w2.x = fma(-hc[c], v2[c].x, w2.x);
+          w2.y = fma(-hc[c], v2[c].y, w2.y);
+        }
+      *reinterpret_cast<double2*>(w + r) = w2;
+      nacc = fma(w2.x, w2.x, fma(w2.y, w2.y, nacc));
+    } else {
+      double w1 = w[r];
+      for (int c = 0; c < kb; ++c) w1 = fma(-hc[c], vp[c][r], w1);
+      w[r] = w1;
       nacc = fma(w1, w1, nacc);
     }
   }
@@ -640,6 +709,11 @@ int32_t b200_gmres_solve(b200_gmres* gm, b200_linop* op, const double* b, double
   const int G = gm->G;
   const int orth = o.orth;
   const int check_every = o.check_every > 0 ? o.check_every : 8;
+  // Gram-Schmidt block: -1 => as many vectors as fit in ~64 MB (half of the 126 MB L2), at most JT; 0 => unblocked
+  int blk = o.block;
+  if (blk < 0) blk = (int)std::min<int64_t>(JT, std::max<int64_t>(1, ((int64_t)64 << 20) / (8 * n)));
+  if (blk > JT) blk = JT;
+  if (orth == B200_ORTH_MGS) blk = 0;
   const int64_t itmax = o.itmax > 0 ? o.itmax : n;
   const int restart_len = o.restart > 0 ? (int)std::min<int64_t>(o.restart, n) : 0;
   const int ew_grid = (int)std::min<int64_t>((n + GM_THREADS * 2 - 1) / (GM_THREADS * 2), (int64_t)ctx->sm_count * 8);
@@ -712,15 +786,29 @@ int32_t b200_gmres_solve(b200_gmres* gm, b200_linop* op, const double* b, double
                (gm->d_hraw && (int64_t)k * (k + 3) / 2 <= gm->hraw_cap) ? gm->d_hraw : nullptr);
       } else {
         const size_t shm = sizeof(double) * (k + 32);
-        PLAUNCH(ctx, B200_KID_MULTIDOT, (k + 1.0) * Bv, multidot_kernel, G, GM_THREADS, 0, gm->d_state, (const double* const*)gm->d_Vptrs, k, gm->w, n, gm->d_partial);
-        LAUNCH(ctx, reduce_h_kernel, (k + 7) / 8, GM_THREADS, 0, gm->d_state, k, G, gm->d_partial, gm->d_h, (double*)nullptr);
-        PLAUNCH(ctx, B200_KID_UPDATE, (k + 2.0) * Bv, update_kernel, G, GM_THREADS, shm, gm->d_state, 0, (const double* const*)gm->d_Vptrs, k, gm->d_h, -1.0, gm->w, gm->w, n,
-               gm->d_norm_partial);
-        if (orth == B200_ORTH_CGS2) {
-          PLAUNCH(ctx, B200_KID_MULTIDOT, (k + 1.0) * Bv, multidot_kernel, G, GM_THREADS, 0, gm->d_state, (const double* const*)gm->d_Vptrs, k, gm->w, n, gm->d_partial);
-          LAUNCH(ctx, reduce_h_kernel, (k + 7) / 8, GM_THREADS, 0, gm->d_state, k, G, gm->d_partial, gm->d_hacc, gm->d_h);
-          PLAUNCH(ctx, B200_KID_UPDATE, (k + 2.0) * Bv, update_kernel, G, GM_THREADS, shm, gm->d_state, 0, (const double* const*)gm->d_Vptrs, k, gm->d_hacc, -1.0, gm->w,
-                 gm->w, n, gm->d_norm_partial);
+        const int passes = (orth == B200_ORTH_CGS2) ? 2 : 1;
+        if (blk > 0 && k > blk) {
+          // L2-blocked Gram-Schmidt: per block one multi-dot sweep (HBM -> L2) and one update sweep (L2 hits)
+          for (int pass = 0; pass < passes; ++pass)
+            for (int c0 = 0; c0 < k; c0 += blk) {
+              const int kb = std::min(blk, k - c0);
+              const bool last = (pass == passes - 1) && (c0 + kb >= k);
+              PLAUNCH(ctx, B200_KID_MULTIDOT, (kb + 1.0) * Bv, (multidot_kernel<true>), G, GM_THREADS, 0, gm->d_state,
+                      (const double* const*)(gm->d_Vptrs + c0), kb, gm->w, n, gm->d_partial);
+              PLAUNCH(ctx, B200_KID_UPDATE, 2.0 * Bv, update_block_kernel, G, GM_THREADS, 0, gm->d_state, (const double* const*)(gm->d_Vptrs + c0), kb,
+                      (const double*)gm->d_partial, pass, gm->d_h + c0, gm->w, n, last ? gm->d_norm_partial : (double*)nullptr);
+            }
+        } else {
+          PLAUNCH(ctx, B200_KID_MULTIDOT, (k + 1.0) * Bv, (multidot_kernel<false>), G, GM_THREADS, 0, gm->d_state, (const double* const*)gm->d_Vptrs, k, gm->w, n, gm->d_partial);
+          LAUNCH(ctx, reduce_h_kernel, (k + 7) / 8, GM_THREADS, 0, gm->d_state, k, G, gm->d_partial, gm->d_h, (double*)nullptr);
+          PLAUNCH(ctx, B200_KID_UPDATE, (k + 2.0) * Bv, update_kernel, G, GM_THREADS, shm, gm->d_state, 0, (const double* const*)gm->d_Vptrs, k, gm->d_h, -1.0, gm->w, gm->w, n,
+                  gm->d_norm_partial);
+          if (orth == B200_ORTH_CGS2) {
+            PLAUNCH(ctx, B200_KID_MULTIDOT, (k + 1.0) * Bv, (multidot_kernel<false>), G, GM_THREADS, 0, gm->d_state, (const double* const*)gm->d_Vptrs, k, gm->w, n, gm->d_partial);
+            LAUNCH(ctx, reduce_h_kernel, (k + 7) / 8, GM_THREADS, 0, gm->d_state, k, G, gm->d_partial, gm->d_hacc, gm->d_h);
+            PLAUNCH(ctx, B200_KID_UPDATE, (k + 2.0) * Bv, update_kernel, G, GM_THREADS, shm, gm->d_state, 0, (const double* const*)gm->d_Vptrs, k, gm->d_hacc, -1.0, gm->w,
+                    gm->w, n, gm->d_norm_partial);
+          }
         }
         PLAUNCH(ctx, B200_KID_GIVENS, 0.0, givens_kernel, 1, GM_THREADS, 0, gm->d_state, k, G, gm->d_norm_partial, gm->d_h, gm->d_R, gm->d_cs, gm->d_sn, gm->d_z,
                (gm->d_hraw && (int64_t)k * (k + 3) / 2 <= gm->hraw_cap) ? gm->d_hraw : nullptr);
@@ -744,6 +832,8 @@ int32_t b200_gmres_solve(b200_gmres* gm, b200_linop* op, const double* b, double
     //   CGS (2j+2) Bv | CGS2 (4j+4) Bv | MGS (3j+1) Bv (dot pass reads v_{i+1}, update pass reads v_i, w read+written)
     for (int j = 1; j <= k; ++j) {
       double orthb = (orth == B200_ORTH_CGS) ? (2.0 * j + 2.0) : (orth == B200_ORTH_CGS2) ? (4.0 * j + 4.0) : (3.0 * j + 1.0);
+      if (blk > 0 && j > blk && orth != B200_ORTH_MGS)  // blocked: basis crosses HBM once per pass; w is L2 resident
+        orthb = ((orth == B200_ORTH_CGS2) ? 2.0 : 1.0) * (j + 2.0);
       bytes += (3.0 + 2.0 + orthb) * Bv;
     }
     // x += V_k y

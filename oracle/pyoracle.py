@@ -28,7 +28,7 @@ ORDER_NATURAL, ORDER_LARGEST_FIRST = 0, 1
 
 class GmresOpts(C.Structure):
     _fields_ = [("memory", C.c_int32), ("restart", C.c_int32), ("itmax", C.c_int32), ("orth", C.c_int32),
-                ("warm_start", C.c_int32), ("engine", C.c_int32), ("check_every", C.c_int32), ("reserved", C.c_int32),
+                ("warm_start", C.c_int32), ("engine", C.c_int32), ("check_every", C.c_int32), ("block", C.c_int32),
                 ("atol", C.c_double), ("rtol", C.c_double)]
 
 
@@ -119,7 +119,7 @@ def get_threads():
 
 
 def default_gmres_opts(**kw):
-    o = GmresOpts(memory=20, restart=0, itmax=0, orth=ORTH_MGS, warm_start=0, engine=0, check_every=0, reserved=0,
+    o = GmresOpts(memory=20, restart=0, itmax=0, orth=ORTH_MGS, warm_start=0, engine=0, check_every=0, block=0,
                   atol=0.0, rtol=0.0)
     for k, v in kw.items():
         setattr(o, k, v)
