@@ -190,7 +190,8 @@ int32_t b200_ctx_sm_count(b200_ctx* ctx, int32_t* count);
 /* per-kernel-family device timing with CUDA events on the ctx stream (bench.py's live roofline measurement);
  * bytes = the algorithmic HBM bytes of the timed launches (DESIGN.md accounting). */
 enum { B200_KID_JVP = 0, B200_KID_MULTIDOT = 1, B200_KID_UPDATE = 2, B200_KID_MGS = 3, B200_KID_NORMALIZE = 4,
-       B200_KID_RESIDUAL = 5, B200_KID_GIVENS = 6, B200_KID_RESIDENT = 7, B200_KID_COUNT = 8 };
+       B200_KID_RESIDUAL = 5, B200_KID_GIVENS = 6, B200_KID_RESIDENT = 7, B200_KID_LU_PANEL = 8, B200_KID_LU_GEMM = 9,
+       B200_KID_LU_OTHER = 10, B200_KID_SPARSE = 11, B200_KID_COUNT = 12 };
 int32_t b200_ctx_profile_enable(b200_ctx* ctx, int32_t on);
 int32_t b200_ctx_profile_reset(b200_ctx* ctx);
 int32_t b200_ctx_profile_get(b200_ctx* ctx, int32_t kernel_id, double* ms_host, double* bytes_host, int64_t* launches_host);

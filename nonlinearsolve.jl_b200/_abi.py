@@ -28,7 +28,7 @@ FORCING_NONE, FORCING_EW2 = 0, 1
 TERM_ABS_NORM_SAFE_BEST, TERM_ABS_NORM, TERM_ABS_NORM_SAFE = 0, 1, 2
 U0_REFERENCE, U0_PERTURBED_Z = 0, 1
 ORDER_NATURAL, ORDER_LARGEST_FIRST = 0, 1
-KID_NAMES = ["jvp", "multidot", "update", "mgs", "normalize", "residual", "givens", "resident"]
+KID_NAMES = ["jvp", "multidot", "update", "mgs", "normalize", "residual", "givens", "resident", "lu_panel", "lu_gemm", "lu_other", "sparse"]
 
 
 class GmresOpts(C.Structure):

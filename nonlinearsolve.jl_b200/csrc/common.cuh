@@ -22,6 +22,8 @@ struct b200_ctx {
   double* h_scalars = nullptr;   // pinned, 64 doubles
   void* l2_flush = nullptr;
   size_t l2_flush_bytes = 0;
+  cudaStream_t aux_stream = nullptr;  // look-ahead panel factorisation of the dense LU
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr;
   // optional per-kernel-family event timing (b200_ctx_profile_*)
   bool prof_on = false;
   struct ProfSlot { double ms = 0, bytes = 0; int64_t launches = 0; } prof[B200_KID_COUNT];

@@ -28,6 +28,7 @@ void b200_ctx::prof_end() {
 void b200_ctx::prof_collect() {
   if (prof_pending.empty()) return;
   cudaStreamSynchronize(stream);
+  if (aux_stream) cudaStreamSynchronize(aux_stream);
   for (ProfPending& p : prof_pending) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
@@ -109,6 +110,9 @@ int32_t b200_ctx_destroy(b200_ctx* ctx) {
   if (ctx->d_scalars) cudaFree(ctx->d_scalars);
   if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
   if (ctx->l2_flush) cudaFree(ctx->l2_flush);
+  if (ctx->aux_stream) { cudaStreamSynchronize(ctx->aux_stream); cudaStreamDestroy(ctx->aux_stream); cudaEventDestroy(ctx->ev_a); cudaEventDestroy(ctx->ev_b); }
+  ctx->prof_collect();
+  for (cudaEvent_t e : ctx->prof_free) cudaEventDestroy(e);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return B200_OK;

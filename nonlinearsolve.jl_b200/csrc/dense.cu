@@ -1,22 +1,32 @@
 // dense.cu — dense Jacobian fallback (kernels K7, K8): analytic fill of the column-major n x n
-// Jacobian and a blocked right-looking LU with partial pivoting (LAPACK getrf/getrs semantics).
+// Jacobian and a two-level blocked right-looking LU with partial pivoting (LAPACK getrf/getrs semantics).
 //
 // Reference path replaced: JacobianCache call lib/NonlinearSolveBase/src/jacobian.jl:237-258 (DI.jacobian! with dense
 // AutoForwardDiff: exact derivatives) and the LinearSolve LU reached through linear_solve.jl:100-117 /
 // NonlinearSolveBaseLinearSolveExt.jl:16-32, 102-111 (copyto!(A, J); lu!; ldiv!).
 //
-// Structure of getrf: for each panel of NB columns — (1) panel factorisation on CUDA cores (pivot search by block
-// arg-max, row swap, scale, rank-1 update inside the panel), (2) the panel's row interchanges applied to the columns left
-// and right of it, (3) TRSM  U12 = L11^{-1} A12 with L11 staged in shared memory, (4) the trailing update
-// A22 -= L21 U12 — the only GEMM-shaped part — on the FP64 tensor cores (mma.sync.m8n8k4.f64 = DMMA; tcgen05 has no
-// FP64 kind), operands staged through shared memory.
+// getrf structure (outer block NBO = 128, inner block NBI = 32):
+//   inner panel (32 columns), column by column, every step spread over many CTAs:
+//       pivot_search (arg-max partials)  ->  pivot_apply (1 CTA: final arg-max, ipiv, row swap inside the outer panel,
+//       1/pivot)  ->  column_update (scale + rank-1 update of the inner panel + arg-max partials of the NEXT column fused)
+//   after an inner panel: TRSM + GEMM (K = 32) on the remaining columns of the outer panel
+//   after the outer panel: row interchanges applied to the columns left/right of it, block TRSM for U12, and the
+//       trailing update  A22 -= L21 U12  with K = 128 — the GEMM-shaped 2/3 n^3 flops — on the FP64 tensor cores:
+//       `gemm_sub_kernel`, 128 x 128 CTA tiles, 8 warps x (32 x 64) warp tiles of mma.sync.m8n8k4.f64 (DMMA in SASS;
+//       tcgen05 has no FP64 kind), K streamed in chunks of 16 through double-buffered, bank-conflict-free shared memory
+//       with register prefetch of the next chunk.
+// Pivot sequence is LAPACK's (first maximum wins), checked bit-exact against the oracle / scipy in the tests.
 #include "common.cuh"
 #include <math.h>
 #include <algorithm>
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 
 namespace {
-constexpr int NB = 32;         // panel width
+constexpr int NBO = 256;  // outer block (GEMM K)
+constexpr int NBI = 32;   // inner panel width
 constexpr int DT = 256;
+constexpr int PS_MAX = 160;  // max CTAs of the panel grids
 
 // ------------------------------------------------------------------ Jacobian fill
 __global__ void __launch_bounds__(DT) bruss_dense_fill_kernel(int dim, int N, double a, double A, const double* __restrict__ u,
@@ -69,81 +79,230 @@ __global__ void __launch_bounds__(DT) unit_vector_kernel(int64_t n, int64_t j, d
   if (i < n) e[i] = (i == j) ? 1.0 : 0.0;
 }
 
-// ------------------------------------------------------------------ LU panel kernels (single CTA each)
-// pivot search + swap inside the panel + scale + rank-1 update of the remaining panel columns, for panel column jj
-__global__ void __launch_bounds__(1024) panel_column_kernel(int64_t n, double* __restrict__ A, int64_t ld, int64_t k0, int kb, int jj,
-                                                             int64_t* __restrict__ ipiv, int* __restrict__ info) {
-  __shared__ double smax[32];
-  __shared__ int64_t sidx[32];
-  __shared__ int64_t piv_s;
-  __shared__ double pivval_s;
-  const int64_t k = k0 + jj;
-  double* colk = A + k * ld;
-  // arg-max |A[i,k]|, i >= k ; ties -> smallest index (LAPACK idamax)
-  double best = -1.0;
-  int64_t bidx = k;
-  for (int64_t i = k + threadIdx.x; i < n; i += blockDim.x) {
-    const double v = fabs(colk[i]);
-    if (v > best || (v != v && best == best)) { best = v; bidx = i; }
-  }
+// ------------------------------------------------------------------ panel factorisation (multi-CTA, column by column)
+struct PanelScratch {      // device scratch shared by the three panel kernels
+  double pmax[PS_MAX];     // per-CTA arg-max partials of the current column
+  int64_t pidx[PS_MAX];
+  double rowbuf[2][NBI];   // cooperative panel: pivot row / displaced row exchanged between CTAs
+  double inv_pivot;        // 1 / pivot of the current column (0 if the pivot is exactly zero)
+  int64_t piv;
+  int info;
+  int nparts;
+};
+
+__device__ __forceinline__ void argmax_combine(double& best, int64_t& bidx, double ob, int64_t oi) {
+  // LAPACK idamax: largest |value|, first index wins ties; a NaN encountered first stays
+  if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+}
+__device__ __forceinline__ void block_argmax(double& best, int64_t& bidx, double* smax, int64_t* sidx) {
   for (int o = 16; o > 0; o >>= 1) {
     const double ob = __shfl_xor_sync(0xffffffffu, best, o);
     const int64_t oi = __shfl_xor_sync(0xffffffffu, bidx, o);
-    if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+    argmax_combine(best, bidx, ob, oi);
   }
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __syncthreads();
   if (lane == 0) { smax[wid] = best; sidx[wid] = bidx; }
   __syncthreads();
   if (wid == 0) {
     best = (lane < nw) ? smax[lane] : -2.0;
-    bidx = (lane < nw) ? sidx[lane] : k;
+    bidx = (lane < nw) ? sidx[lane] : INT64_MAX;
     for (int o = 16; o > 0; o >>= 1) {
       const double ob = __shfl_xor_sync(0xffffffffu, best, o);
       const int64_t oi = __shfl_xor_sync(0xffffffffu, bidx, o);
-      if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
-    }
-    if (lane == 0) {
-      piv_s = bidx;
-      ipiv[k] = bidx + 1;
-      pivval_s = colk[bidx];
-      if (colk[bidx] == 0.0 && *info == 0) *info = (int)(k + 1);
-    }
-  }
-  __syncthreads();
-  const int64_t piv = piv_s;
-  const double pivval = pivval_s;
-  // swap rows k and piv inside the panel
-  if (piv != k) {
-    for (int c = threadIdx.x; c < kb; c += blockDim.x) {
-      double* col = A + (k0 + c) * ld;
-      const double t = col[k];
-      col[k] = col[piv];
-      col[piv] = t;
-    }
-  }
-  __syncthreads();
-  if (pivval == 0.0) return;
-  const double inv = 1.0 / pivval;
-  // scale + rank-1 update of panel columns jj+1..kb-1
-  for (int64_t i = k + 1 + threadIdx.x; i < n; i += blockDim.x) {
-    const double l = colk[i] * inv;
-    colk[i] = l;
-    for (int c = jj + 1; c < kb; ++c) {
-      double* col = A + (k0 + c) * ld;
-      col[i] = fma(-l, col[k], col[i]);
+      argmax_combine(best, bidx, ob, oi);
     }
   }
 }
 
-// apply the panel's interchanges to every column outside the panel (thread per column)
-__global__ void __launch_bounds__(DT) swap_rows_kernel(int64_t n, double* __restrict__ A, int64_t ld, int64_t k0, int kb,
-                                                        const int64_t* __restrict__ ipiv) {
-  int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n - kb) return;
-  if (c >= k0) c += kb;  // skip the panel's own columns
+// arg-max partials of |A[i, col]|, i in [col, n)
+__global__ void __launch_bounds__(DT) pivot_search_kernel(int64_t n, const double* __restrict__ A, int64_t ld, int64_t col, PanelScratch* __restrict__ ps) {
+  __shared__ double smax[32];
+  __shared__ int64_t sidx[32];
+  const double* c = A + col * ld;
+  double best = -1.0;
+  int64_t bidx = INT64_MAX;
+  for (int64_t i = col + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double v = fabs(c[i]);
+    if (v > best) { best = v; bidx = i; }
+  }
+  block_argmax(best, bidx, smax, sidx);
+  if (threadIdx.x == 0) {
+    ps->pmax[blockIdx.x] = best;
+    ps->pidx[blockIdx.x] = bidx;
+    if (blockIdx.x == 0) ps->nparts = gridDim.x;
+  }
+}
+
+// single CTA: final arg-max, ipiv, info, swap rows col <-> piv inside the outer panel [pc0, pc0 + pw), 1/pivot
+__global__ void __launch_bounds__(128) pivot_apply_kernel(double* __restrict__ A, int64_t ld, int64_t col, int64_t pc0, int pw,
+                                                           int64_t* __restrict__ ipiv, PanelScratch* __restrict__ ps) {
+  __shared__ int64_t piv_s;
+  if (threadIdx.x < 32) {
+    double best = -2.0;
+    int64_t bidx = INT64_MAX;
+    for (int b = threadIdx.x; b < ps->nparts; b += 32) argmax_combine(best, bidx, ps->pmax[b], ps->pidx[b]);
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int64_t oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+      argmax_combine(best, bidx, ob, oi);
+    }
+    if (threadIdx.x == 0) {
+      if (bidx == INT64_MAX) bidx = col;  // all-NaN column: keep the diagonal
+      piv_s = bidx;
+      ps->piv = bidx;
+      ipiv[col] = bidx + 1;
+      const double pv = A[col * ld + bidx];
+      ps->inv_pivot = (pv == 0.0) ? 0.0 : 1.0 / pv;
+      if (pv == 0.0 && ps->info == 0) ps->info = (int)(col + 1);
+    }
+  }
+  __syncthreads();
+  const int64_t piv = piv_s;
+  if (piv != col) {
+    for (int c = threadIdx.x; c < pw; c += blockDim.x) {
+      double* cp = A + (pc0 + c) * ld;
+      const double t = cp[col];
+      cp[col] = cp[piv];
+      cp[piv] = t;
+    }
+  }
+}
+
+// rows i > col: l = A[i,col] / pivot ; A[i, col+1 .. ce) -= l * A[col, col+1 .. ce) ; fused arg-max partials of column col+1
+__global__ void __launch_bounds__(DT) column_update_kernel(int64_t n, double* __restrict__ A, int64_t ld, int64_t col, int64_t ce, int search_next,
+                                                            PanelScratch* __restrict__ ps) {
+  __shared__ double urow[NBI];
+  __shared__ double smax[32];
+  __shared__ int64_t sidx[32];
+  const double inv = ps->inv_pivot;
+  const int nc = (int)(ce - col - 1);
+  for (int c = threadIdx.x; c < nc; c += blockDim.x) urow[c] = A[(col + 1 + c) * ld + col];
+  __syncthreads();
+  double best = -1.0;
+  int64_t bidx = INT64_MAX;
+  if (inv != 0.0) {
+    for (int64_t i = col + 1 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+      const double l = A[col * ld + i] * inv;
+      A[col * ld + i] = l;
+      for (int c = 0; c < nc; ++c) {
+        double* p = A + (col + 1 + c) * ld + i;
+        const double v = fma(-l, urow[c], *p);
+        *p = v;
+        if (c == 0) {
+          const double av = fabs(v);
+          if (av > best) { best = av; bidx = i; }
+        }
+      }
+    }
+  } else if (search_next) {
+    for (int64_t i = col + 1 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+      const double av = fabs(A[(col + 1) * ld + i]);
+      if (av > best) { best = av; bidx = i; }
+    }
+  }
+  if (search_next) {
+    block_argmax(best, bidx, smax, sidx);
+    if (threadIdx.x == 0) {
+      ps->pmax[blockIdx.x] = best;
+      ps->pidx[blockIdx.x] = bidx;
+      if (blockIdx.x == 0) ps->nparts = gridDim.x;
+    }
+  }
+}
+
+// ---- cooperative inner panel: the kbi (<= 32) columns [c0, c0+kbi), rows [c0, n), factored by ONE kernel.  Every CTA keeps
+// its contiguous chunk of panel rows in shared memory (column-major, so a thread-per-row sweep is conflict free) for the
+// whole panel; per column only the arg-max partials and two 32-double rows cross CTAs, through two grid-wide barriers.
+// Replaces 2 dependent launches per column (pivot_apply + column_update, ~16 us per column) by ~2 barriers.
+__global__ void __launch_bounds__(DT) panel_coop_kernel(int64_t n, double* __restrict__ A, int64_t ld, int64_t c0, int kbi, int rpc,
+                                                         int64_t* __restrict__ ipiv, PanelScratch* __restrict__ ps) {
+  cg::grid_group grid = cg::this_grid();
+  extern __shared__ double pa[];  // [kbi][rpc_pad]
+  __shared__ double urow[NBI];
+  __shared__ double smax[32];
+  __shared__ int64_t sidx[32];
+  __shared__ int64_t piv_s;
+  const int rp = rpc | 1;
+  const int64_t row0 = c0 + (int64_t)blockIdx.x * rpc;          // first global row of this CTA
+  const int nrows = (int)max((int64_t)0, min((int64_t)rpc, n - row0));
+  for (int c = 0; c < kbi; ++c)
+    for (int r = threadIdx.x; r < nrows; r += DT) pa[c * rp + r] = A[(c0 + c) * ld + row0 + r];
+  __syncthreads();
+  for (int jj = 0; jj < kbi; ++jj) {
+    const int64_t col = c0 + jj;
+    // (a) local arg-max of |a[., jj]| over rows >= col
+    double best = -1.0;
+    int64_t bidx = INT64_MAX;
+    for (int r = threadIdx.x; r < nrows; r += DT) {
+      const int64_t gr = row0 + r;
+      if (gr >= col) {
+        const double v = fabs(pa[jj * rp + r]);
+        if (v > best) { best = v; bidx = gr; }
+      }
+    }
+    block_argmax(best, bidx, smax, sidx);
+    if (threadIdx.x == 0) { ps->pmax[blockIdx.x] = best; ps->pidx[blockIdx.x] = bidx; }
+    grid.sync();
+    // (b) global arg-max (identical in every CTA), pivot bookkeeping, rows published by their owners
+    if (threadIdx.x < 32) {
+      double gb = -2.0;
+      int64_t gi = INT64_MAX;
+      for (int b = threadIdx.x; b < (int)gridDim.x; b += 32) argmax_combine(gb, gi, ps->pmax[b], ps->pidx[b]);
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, gb, o);
+        const int64_t oi = __shfl_xor_sync(0xffffffffu, gi, o);
+        argmax_combine(gb, gi, ob, oi);
+      }
+      if (threadIdx.x == 0) {
+        if (gi == INT64_MAX) gi = col;
+        piv_s = gi;
+        if (blockIdx.x == 0) ipiv[col] = gi + 1;
+      }
+    }
+    __syncthreads();
+    const int64_t piv = piv_s;
+    const bool own_piv = piv >= row0 && piv < row0 + nrows;
+    const bool own_col = col >= row0 && col < row0 + nrows;
+    if (own_piv && threadIdx.x < kbi) ps->rowbuf[0][threadIdx.x] = pa[threadIdx.x * rp + (int)(piv - row0)];
+    if (own_col && piv != col && threadIdx.x < kbi) ps->rowbuf[1][threadIdx.x] = pa[threadIdx.x * rp + (int)(col - row0)];
+    grid.sync();
+    // (c) complete the interchange, then scale + rank-1 update of the rows below the diagonal
+    if (threadIdx.x < kbi) {
+      const double pv = ps->rowbuf[0][threadIdx.x];
+      urow[threadIdx.x] = pv;
+      if (own_col) pa[threadIdx.x * rp + (int)(col - row0)] = pv;
+      if (own_piv && piv != col) pa[threadIdx.x * rp + (int)(piv - row0)] = ps->rowbuf[1][threadIdx.x];
+    }
+    __syncthreads();
+    const double pivval = urow[jj];
+    if (pivval == 0.0) {
+      if (blockIdx.x == 0 && threadIdx.x == 0 && ps->info == 0) ps->info = (int)(col + 1);
+    } else {
+      const double inv = 1.0 / pivval;
+      for (int r = threadIdx.x; r < nrows; r += DT) {
+        if (row0 + r > col) {
+          const double l = pa[jj * rp + r] * inv;
+          pa[jj * rp + r] = l;
+          for (int c = jj + 1; c < kbi; ++c) pa[c * rp + r] = fma(-l, urow[c], pa[c * rp + r]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  for (int c = 0; c < kbi; ++c)
+    for (int r = threadIdx.x; r < nrows; r += DT) A[(c0 + c) * ld + row0 + r] = pa[c * rp + r];
+}
+
+// apply the interchanges ipiv[r0 .. r0+cnt) to columns [c_lo, c_hi) excluding [x_lo, x_hi)  (thread per column)
+__global__ void __launch_bounds__(DT) swap_rows_kernel(double* __restrict__ A, int64_t ld, int64_t r0, int cnt, const int64_t* __restrict__ ipiv,
+                                                        int64_t c_lo, int64_t c_hi, int64_t x_lo, int64_t x_hi) {
+  int64_t c = c_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= x_lo) c += (x_hi - x_lo);
+  if (c >= c_hi) return;
   double* col = A + c * ld;
-  for (int q = 0; q < kb; ++q) {
-    const int64_t r = k0 + q, p = ipiv[r] - 1;
+  for (int q = 0; q < cnt; ++q) {
+    const int64_t r = r0 + q, p = ipiv[r] - 1;
     if (p != r) {
       const double t = col[r];
       col[r] = col[p];
@@ -152,90 +311,132 @@ __global__ void __launch_bounds__(DT) swap_rows_kernel(int64_t n, double* __rest
   }
 }
 
-// U12 = L11^{-1} A12 : thread per column of A12, L11 (unit lower, kb x kb) in shared memory
-__global__ void __launch_bounds__(DT) trsm_kernel(int64_t n, double* __restrict__ A, int64_t ld, int64_t k0, int kb) {
-  __shared__ double L[NB][NB + 1];
+// X = L^{-1} X for the kb x ncols block at rows [r0, r0+kb), columns [c0, c0+ncols); L = unit lower triangle at (r0, r0)
+__global__ void __launch_bounds__(DT) trsm_kernel(double* __restrict__ A, int64_t ld, int64_t r0, int kb, int64_t c0, int64_t ncols) {
+  __shared__ double L[NBI][NBI + 1];
   for (int t = threadIdx.x; t < kb * kb; t += blockDim.x) {
     const int r = t % kb, c = t / kb;
-    L[r][c] = A[(k0 + c) * ld + k0 + r];
+    L[r][c] = A[(r0 + c) * ld + r0 + r];
   }
   __syncthreads();
-  const int64_t c = k0 + kb + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n) return;
-  double* col = A + c * ld + k0;
-  double x[NB];
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncols) return;
+  double* col = A + (c0 + c) * ld + r0;
+  double x[NBI];
 #pragma unroll
-  for (int r = 0; r < NB; ++r) x[r] = (r < kb) ? col[r] : 0.0;
+  for (int r = 0; r < NBI; ++r) x[r] = (r < kb) ? col[r] : 0.0;
 #pragma unroll
-  for (int r = 0; r < NB; ++r) {
+  for (int r = 0; r < NBI; ++r) {
     if (r < kb) {
       double s = x[r];
 #pragma unroll
-      for (int q = 0; q < NB; ++q)
+      for (int q = 0; q < NBI; ++q)
         if (q < r) s = fma(-L[r][q], x[q], s);
       x[r] = s;
     }
   }
 #pragma unroll
-  for (int r = 0; r < NB; ++r)
+  for (int r = 0; r < NBI; ++r)
     if (r < kb) col[r] = x[r];
 }
 
-// ------------------------------------------------------------------ trailing update on the FP64 tensor cores
-// C[m x nn] -= Lp[m x kb] * U[kb x nn], all column-major inside A.  CTA tile 64 x 64, 8 warps laid out 4 (m) x 2 (n),
-// each warp owns a 16 x 32 sub-tile = 2 x 4 DMMA m8n8k4 accumulator fragments; the K = kb <= 32 slab of both operands
-// is staged once in shared memory (padded against bank conflicts).
-constexpr int GT_M = 64, GT_N = 64;
+// ------------------------------------------------------------------ C -= A * B on the FP64 tensor cores
+// A: M x K (lda), B: K x N (ldb), C: M x N (ldc), all column-major.  CTA = 4 warps, tile 128 (M) x 64 (N), each warp a
+// 32 x 64 sub-tile = 4 x 8 DMMA m8n8k4 accumulator fragments; K streamed in chunks of 8 through double-buffered shared
+// memory (rows padded by 4 doubles: fragment loads are bank-conflict free) with register prefetch of the next chunk.
+// 222 registers x 128 threads -> two CTAs per SM, so one CTA's C read-modify-write epilogue overlaps the other's MMAs.
+constexpr int GM_BM = 128, GM_BN = 64, GM_BK = 8, GM_PAD = 4, GM_T = 128, GM_STAGES = 4;
 __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
-__global__ void __launch_bounds__(DT) trailing_dmma_kernel(int64_t n, double* __restrict__ A, int64_t ld, int64_t k0, int kb) {
-  __shared__ double Ls[NB][GT_M + 4];  // Ls[k][i] = L21[i, k]
-  __shared__ double Us[NB][GT_N + 4];  // Us[k][j] = U12[k, j]
-  const int64_t k1 = k0 + kb;
-  const int64_t i0 = k1 + (int64_t)blockIdx.x * GT_M;
-  const int64_t j0 = k1 + (int64_t)blockIdx.y * GT_N;
-  for (int t = threadIdx.x; t < NB * GT_M; t += DT) {
-    const int i = t % GT_M, k = t / GT_M;
-    Ls[k][i] = (k < kb && i0 + i < n) ? A[(k0 + k) * ld + i0 + i] : 0.0;
+// 8-byte asynchronous global->shared copy (LDGSTS); src_bytes = 0 zero-fills the destination (out-of-range elements)
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc, int src_bytes) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(gsrc), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// K is streamed in chunks of 8 through a 4-stage cp.async ring: three chunks are always in flight underneath the MMAs of
+// the current one, so the ~1 us L2/HBM latency of the operand loads is covered even with only 8 resident warps per SM.
+__global__ void __launch_bounds__(GM_T, 2) gemm_sub_kernel(int64_t M, int64_t N, int K, const double* __restrict__ A, int64_t lda,
+                                                            const double* __restrict__ B, int64_t ldb, double* __restrict__ C, int64_t ldc) {
+  extern __shared__ double gsm[];
+  double(*As)[GM_BK][GM_BM + GM_PAD] = reinterpret_cast<double(*)[GM_BK][GM_BM + GM_PAD]>(gsm);                                            // [stage][k][m]
+  double(*Bs)[GM_BK][GM_BN + GM_PAD] = reinterpret_cast<double(*)[GM_BK][GM_BN + GM_PAD]>(gsm + GM_STAGES * GM_BK * (GM_BM + GM_PAD));  // [stage][k][n]
+  const int64_t m0 = (int64_t)blockIdx.x * GM_BM, n0 = (int64_t)blockIdx.y * GM_BN;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp * 32;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int bk = tid & 7, bn = tid >> 3;  // B staging: k fastest; thread covers n = bn + 16 q, q = 0..3
+  const bool m_ok = m0 + tid < M;
+  const double* a_src = A + (m_ok ? m0 + tid : 0);
+  auto issue_chunk = [&](int ch) {
+    const int st = ch % GM_STAGES, kc = ch * GM_BK;
+#pragma unroll
+    for (int q = 0; q < GM_BK; ++q) {
+      const bool ok = m_ok && (kc + q < K);
+      cp_async8(&As[st][q][tid], a_src + (int64_t)(ok ? kc + q : 0) * lda, ok ? 8 : 0);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int64_t nn = n0 + bn + 16 * q;
+      const bool ok = (nn < N) && (kc + bk < K);
+      cp_async8(&Bs[st][bk][bn + 16 * q], B + (ok ? nn * ldb + kc + bk : 0), ok ? 8 : 0);
+    }
+  };
+  double acc[4][8][2];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 8; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+  const int nchunks = (K + GM_BK - 1) / GM_BK;
+#pragma unroll
+  for (int s = 0; s < GM_STAGES - 1; ++s) {
+    if (s < nchunks) issue_chunk(s);
+    cp_async_commit();
   }
-  for (int t = threadIdx.x; t < NB * GT_N; t += DT) {
-    const int k = t % NB, j = t / NB;
-    Us[k][j] = (k < kb && j0 + j < n) ? A[(j0 + j) * ld + k0 + k] : 0.0;
+  for (int ch = 0; ch < nchunks; ++ch) {
+    cp_async_wait<GM_STAGES - 2>();  // chunk `ch` has landed
+    __syncthreads();                 // ... for every thread, and everyone is done reading stage (ch-1) % STAGES
+    if (ch + GM_STAGES - 1 < nchunks) issue_chunk(ch + GM_STAGES - 1);
+    cp_async_commit();
+    const int st = ch % GM_STAGES;
+#pragma unroll
+    for (int kk = 0; kk < GM_BK; kk += 4) {
+      double af[4], bf[8];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) af[a] = As[st][kk + t4][wm + a * 8 + g];
+#pragma unroll
+      for (int b = 0; b < 8; ++b) bf[b] = Bs[st][kk + t4][b * 8 + g];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) dmma_m8n8k4(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+    }
   }
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int wm = (warp & 3) * 16, wn = (warp >> 2) * 32;
-  const int g = lane >> 2, t4 = lane & 3;  // groupID, thread-in-group
-  double acc[2][4][2];
 #pragma unroll
-  for (int a = 0; a < 2; ++a)
+  for (int a = 0; a < 4; ++a)
 #pragma unroll
-    for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
-#pragma unroll
-  for (int kk = 0; kk < NB; kk += 4) {
-    double af[2], bf[4];
-#pragma unroll
-    for (int a = 0; a < 2; ++a) af[a] = Ls[kk + t4][wm + a * 8 + g];      // A fragment: row g, col t4 (row-major m8 x k4)
-#pragma unroll
-    for (int b = 0; b < 4; ++b) bf[b] = Us[kk + t4][wn + b * 8 + g];      // B fragment: row t4, col g (col-major k4 x n8)
-#pragma unroll
-    for (int a = 0; a < 2; ++a)
-#pragma unroll
-      for (int b = 0; b < 4; ++b) dmma_m8n8k4(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
-  }
-  // C fragment: row g, cols 2*t4, 2*t4+1
-#pragma unroll
-  for (int a = 0; a < 2; ++a)
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      const int64_t i = i0 + wm + a * 8 + g;
-      const int64_t j = j0 + wn + b * 8 + 2 * t4;
-      if (i < n) {
-        if (j < n) A[j * ld + i] -= acc[a][b][0];
-        if (j + 1 < n) A[(j + 1) * ld + i] -= acc[a][b][1];
+    for (int b = 0; b < 8; ++b) {
+      const int64_t i = m0 + wm + a * 8 + g;
+      const int64_t j = n0 + b * 8 + 2 * t4;
+      if (i < M) {
+        if (j < N) C[j * ldc + i] -= acc[a][b][0];
+        if (j + 1 < N) C[(j + 1) * ldc + i] -= acc[a][b][1];
       }
     }
+}
+
+constexpr size_t GEMM_SMEM = sizeof(double) * GM_STAGES * GM_BK * ((GM_BM + GM_PAD) + (GM_BN + GM_PAD));
+
+int32_t gemm_sub(b200_ctx* ctx, int64_t M, int64_t N, int K, const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc) {
+  if (M <= 0 || N <= 0 || K <= 0) return B200_OK;
+  dim3 grid((unsigned)((M + GM_BM - 1) / GM_BM), (unsigned)((N + GM_BN - 1) / GM_BN));
+  PLAUNCH(ctx, B200_KID_LU_GEMM, 2.0 * (double)M * (double)N * (double)K /* flops, not bytes */, gemm_sub_kernel, grid, GM_T, GEMM_SMEM, M, N, K, A, lda, B, ldb, C,
+          ldc);
+  return B200_OK;
 }
 
 // ------------------------------------------------------------------ triangular solves (nrhs small)
@@ -248,12 +449,11 @@ __global__ void __launch_bounds__(DT) apply_pivots_kernel(int64_t n, int64_t nrh
     if (p != k) { const double t = b[k]; b[k] = b[p]; b[p] = t; }
   }
 }
-// one block step of the forward (unit lower) or backward (upper) substitution: solve the NB x NB diagonal block in a
-// single warp, then subtract its contribution from the rest of the right-hand side (all CTAs).
-__global__ void __launch_bounds__(DT) trisolve_diag_kernel(int lower, int64_t n, const double* __restrict__ A, int64_t ld, int64_t k0, int kb,
-                                                            double* __restrict__ b) {
-  __shared__ double T[NB][NB + 1];
-  __shared__ double x[NB];
+// one block step of the forward (unit lower) or backward (upper) substitution: solve the NBI x NBI diagonal block, then
+// subtract its contribution from the rest of the right-hand side (all CTAs).
+__global__ void __launch_bounds__(64) trisolve_diag_kernel(int lower, const double* __restrict__ A, int64_t ld, int64_t k0, int kb, double* __restrict__ b) {
+  __shared__ double T[NBI][NBI + 1];
+  __shared__ double x[NBI];
   for (int t = threadIdx.x; t < kb * kb; t += blockDim.x) {
     const int r = t % kb, c = t / kb;
     T[r][c] = A[(k0 + c) * ld + k0 + r];
@@ -272,7 +472,7 @@ __global__ void __launch_bounds__(DT) trisolve_diag_kernel(int lower, int64_t n,
 }
 __global__ void __launch_bounds__(DT) trisolve_update_kernel(int lower, int64_t n, const double* __restrict__ A, int64_t ld, int64_t k0, int kb,
                                                               double* __restrict__ b) {
-  __shared__ double x[NB];
+  __shared__ double x[NBI];
   for (int t = threadIdx.x; t < kb; t += blockDim.x) x[t] = b[k0 + t];
   __syncthreads();
   const int64_t lo = lower ? k0 + kb : 0, hi = lower ? n : k0;
@@ -294,7 +494,8 @@ int32_t b200_dense_jac_fill(b200_problem* p, const double* u, double* J, int64_t
   switch (p->kind) {
     case B200_PROB_BRUSS2D:
     case B200_PROB_BRUSS3D:
-      LAUNCH(ctx, bruss_dense_fill_kernel, grid, DT, 0, p->kind == B200_PROB_BRUSS2D ? 2 : 3, p->N, p->a, p->A, u, J, ld);
+      PLAUNCH(ctx, B200_KID_LU_OTHER, 8.0 * (double)ld * (double)n, bruss_dense_fill_kernel, grid, DT, 0, p->kind == B200_PROB_BRUSS2D ? 2 : 3, p->N, p->a, p->A,
+              u, J, ld);
       break;
     case B200_PROB_QUADRATIC:
     case B200_PROB_TRIDIAG_QUAD:
@@ -319,23 +520,91 @@ int32_t b200_dense_jac_fill(b200_problem* p, const double* u, double* J, int64_t
 
 int32_t b200_getrf(b200_ctx* ctx, int64_t n, double* A, int64_t ld, int64_t* ipiv, int32_t* info_host) {
   B200_REQUIRE(ctx, n > 0 && ld >= n, "getrf: bad dimensions");
-  int* d_info = reinterpret_cast<int*>(ctx->d_scalars + 16);
-  CUDA_TRY(ctx, cudaMemsetAsync(d_info, 0, sizeof(int), ctx->stream));
-  for (int64_t k0 = 0; k0 < n; k0 += NB) {
-    const int kb = (int)std::min<int64_t>(NB, n - k0);
-    const int pthreads = (n - k0 >= 8192) ? 1024 : (n - k0 >= 1024 ? 512 : 128);
-    for (int jj = 0; jj < kb; ++jj) LAUNCH(ctx, panel_column_kernel, 1, pthreads, 0, n, A, ld, k0, kb, jj, ipiv, d_info);
-    if (n - kb > 0) LAUNCH(ctx, swap_rows_kernel, (int)((n - kb + DT - 1) / DT), DT, 0, n, A, ld, k0, kb, (const int64_t*)ipiv);
-    const int64_t rest = n - (k0 + kb);
-    if (rest > 0) {
-      LAUNCH(ctx, trsm_kernel, (int)((rest + DT - 1) / DT), DT, 0, n, A, ld, k0, kb);
-      dim3 grid((unsigned)((rest + GT_M - 1) / GT_M), (unsigned)((rest + GT_N - 1) / GT_N));
-      LAUNCH(ctx, trailing_dmma_kernel, grid, DT, 0, n, A, ld, k0, kb);
+  static_assert(sizeof(PanelScratch) <= sizeof(double) * B200_RED_MAX_BLOCKS, "panel scratch must fit in d_partials");
+  PanelScratch* ps = reinterpret_cast<PanelScratch*>(ctx->d_partials + 2 * B200_RED_MAX_BLOCKS);
+  CUDA_TRY(ctx, cudaMemsetAsync(ps, 0, sizeof(PanelScratch), ctx->stream));
+  CUDA_TRY(ctx, cudaFuncSetAttribute(panel_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  CUDA_TRY(ctx, cudaFuncSetAttribute(gemm_sub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+  if (!ctx->aux_stream) {
+    CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+    CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_a, cudaEventDisableTiming));
+    CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_b, cudaEventDisableTiming));
+  }
+  cudaStream_t s_main = ctx->stream, s_panel = ctx->aux_stream;
+  auto nparts = [&](int64_t rows) { return (int)std::min<int64_t>(PS_MAX, std::max<int64_t>(1, (rows + 4 * DT - 1) / (4 * DT))); };
+
+  // factor the outer panel A[k0:n, k0:k0+kbo] (inner panels of NBI columns); issued on whatever ctx->stream currently is
+  auto factor_panel = [&](int64_t k0, int kbo) -> int32_t {
+    const int64_t k1 = k0 + kbo;
+    for (int i0 = 0; i0 < kbo; i0 += NBI) {
+      const int kbi = std::min(NBI, kbo - i0);
+      const int64_t c0 = k0 + i0, c1 = c0 + kbi;
+      {
+        // cooperative panel: as many CTAs as keep >= 128 rows each, at most one per SM (all co-resident)
+        const int64_t m = n - c0;
+        int P = (int)std::min<int64_t>(std::min(ctx->sm_count, PS_MAX), std::max<int64_t>(1, (m + 127) / 128));
+        int rpc = (int)((m + P - 1) / P);
+        P = (int)((m + rpc - 1) / rpc);
+        const size_t smem = sizeof(double) * (size_t)kbi * (size_t)(rpc | 1);
+        int kbi_ = kbi;
+        int64_t n_ = n, ld_ = ld, c0_ = c0;
+        double* A_ = A;
+        int64_t* ipiv_ = ipiv;
+        PanelScratch* ps_ = ps;
+        void* args[] = {&n_, &A_, &ld_, &c0_, &kbi_, &rpc, &ipiv_, &ps_};
+        if (ctx->prof_on) ctx->prof_begin(B200_KID_LU_PANEL, 0.0);
+        CUDA_TRY(ctx, cudaLaunchCooperativeKernel((const void*)panel_coop_kernel, dim3(P), dim3(DT), args, smem, ctx->stream));
+        ctx->launches++;
+        if (ctx->prof_on) ctx->prof_end();
+        // the panel's interchanges applied to the other columns of the outer panel
+        if (kbo - kbi > 0)
+          PLAUNCH(ctx, B200_KID_LU_OTHER, 0.0, swap_rows_kernel, (int)((kbo - kbi + DT - 1) / DT), DT, 0, A, ld, c0, kbi, (const int64_t*)ipiv, k0, k1, c0, c1);
+      }
+      const int64_t rest = k1 - c1;  // rest of the outer panel: U = L11^{-1} A12 ; A22 -= L21 U
+      if (rest > 0) {
+        PLAUNCH(ctx, B200_KID_LU_OTHER, 0.0, trsm_kernel, (int)((rest + DT - 1) / DT), DT, 0, A, ld, c0, kbi, c1, rest);
+        B200_TRY(gemm_sub(ctx, n - c1, rest, kbi, A + c0 * ld + c1, ld, A + c1 * ld + c0, ld, A + c1 * ld + c1, ld));
+      }
     }
+    return B200_OK;
+  };
+
+  B200_TRY(factor_panel(0, (int)std::min<int64_t>(NBO, n)));
+  for (int64_t k0 = 0; k0 < n; k0 += NBO) {
+    const int kbo = (int)std::min<int64_t>(NBO, n - k0);
+    const int64_t k1 = k0 + kbo;
+    // ---- interchanges of this panel applied to the columns left and right of it
+    if (n - kbo > 0)
+      PLAUNCH(ctx, B200_KID_LU_OTHER, 0.0, swap_rows_kernel, (int)((n - kbo + DT - 1) / DT), DT, 0, A, ld, k0, kbo, (const int64_t*)ipiv, (int64_t)0, n, k0, k1);
+    const int64_t rest = n - k1;
+    if (rest <= 0) break;
+    // ---- U12 = L11^{-1} A12 by 32-row blocks
+    for (int b0 = 0; b0 < kbo; b0 += NBI) {
+      const int kb = std::min(NBI, kbo - b0);
+      PLAUNCH(ctx, B200_KID_LU_OTHER, 0.0, trsm_kernel, (int)((rest + DT - 1) / DT), DT, 0, A, ld, k0 + b0, kb, k1, rest);
+      const int below = kbo - b0 - kb;
+      if (below > 0)
+        B200_TRY(gemm_sub(ctx, below, rest, kb, A + (k0 + b0) * ld + (k0 + b0 + kb), ld, A + k1 * ld + (k0 + b0), ld, A + k1 * ld + (k0 + b0 + kb), ld));
+    }
+    // ---- trailing update on the FP64 tensor cores, with look-ahead: first the columns of the NEXT panel, whose
+    //      factorisation (latency-bound, few SMs) then runs on a second stream underneath the rest of the GEMM.
+    const int kbn = (int)std::min<int64_t>(NBO, rest);
+    B200_TRY(gemm_sub(ctx, rest, kbn, kbo, A + k0 * ld + k1, ld, A + k1 * ld + k0, ld, A + k1 * ld + k1, ld));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_a, s_main));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(s_panel, ctx->ev_a, 0));
+    static const bool lookahead = getenv("B200_LU_LOOKAHEAD") ? atoi(getenv("B200_LU_LOOKAHEAD")) != 0 : true;
+    ctx->stream = lookahead ? s_panel : s_main;
+    int32_t st = factor_panel(k1, kbn);
+    ctx->stream = s_main;
+    B200_TRY(st);
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_b, s_panel));
+    if (rest - kbn > 0)
+      B200_TRY(gemm_sub(ctx, rest, rest - kbn, kbo, A + k0 * ld + k1, ld, A + (k1 + kbn) * ld + k0, ld, A + (k1 + kbn) * ld + k1, ld));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(s_main, ctx->ev_b, 0));
   }
   CHECK_LAUNCH(ctx);
   if (info_host) {
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scalars + 16, d_info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scalars + 16, &ps->info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     *info_host = *reinterpret_cast<int*>(ctx->h_scalars + 16);
   }
@@ -347,17 +616,17 @@ int32_t b200_getrs(b200_ctx* ctx, int64_t n, int64_t nrhs, const double* A, int6
   LAUNCH(ctx, apply_pivots_kernel, (int)((nrhs + DT - 1) / DT), DT, 0, n, nrhs, ipiv, B, ldb);
   for (int64_t r = 0; r < nrhs; ++r) {
     double* b = B + r * ldb;
-    for (int64_t k0 = 0; k0 < n; k0 += NB) {  // L y = P b
-      const int kb = (int)std::min<int64_t>(NB, n - k0);
-      LAUNCH(ctx, trisolve_diag_kernel, 1, 64, 0, 1, n, A, ld, k0, kb, b);
+    for (int64_t k0 = 0; k0 < n; k0 += NBI) {  // L y = P b
+      const int kb = (int)std::min<int64_t>(NBI, n - k0);
+      LAUNCH(ctx, trisolve_diag_kernel, 1, 64, 0, 1, A, ld, k0, kb, b);
       const int64_t rest = n - (k0 + kb);
       if (rest > 0) LAUNCH(ctx, trisolve_update_kernel, (int)((rest + DT - 1) / DT), DT, 0, 1, n, A, ld, k0, kb, b);
     }
-    const int64_t nblk = (n + NB - 1) / NB;
+    const int64_t nblk = (n + NBI - 1) / NBI;
     for (int64_t blk = nblk - 1; blk >= 0; --blk) {  // U x = y
-      const int64_t k0 = blk * NB;
-      const int kb = (int)std::min<int64_t>(NB, n - k0);
-      LAUNCH(ctx, trisolve_diag_kernel, 1, 64, 0, 0, n, A, ld, k0, kb, b);
+      const int64_t k0 = blk * NBI;
+      const int kb = (int)std::min<int64_t>(NBI, n - k0);
+      LAUNCH(ctx, trisolve_diag_kernel, 1, 64, 0, 0, A, ld, k0, kb, b);
       if (k0 > 0) LAUNCH(ctx, trisolve_update_kernel, (int)((k0 + DT - 1) / DT), DT, 0, 0, n, A, ld, k0, kb, b);
     }
   }
