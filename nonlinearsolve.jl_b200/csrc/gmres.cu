@@ -456,6 +456,292 @@ __global__ void __launch_bounds__(GM_THREADS) dense_gemv_kernel(int trans, int64
     }
   }
 }
+// =====================================================================================================================
+// Resident Arnoldi step (engine B200_ENGINE_RESIDENT): ONE cooperative kernel per Arnoldi iteration for the built-in
+// Brusselator operators.  One CTA per SM; CTA b owns the cells [b*cpc, (b+1)*cpc) of both species for the whole step:
+//   1. w = J(u) v_k is evaluated straight into registers (RR rows per thread) — it never touches HBM;
+//   2. the Krylov basis is streamed through shared memory ONCE per Gram-Schmidt pass by TMA bulk copies
+//      (cp.async.bulk + mbarrier, two stages: v_{i+1} lands while v_i is being used); per basis vector: dot partial ->
+//      grid barrier -> every CTA sums the same per-CTA partials in the same order (deterministic) -> w -= h_i v_i
+//      from the copy still in shared memory.  This is modified Gram-Schmidt (Krylov.jl's scheme), applied twice when
+//      reorthogonalisation is requested: `passes * k * Bv` of HBM traffic instead of the 2x of the multi-kernel engine;
+//   3. ||w||, Givens recurrence (CTA 0), normalisation and the store of v_{k+1} close the step.
+// Grid-wide barriers are a release/acquire counter in global memory (cooperative launch guarantees co-residency); spins
+// are bounded so a fault can never hang the GPU.
+constexpr int RS_THREADS = 512;
+constexpr int RS_RR = 28;  // max rows per thread -> at most 28 * 512 = 14336 rows (7168 cells) per CTA
+
+struct ResidentParams {
+  int dim, N, k, passes, G, late_issue;
+  int64_t NC;       // cells
+  int cpc;          // cells per CTA (even)
+  double a, A;
+  const double* u;
+  const double* const* V;
+  double* vnew;     // V[k]
+  unsigned long long* slots;  // [2][G][2] ping-pong {data32 | epoch << 32} words (NCCL-LL style flag-in-word publication)
+  unsigned epoch_base;        // unique, monotonically increasing across launches
+  double* dbg;                // optional phase timers (cycles) of CTA 0: wait, dot, gather, update, steps
+  int* err;
+  double* h;        // Hessenberg column workspace (k + 1)
+  double *R, *cs, *sn, *z, *hraw;
+  GmresState* st;
+};
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned target, int* err) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(bar, 1u);
+    unsigned spins = 0;
+    while (ld_acquire_u32(bar) < target) {
+      if (++spins > (1u << 24)) { *err = 1; break; }  // ~seconds: bounded, never a hang
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+// Cross-CTA all-to-all of one double per CTA with the synchronisation folded into the data (the idea of NCCL's LL
+// protocol): each 64-bit word carries 32 data bits and a 32-bit epoch, and 64-bit stores are single transactions, so a
+// reader that sees the expected epoch in both words has the value — no fence, no atomic, no separate barrier, one L2 round
+// trip.  Two slot buffers alternate by step parity: a CTA can only overwrite a buffer two steps later, i.e. after every
+// other CTA has passed the step in between and therefore finished reading the older value.
+// Every slot sits in its own 256-byte block so that the all-to-all polls spread over the L2 slices instead of hammering one.
+constexpr int LL_STRIDE = 32;  // u64 words per slot
+constexpr int LL_MAXG = 160;
+__device__ __forceinline__ void ll_publish(unsigned long long* slots, int b, double v, unsigned epoch) {
+  const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+  const unsigned long long w0 = (bits & 0xffffffffull) | ((unsigned long long)epoch << 32);
+  const unsigned long long w1 = (bits >> 32) | ((unsigned long long)epoch << 32);
+  asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(slots + (size_t)LL_STRIDE * b), "l"(w0), "l"(w1) : "memory");
+}
+constexpr int LL_PER_LANE = 5;  // up to 160 CTAs
+#ifndef P_LL_SLEEP
+#define P_LL_SLEEP 0
+#endif
+__device__ __forceinline__ double ll_gather_sum(const unsigned long long* slots, int G, unsigned epoch, int* err) {
+  const int lane = threadIdx.x & 31;
+  unsigned long long w0[LL_PER_LANE], w1[LL_PER_LANE];
+  unsigned spins = 0;
+  bool ok;
+  if (P_LL_SLEEP > 0) __nanosleep(P_LL_SLEEP);  // the answer cannot be there earlier than one L2 round trip: do not add load
+  do {
+    ok = true;
+#pragma unroll
+    for (int q = 0; q < LL_PER_LANE; ++q) {
+      const int s = lane + 32 * q;
+      if (s < G) asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0[q]), "=l"(w1[q]) : "l"(slots + (size_t)LL_STRIDE * s) : "memory");
+    }
+#pragma unroll
+    for (int q = 0; q < LL_PER_LANE; ++q) {
+      const int s = lane + 32 * q;
+      if (s < G) ok = ok && ((unsigned)(w0[q] >> 32) == epoch) && ((unsigned)(w1[q] >> 32) == epoch);
+    }
+    if (++spins > (1u << 22)) { *err = 1; break; }  // bounded: a fault can never hang the GPU
+  } while (!__all_sync(0xffffffffu, ok));
+  double s = 0.0;
+#pragma unroll
+  for (int q = 0; q < LL_PER_LANE; ++q) {
+    const int sl = lane + 32 * q;
+    if (sl < G) s += __longlong_as_double((long long)((w0[q] & 0xffffffffull) | (w1[q] << 32)));
+  }
+  return warp_sum(s);
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  unsigned done = 0, spins = 0;
+  while (!done) {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(a), "r"(parity) : "memory");
+    if (++spins > (1u << 26)) break;
+  }
+}
+__device__ __forceinline__ void tma_bulk_load(void* smem_dst, const void* gsrc, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+               : "memory");
+}
+
+__global__ void __launch_bounds__(RS_THREADS, 1) resident_arnoldi_kernel(ResidentParams P) {
+  if (P.st->status != 0) return;  // uniform across the grid: nobody reaches a barrier
+  extern __shared__ __align__(16) double rsm[];
+  const int cpc = P.cpc;
+  const int rows_cap = 2 * cpc;              // rows of one stage
+  double* stage0 = rsm;
+  double* stage1 = rsm + rows_cap;
+  __shared__ uint64_t mbar[2];
+  __shared__ double red[32];
+  __shared__ double hshare;
+  const int tid = threadIdx.x, b = blockIdx.x, G = P.G;
+  const int64_t c0 = (int64_t)b * cpc;
+  const int ncell = (int)max((int64_t)0, min((int64_t)cpc, P.NC - c0));  // even (NC and cpc are even)
+  const int nrow = 2 * ncell;
+  const unsigned seg_bytes = (unsigned)ncell * 8u;
+  if (tid == 0) {
+    mbar_init(&mbar[0], 1);
+    mbar_init(&mbar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  // ---- 1. w = J(u) v_k for this CTA's rows, into registers
+  const double* vk = P.V[P.k - 1];
+  double w[RS_RR];
+  const int N = P.N;
+  const int64_t N2 = (int64_t)N * N, NC = P.NC;
+#pragma unroll
+  for (int q = 0; q < RS_RR; ++q) {
+    const int lr = tid + RS_THREADS * q;
+    w[q] = 0.0;
+    if (lr < nrow) {
+      const int s = lr >= ncell;
+      const int64_t c = c0 + (lr - s * ncell);
+      int64_t cim, cip, cjm, cjp, ckm = 0, ckp = 0;
+      if (P.dim == 3) {
+        const int kk = (int)(c / N2);
+        const int r = (int)(c - (int64_t)kk * N2);
+        const int j = r / N, i = r - j * N;
+        cim = c + ((i == 0) ? (N - 1) : -1); cip = c + ((i + 1 == N) ? -(N - 1) : 1);
+        cjm = c + ((j == 0) ? (int64_t)(N - 1) * N : -N); cjp = c + ((j + 1 == N) ? -(int64_t)(N - 1) * N : N);
+        ckm = c + ((kk == 0) ? (int64_t)(N - 1) * N2 : -N2); ckp = c + ((kk + 1 == N) ? -(int64_t)(N - 1) * N2 : N2);
+      } else {
+        const int j = (int)(c / N), i = (int)(c - (int64_t)j * N);
+        cim = c + ((i == 0) ? (N - 1) : -1); cip = c + ((i + 1 == N) ? -(N - 1) : 1);
+        cjm = c + ((j == 0) ? (int64_t)(N - 1) * N : -N); cjp = c + ((j + 1 == N) ? -(int64_t)(N - 1) * N : N);
+      }
+      const double* x = vk + (int64_t)s * NC;
+      const double xc = x[c];
+      double lap = x[cim] + x[cip] + x[cjp] + x[cjm] - 4.0 * xc;
+      if (P.dim == 3) lap = lap + (x[ckp] + x[ckm] - 2.0 * xc);
+      const double uc = P.u[c], vc = P.u[c + NC], dc = vk[c], ec = vk[c + NC];
+      const double uv2 = 2.0 * uc * vc, uu = uc * uc;
+      w[q] = s ? (P.a * lap + (P.A - uv2) * dc - uu * ec) : (P.a * lap + (uv2 - (P.A + 1.0)) * dc + uu * ec);
+    }
+  }
+  // ---- 2. (iterated) modified Gram-Schmidt with the basis streamed through shared memory by TMA bulk copies
+  const int k = P.k, total = P.passes * k;
+  auto issue = [&](int t) {  // load basis vector (t % k) into stage (t & 1)
+    if (tid == 0 && nrow > 0) {
+      const double* src = P.V[t % k];
+      double* dst = (t & 1) ? stage1 : stage0;
+      mbar_expect_tx(&mbar[t & 1], 2u * seg_bytes);
+      tma_bulk_load(dst, src + c0, seg_bytes, &mbar[t & 1]);
+      tma_bulk_load(dst + ncell, src + NC + c0, seg_bytes, &mbar[t & 1]);
+    }
+  };
+  long long acc_wait = 0, acc_dot = 0, acc_gather = 0, acc_update = 0;
+  issue(0);
+  for (int t = 0; t < total; ++t) {
+    const int i = t % k;
+    __syncthreads();                     // every thread is done reading stage (t+1)&1 (used by step t-1)
+    if (!P.late_issue && t + 1 < total) issue(t + 1);     // prefetch the next basis vector underneath this step
+    const double* vs = (t & 1) ? stage1 : stage0;
+    long long tc0 = clock64();
+    if (nrow > 0) mbar_wait(&mbar[t & 1], (unsigned)((t >> 1) & 1));
+    long long tc1 = clock64();
+    double d = 0.0;
+#pragma unroll
+    for (int q = 0; q < RS_RR; ++q) {
+      const int lr = tid + RS_THREADS * q;
+      if (lr < nrow) d = fma(vs[lr], w[q], d);
+    }
+    d = block_sum(d, red);
+    long long tc2 = clock64();
+    // publish this CTA's partial and gather everybody's in ONE round trip (no atomics, no separate barrier): the
+    // reduction over CTAs is done identically by every CTA, in a fixed order -> deterministic and identical everywhere
+    unsigned long long* slots = P.slots + (size_t)(t & 1) * LL_STRIDE * LL_MAXG;
+    const unsigned epoch = P.epoch_base + (unsigned)t + 1u;
+    if (tid == 0) ll_publish(slots, b, d, epoch);
+    if (tid < 32) {
+      const double s = ll_gather_sum(slots, G, epoch, P.err);
+      if (tid == 0) hshare = s;
+    }
+    __syncthreads();
+    if (P.late_issue && t + 1 < total) issue(t + 1);
+    long long tc3 = clock64();
+    const double h = hshare;
+#pragma unroll
+    for (int q = 0; q < RS_RR; ++q) {
+      const int lr = tid + RS_THREADS * q;
+      if (lr < nrow) w[q] = fma(-h, vs[lr], w[q]);
+    }
+    if (b == 0 && tid == 0) P.h[i] = (t < k) ? h : P.h[i] + h;
+    if (P.dbg && tid == 0) {
+      long long tc4 = clock64();
+      acc_wait += tc1 - tc0; acc_dot += tc2 - tc1; acc_gather += tc3 - tc2; acc_update += tc4 - tc3;
+    }
+  }
+  if (P.dbg && tid == 0) {  // per-CTA phase totals (cycles), written once: [b*4 + phase]; steps in dbg[4*G]
+    P.dbg[4 * b + 0] += (double)acc_wait; P.dbg[4 * b + 1] += (double)acc_dot; P.dbg[4 * b + 2] += (double)acc_gather; P.dbg[4 * b + 3] += (double)acc_update;
+    if (b == 0) P.dbg[4 * G] += (double)total;
+  }
+  // ---- 3. ||w||, Givens (CTA 0), normalise, store v_{k+1}
+  double nacc = 0.0;
+#pragma unroll
+  for (int q = 0; q < RS_RR; ++q) nacc = fma(w[q], w[q], nacc);
+  nacc = block_sum(nacc, red);
+  {
+    unsigned long long* slots = P.slots + (size_t)(total & 1) * LL_STRIDE * LL_MAXG;
+    const unsigned epoch = P.epoch_base + (unsigned)total + 1u;
+    if (tid == 0) ll_publish(slots, b, nacc, epoch);
+    if (tid < 32) {
+      const double s = ll_gather_sum(slots, G, epoch, P.err);
+      if (tid == 0) hshare = s;
+    }
+  }
+  __syncthreads();
+  const double hbis = sqrt(hshare);
+  const double inv = hbis > 0.0 ? 1.0 / hbis : 0.0;
+#pragma unroll
+  for (int q = 0; q < RS_RR; ++q) {
+    const int lr = tid + RS_THREADS * q;
+    if (lr < nrow) {
+      const int s = lr >= ncell;
+      P.vnew[(int64_t)s * NC + c0 + (lr - s * ncell)] = w[q] * inv;
+    }
+  }
+  if (b == 0 && tid == 0) {  // same recurrence as givens_kernel
+    GmresState* st = P.st;
+    double* Rk = P.R + (int64_t)(k - 1) * k / 2;
+    if (P.hraw) {
+      double* hr = P.hraw + (int64_t)(k - 1) * (k + 2) / 2;
+      for (int i = 0; i < k; ++i) hr[i] = P.h[i];
+      hr[k] = hbis;
+    }
+    for (int i = 0; i < k; ++i) Rk[i] = P.h[i];
+    for (int i = 0; i + 1 < k; ++i) {
+      const double rt = P.cs[i] * Rk[i] + P.sn[i] * Rk[i + 1];
+      Rk[i + 1] = P.sn[i] * Rk[i] - P.cs[i] * Rk[i + 1];
+      Rk[i] = rt;
+    }
+    double c, s_, rho;
+    sym_givens(Rk[k - 1], hbis, c, s_, rho);
+    P.cs[k - 1] = c; P.sn[k - 1] = s_; Rk[k - 1] = rho;
+    const double zeta = s_ * P.z[k - 1];
+    P.z[k - 1] = c * P.z[k - 1];
+    P.z[k] = zeta;
+    const double rnorm = fabs(zeta);
+    st->rnorm = rnorm; st->hbis = hbis; st->k = k; st->inv_h = inv;
+    int status = 0;
+    if (*P.err) status = B200_LS_NONFINITE;
+    else if (!(rnorm == rnorm) || isinf(rnorm) || !(hbis == hbis) || isinf(hbis)) status = B200_LS_NONFINITE;
+    else if (rnorm <= st->tol) status = B200_LS_SOLVED;
+    else if (st->iter_base + k >= st->itmax) status = B200_LS_MAXITERS;
+    else if (hbis <= 1.8189894035458565e-12) status = B200_LS_BREAKDOWN;
+    else if (k >= st->kmax_cycle) status = -1;
+    st->status = status;
+  }
+}
 }  // namespace
 
 struct b200_gmres {
@@ -473,6 +759,10 @@ struct b200_gmres {
   int64_t hraw_cap;
   GmresState* d_state;
   GmresState* h_state;  // pinned
+  unsigned* d_bar;      // resident engine: error flag (+ legacy barrier counter)
+  unsigned long long* d_slots;  // resident engine: LL publication slots [2][160][2]
+  unsigned ll_epoch;
+  int dbg_on;
 };
 
 namespace {
@@ -648,6 +938,7 @@ int32_t b200_gmres_create(b200_ctx* ctx, int64_t n, const b200_gmres_opts* opts,
   gm->kcap = 0; gm->d_Vptrs = nullptr; gm->vptr_cap = 0;
   gm->d_h = gm->d_hacc = gm->d_R = gm->d_cs = gm->d_sn = gm->d_z = gm->d_y = gm->d_partial = nullptr;
   gm->d_hraw = nullptr; gm->hraw_cap = 0;
+  gm->d_bar = nullptr; gm->d_slots = nullptr; gm->ll_epoch = 0; gm->dbg_on = 0;
   // streaming grid: 4 CTAs of 256 threads per SM, fewer for small n (at least 512 rows per CTA)
   int64_t g = std::min<int64_t>((int64_t)ctx->sm_count * 4, std::max<int64_t>(1, n / 512));
   gm->G = (int)g;
@@ -658,6 +949,10 @@ int32_t b200_gmres_create(b200_ctx* ctx, int64_t n, const b200_gmres_opts* opts,
   CUDA_TRY(ctx, cudaMalloc(&gm->d_norm_partial2, sizeof(double) * std::max(gm->G, B200_RED_MAX_BLOCKS)));
   CUDA_TRY(ctx, cudaMalloc(&gm->d_state, sizeof(GmresState)));
   CUDA_TRY(ctx, cudaMallocHost(&gm->h_state, sizeof(GmresState)));
+  CUDA_TRY(ctx, cudaMalloc(&gm->d_bar, 4 * sizeof(unsigned)));
+  CUDA_TRY(ctx, cudaMalloc(&gm->d_slots, sizeof(unsigned long long) * 2 * LL_STRIDE * LL_MAXG));
+  CUDA_TRY(ctx, cudaMemsetAsync(gm->d_slots, 0, sizeof(unsigned long long) * 2 * LL_STRIDE * LL_MAXG, ctx->stream));
+  CUDA_TRY(ctx, cudaMemsetAsync(gm->d_bar, 0, 4 * sizeof(unsigned), ctx->stream));
   int mem = opts->restart > 0 ? opts->restart : (opts->memory > 0 ? opts->memory : 20);
   if (mem > n) mem = (int)n;
   int32_t s = gm_reserve(gm, std::max(mem + 1, 32));
@@ -674,6 +969,8 @@ int32_t b200_gmres_destroy(b200_gmres* gm) {
   cudaFree(gm->w); cudaFree(gm->r0); cudaFree(gm->d_norm_partial); cudaFree(gm->d_norm_partial2); cudaFree(gm->d_state);
   if (gm->d_hraw) cudaFree(gm->d_hraw);
   cudaFreeHost(gm->h_state);
+  if (gm->d_bar) cudaFree(gm->d_bar);
+  if (gm->d_slots) cudaFree(gm->d_slots);
   gm_free_arrays(gm);
   delete gm;
   return B200_OK;
@@ -691,6 +988,14 @@ int32_t b200_gmres_keep_hessenberg(b200_gmres* gm, int64_t capacity) {
   if (gm->d_hraw) { cudaFree(gm->d_hraw); gm->d_hraw = nullptr; }
   gm->hraw_cap = capacity;
   if (capacity > 0) CUDA_TRY(ctx, cudaMalloc(&gm->d_hraw, sizeof(double) * capacity));
+  return B200_OK;
+}
+// test hook: phase timers of the resident kernel (cycles summed over steps, CTA 0): wait, dot, gather, update, steps
+int32_t b200_gmres_debug(b200_gmres* gm, int32_t enable, double* out_host, int32_t count) {
+  b200_ctx* ctx = gm->ctx;
+  if (out_host && count > 0) B200_TRY(b200_memcpy_d2h(ctx, out_host, gm->d_norm_partial2, sizeof(double) * count));
+  gm->dbg_on = enable;
+  CUDA_TRY(ctx, cudaMemsetAsync(gm->d_norm_partial2, 0, sizeof(double) * 1024, ctx->stream));
   return B200_OK;
 }
 int32_t b200_gmres_get_hessenberg(b200_gmres* gm, double* out_host, int64_t count) {
@@ -714,6 +1019,30 @@ int32_t b200_gmres_solve(b200_gmres* gm, b200_linop* op, const double* b, double
   if (blk < 0) blk = (int)std::min<int64_t>(JT, std::max<int64_t>(1, ((int64_t)64 << 20) / (8 * n)));
   if (blk > JT) blk = JT;
   if (orth == B200_ORTH_MGS) blk = 0;
+  // resident engine: built-in Brusselator operator with the exact JVP, even cell count, one CTA per SM holds its rows
+  bool resident = false;
+  int rs_G = 0, rs_cpc = 0, rs_passes = (orth == B200_ORTH_CGS2) ? 2 : 1;
+  int64_t rs_NC = 0;
+  size_t rs_smem = 0;
+  if (o.engine != B200_ENGINE_MULTIKERNEL && op->kind == LINOP_PROBLEM && op->jvp_mode == B200_JVP_EXACT &&
+      (op->prob->kind == B200_PROB_BRUSS2D || op->prob->kind == B200_PROB_BRUSS3D)) {
+    rs_NC = n / 2;
+    rs_G = ctx->sm_count;
+    int64_t cpc = (rs_NC + rs_G - 1) / rs_G;
+    cpc = (cpc + 1) & ~(int64_t)1;
+    rs_cpc = (int)cpc;
+    rs_smem = sizeof(double) * 4 * (size_t)rs_cpc;  // two stages of 2 * cpc rows
+    const bool fits = (rs_NC % 2 == 0) && (2 * cpc <= (int64_t)RS_RR * RS_THREADS) && (rs_smem + 1024 <= ctx->smem_optin);
+    const bool wanted = (o.engine == B200_ENGINE_RESIDENT) || (o.engine == B200_ENGINE_AUTO && n >= 200000);
+    if (fits && wanted) {
+      resident = true;
+      CUDA_TRY(ctx, cudaFuncSetAttribute(resident_arnoldi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem));
+    } else if (o.engine == B200_ENGINE_RESIDENT) {
+      return ctx->fail(B200_ERR_UNSUPPORTED, "resident GMRES engine: problem does not fit (needs an even cell count and <= 7168 cells per SM)", __FILE__, __LINE__);
+    }
+  } else if (o.engine == B200_ENGINE_RESIDENT) {
+    return ctx->fail(B200_ERR_UNSUPPORTED, "resident GMRES engine needs a built-in Brusselator operator with the exact JVP", __FILE__, __LINE__);
+  }
   const int64_t itmax = o.itmax > 0 ? o.itmax : n;
   const int restart_len = o.restart > 0 ? (int)std::min<int64_t>(o.restart, n) : 0;
   const int ew_grid = (int)std::min<int64_t>((n + GM_THREADS * 2 - 1) / (GM_THREADS * 2), (int64_t)ctx->sm_count * 8);
@@ -770,6 +1099,29 @@ int32_t b200_gmres_solve(b200_gmres* gm, b200_linop* op, const double* b, double
       rc = gm_ensure_vector(gm, k);
       if (rc == B200_ERR_NOMEM || k + 40 > 6000) { oom = 1; --k; break; }  // 48 KB of coefficients in shared memory
       B200_TRY(rc);
+      if (resident) {
+        // one cooperative kernel: JVP -> (iterated) MGS with TMA-staged basis -> norm -> Givens -> v_{k+1}
+        ResidentParams RP;
+        RP.dim = op->prob->kind == B200_PROB_BRUSS2D ? 2 : 3;
+        RP.N = op->prob->N; RP.k = k; RP.passes = rs_passes; RP.G = rs_G; RP.NC = rs_NC; RP.cpc = rs_cpc;
+        RP.a = op->prob->a; RP.A = op->prob->A; RP.u = op->u; RP.V = (const double* const*)gm->d_Vptrs; RP.vnew = gm->V[k];
+        if (gm->ll_epoch > 0xfff00000u) {  // epoch space nearly exhausted: start over with clean slots
+          CUDA_TRY(ctx, cudaMemsetAsync(gm->d_slots, 0, sizeof(unsigned long long) * 2 * LL_STRIDE * LL_MAXG, ctx->stream));
+          gm->ll_epoch = 0;
+        }
+        RP.dbg = gm->dbg_on ? gm->d_norm_partial2 : nullptr;
+        { static const int li = getenv("B200_RS_LATE") ? atoi(getenv("B200_RS_LATE")) : 0; RP.late_issue = li; }
+        RP.slots = gm->d_slots; RP.epoch_base = gm->ll_epoch; RP.err = reinterpret_cast<int*>(gm->d_bar + 1);
+        gm->ll_epoch += (unsigned)(rs_passes * k + 2);
+        RP.h = gm->d_h; RP.R = gm->d_R; RP.cs = gm->d_cs; RP.sn = gm->d_sn; RP.z = gm->d_z;
+        RP.hraw = (gm->d_hraw && (int64_t)k * (k + 3) / 2 <= gm->hraw_cap) ? gm->d_hraw : nullptr;
+        RP.st = gm->d_state;
+        void* args[] = {&RP};
+        if (ctx->prof_on) ctx->prof_begin(B200_KID_RESIDENT, (rs_passes * (double)k + 3.0) * Bv);
+        CUDA_TRY(ctx, cudaLaunchCooperativeKernel((const void*)resident_arnoldi_kernel, dim3(rs_G), dim3(RS_THREADS), args, rs_smem, ctx->stream));
+        ctx->launches++;
+        if (ctx->prof_on) ctx->prof_end();
+      } else {
       // w = A v_k
       B200_TRY(b200i_linop_apply(op, gm->V[k - 1], gm->w));
       if (orth == B200_ORTH_MGS) {
@@ -814,6 +1166,7 @@ int32_t b200_gmres_solve(b200_gmres* gm, b200_linop* op, const double* b, double
                (gm->d_hraw && (int64_t)k * (k + 3) / 2 <= gm->hraw_cap) ? gm->d_hraw : nullptr);
       }
       PLAUNCH(ctx, B200_KID_NORMALIZE, 2.0 * Bv, normalize_kernel, ew_grid, GM_THREADS, 0, gm->d_state, 1, gm->w, gm->V[k], n);
+      }  // multi-kernel engine
       CHECK_LAUNCH(ctx);
       const bool must_check = (k % check_every == 0) || (iters_total + k >= itmax) || (restart_len > 0 && k >= restart_len);
       if (must_check) {
@@ -834,7 +1187,8 @@ int32_t b200_gmres_solve(b200_gmres* gm, b200_linop* op, const double* b, double
       double orthb = (orth == B200_ORTH_CGS) ? (2.0 * j + 2.0) : (orth == B200_ORTH_CGS2) ? (4.0 * j + 4.0) : (3.0 * j + 1.0);
       if (blk > 0 && j > blk && orth != B200_ORTH_MGS)  // blocked: basis crosses HBM once per pass; w is L2 resident
         orthb = ((orth == B200_ORTH_CGS2) ? 2.0 : 1.0) * (j + 2.0);
-      bytes += (3.0 + 2.0 + orthb) * Bv;
+      if (resident) bytes += (rs_passes * (double)j + 3.0) * Bv;  // basis once per pass + u, v_k reads + v_{k+1} store
+      else bytes += (3.0 + 2.0 + orthb) * Bv;
     }
     // x += V_k y
     if (k > 0 && cycle_status != B200_LS_NONFINITE) {
