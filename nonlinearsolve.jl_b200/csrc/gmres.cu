@@ -514,18 +514,27 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned target, int
 // Every slot sits in its own 256-byte block so that the all-to-all polls spread over the L2 slices instead of hammering one.
 constexpr int LL_STRIDE = 32;  // u64 words per slot
 constexpr int LL_MAXG = 160;
-__device__ __forceinline__ void ll_publish(unsigned long long* slots, int b, double v, unsigned epoch) {
+// PUSH model (NCCL-LL all-gather style): CTA b posts its word pair into slot b of EVERY destination CTA's private receive
+// buffer (posted, uncoalesced stores that nobody waits on); each CTA then polls only its own dense buffer with coalesced
+// 128-bit loads (G * 16 bytes = 19 cache lines, no reader contention).  Called by all lanes of warp 0.
+__device__ __forceinline__ void ll_publish(unsigned long long* slots, int b, int G, double v, unsigned epoch) {
   const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
   const unsigned long long w0 = (bits & 0xffffffffull) | ((unsigned long long)epoch << 32);
   const unsigned long long w1 = (bits >> 32) | ((unsigned long long)epoch << 32);
-  asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(slots + (size_t)LL_STRIDE * b), "l"(w0), "l"(w1) : "memory");
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int q = 0; q < 5; ++q) {
+    const int dest = lane + 32 * q;
+    if (dest < G) asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(slots + 2 * ((size_t)dest * LL_MAXG + b)), "l"(w0), "l"(w1) : "memory");
+  }
 }
 constexpr int LL_PER_LANE = 5;  // up to 160 CTAs
 #ifndef P_LL_SLEEP
 #define P_LL_SLEEP 0
 #endif
-__device__ __forceinline__ double ll_gather_sum(const unsigned long long* slots, int G, unsigned epoch, int* err) {
+__device__ __forceinline__ double ll_gather_sum(const unsigned long long* slots, int G, unsigned epoch, int* err, unsigned* rounds = nullptr) {
   const int lane = threadIdx.x & 31;
+  const unsigned long long* mine = slots + 2 * (size_t)blockIdx.x * LL_MAXG;  // this CTA's receive buffer
   unsigned long long w0[LL_PER_LANE], w1[LL_PER_LANE];
   unsigned spins = 0;
   bool ok;
@@ -535,7 +544,7 @@ __device__ __forceinline__ double ll_gather_sum(const unsigned long long* slots,
 #pragma unroll
     for (int q = 0; q < LL_PER_LANE; ++q) {
       const int s = lane + 32 * q;
-      if (s < G) asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0[q]), "=l"(w1[q]) : "l"(slots + (size_t)LL_STRIDE * s) : "memory");
+      if (s < G) asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0[q]), "=l"(w1[q]) : "l"(mine + 2 * s) : "memory");
     }
 #pragma unroll
     for (int q = 0; q < LL_PER_LANE; ++q) {
@@ -544,6 +553,7 @@ __device__ __forceinline__ double ll_gather_sum(const unsigned long long* slots,
     }
     if (++spins > (1u << 22)) { *err = 1; break; }  // bounded: a fault can never hang the GPU
   } while (!__all_sync(0xffffffffu, ok));
+  if (rounds) *rounds += spins;
   double s = 0.0;
 #pragma unroll
   for (int q = 0; q < LL_PER_LANE; ++q) {
@@ -640,6 +650,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) resident_arnoldi_kernel(Residen
     }
   };
   long long acc_wait = 0, acc_dot = 0, acc_gather = 0, acc_update = 0;
+  unsigned poll_rounds = 0;
   issue(0);
   for (int t = 0; t < total; ++t) {
     const int i = t % k;
@@ -659,11 +670,13 @@ __global__ void __launch_bounds__(RS_THREADS, 1) resident_arnoldi_kernel(Residen
     long long tc2 = clock64();
     // publish this CTA's partial and gather everybody's in ONE round trip (no atomics, no separate barrier): the
     // reduction over CTAs is done identically by every CTA, in a fixed order -> deterministic and identical everywhere
-    unsigned long long* slots = P.slots + (size_t)(t & 1) * LL_STRIDE * LL_MAXG;
+    unsigned long long* slots = P.slots + (size_t)(t & 1) * 2 * LL_MAXG * LL_MAXG;
     const unsigned epoch = P.epoch_base + (unsigned)t + 1u;
-    if (tid == 0) ll_publish(slots, b, d, epoch);
     if (tid < 32) {
-      const double s = ll_gather_sum(slots, G, epoch, P.err);
+      if (tid == 0) red[0] = d;  // block_sum leaves the total in thread 0 only
+      __syncwarp();
+      ll_publish(slots, b, G, red[0], epoch);
+      const double s = ll_gather_sum(slots, G, epoch, P.err, &poll_rounds);
       if (tid == 0) hshare = s;
     }
     __syncthreads();
@@ -683,7 +696,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) resident_arnoldi_kernel(Residen
   }
   if (P.dbg && tid == 0) {  // per-CTA phase totals (cycles), written once: [b*4 + phase]; steps in dbg[4*G]
     P.dbg[4 * b + 0] += (double)acc_wait; P.dbg[4 * b + 1] += (double)acc_dot; P.dbg[4 * b + 2] += (double)acc_gather; P.dbg[4 * b + 3] += (double)acc_update;
-    if (b == 0) P.dbg[4 * G] += (double)total;
+    if (b == 0) { P.dbg[4 * G] += (double)total; P.dbg[4 * G + 1] += (double)poll_rounds; }
   }
   // ---- 3. ||w||, Givens (CTA 0), normalise, store v_{k+1}
   double nacc = 0.0;
@@ -691,10 +704,12 @@ __global__ void __launch_bounds__(RS_THREADS, 1) resident_arnoldi_kernel(Residen
   for (int q = 0; q < RS_RR; ++q) nacc = fma(w[q], w[q], nacc);
   nacc = block_sum(nacc, red);
   {
-    unsigned long long* slots = P.slots + (size_t)(total & 1) * LL_STRIDE * LL_MAXG;
+    unsigned long long* slots = P.slots + (size_t)(total & 1) * 2 * LL_MAXG * LL_MAXG;
     const unsigned epoch = P.epoch_base + (unsigned)total + 1u;
-    if (tid == 0) ll_publish(slots, b, nacc, epoch);
     if (tid < 32) {
+      if (tid == 0) red[0] = nacc;
+      __syncwarp();
+      ll_publish(slots, b, G, red[0], epoch);
       const double s = ll_gather_sum(slots, G, epoch, P.err);
       if (tid == 0) hshare = s;
     }
@@ -950,8 +965,8 @@ int32_t b200_gmres_create(b200_ctx* ctx, int64_t n, const b200_gmres_opts* opts,
   CUDA_TRY(ctx, cudaMalloc(&gm->d_state, sizeof(GmresState)));
   CUDA_TRY(ctx, cudaMallocHost(&gm->h_state, sizeof(GmresState)));
   CUDA_TRY(ctx, cudaMalloc(&gm->d_bar, 4 * sizeof(unsigned)));
-  CUDA_TRY(ctx, cudaMalloc(&gm->d_slots, sizeof(unsigned long long) * 2 * LL_STRIDE * LL_MAXG));
-  CUDA_TRY(ctx, cudaMemsetAsync(gm->d_slots, 0, sizeof(unsigned long long) * 2 * LL_STRIDE * LL_MAXG, ctx->stream));
+  CUDA_TRY(ctx, cudaMalloc(&gm->d_slots, sizeof(unsigned long long) * 4 * LL_MAXG * LL_MAXG));
+  CUDA_TRY(ctx, cudaMemsetAsync(gm->d_slots, 0, sizeof(unsigned long long) * 4 * LL_MAXG * LL_MAXG, ctx->stream));
   CUDA_TRY(ctx, cudaMemsetAsync(gm->d_bar, 0, 4 * sizeof(unsigned), ctx->stream));
   int mem = opts->restart > 0 ? opts->restart : (opts->memory > 0 ? opts->memory : 20);
   if (mem > n) mem = (int)n;
@@ -1106,7 +1121,7 @@ int32_t b200_gmres_solve(b200_gmres* gm, b200_linop* op, const double* b, double
         RP.N = op->prob->N; RP.k = k; RP.passes = rs_passes; RP.G = rs_G; RP.NC = rs_NC; RP.cpc = rs_cpc;
         RP.a = op->prob->a; RP.A = op->prob->A; RP.u = op->u; RP.V = (const double* const*)gm->d_Vptrs; RP.vnew = gm->V[k];
         if (gm->ll_epoch > 0xfff00000u) {  // epoch space nearly exhausted: start over with clean slots
-          CUDA_TRY(ctx, cudaMemsetAsync(gm->d_slots, 0, sizeof(unsigned long long) * 2 * LL_STRIDE * LL_MAXG, ctx->stream));
+          CUDA_TRY(ctx, cudaMemsetAsync(gm->d_slots, 0, sizeof(unsigned long long) * 4 * LL_MAXG * LL_MAXG, ctx->stream));
           gm->ll_epoch = 0;
         }
         RP.dbg = gm->dbg_on ? gm->d_norm_partial2 : nullptr;
