@@ -5,7 +5,10 @@
 
 Workload (BASELINE.json configs[2], the configuration the metric is quoted on): 3D Brusselator N=100 (10^6 cells, 2*10^6
 unknowns), NewtonRaphson(linsolve = KrylovJL_GMRES()) with the matrix-free exact JVP, abstol = 1e-8 (the reference
-test's value, sparsity_tests__item1.jl:54), GMRES tolerances inherited from the nonlinear solve (solve.jl:203).
+test's value, sparsity_tests__item1.jl:54), GMRES tolerances inherited from the nonlinear solve (solve.jl:203), Krylov.jl's
+default orthogonalisation (modified Gram-Schmidt, no reorthogonalisation, no restart) — `--orth cgs2` times the
+reorthogonalised variant (Krylov's `reorthogonalization = true`), which is the library's own default because it is the
+robust one on stiffer grids.
 One "step" = one complete Newton solve from the synthetic initial condition (3 Newton iterations, ~2000 Arnoldi
 iterations): a fixed, deterministic amount of hot-path work.  `value` = GMRES JVPs (Arnoldi iterations) per second with
 inputs resident in HBM; `e2e` = the same through the host-buffer call (H2D of u0, solve, D2H of u and resid inside the
@@ -104,8 +107,8 @@ def host_cpus():
 _CPU_THREADS = {}
 
 
-def cpu_sample(N, steps, count):
-    """Time the CPU oracle on a bounded sample of the workload: `count` Arnoldi iterations (exact JVP + CGS2
+def cpu_sample(N, steps, count, orth="mgs"):
+    """Time the CPU oracle on a bounded sample of the workload: `count` Arnoldi iterations (exact JVP + Gram-Schmidt
     orthogonalisation, the same arithmetic as the GPU arm) at the workload's mean Krylov basis size, using the thread
     count (all usable cores, or half / a quarter of them when SMT or memory-bandwidth saturation makes that faster)
     that a one-iteration calibration finds best."""
@@ -116,22 +119,23 @@ def cpu_sample(N, steps, count):
     P = po.OracleProblem.bruss3d(N)
     u = P.u0(1)
     k0 = MEAN_BASIS.get(N, max(8, int(3.45 * N)))
+    ocode = po.ORTH_MGS if orth == "mgs" else po.ORTH_CGS2
     if N not in _CPU_THREADS:
         T = host_cpus()
         best = None
         for cand in sorted({T, max(1, T // 2), max(1, T // 4)}, reverse=True):
             po.set_threads(cand)
-            t = po.arnoldi_sample(P, u, k0, 1, po.ORTH_CGS2)
+            t = po.arnoldi_sample(P, u, k0, 1, ocode)
             if best is None or t < best[0]:
                 best = (t, cand)
         _CPU_THREADS[N] = best[1]
     po.set_threads(_CPU_THREADS[N])
     times = []
     for _ in range(steps):
-        times.append(po.arnoldi_sample(P, u, k0, count, po.ORTH_CGS2))
+        times.append(po.arnoldi_sample(P, u, k0, count, ocode))
     cores = _CPU_THREADS[N]
-    sample = "%d Arnoldi iterations (exact JVP + CGS2 Gram-Schmidt + normalise) at the solve's mean basis size k=%d, N=%d, %d OpenMP threads" % (
-        count, k0, N, cores)
+    sample = "%d Arnoldi iterations (exact JVP + %s Gram-Schmidt + normalise) at the solve's mean basis size k=%d, N=%d, %d OpenMP threads" % (
+        count, orth.upper(), k0, N, cores)
     return times, cores, sample, k0
 
 
@@ -142,8 +146,8 @@ def run_reference(args):
         return
     count = 4
     for _ in range(min(args.warmup, 1)):
-        cpu_sample(args.N, 1, 1)
-    times, cores, sample, k0 = cpu_sample(args.N, args.steps, count)
+        cpu_sample(args.N, 1, 1, args.orth)
+    times, cores, sample, k0 = cpu_sample(args.N, args.steps, count, args.orth)
     total = sum(times)
     val = args.steps * count / total
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -162,7 +166,7 @@ def ensemble_params(K):
     return 3.4 + 0.1 * (m % 64) / 64.0, 1.0 + 0.05 * (m // 64) / 128.0
 
 
-def run_ensemble(nls, torch, dist, ctx, rank, world, K_total=8192, N=32, reps=2):
+def run_ensemble(nls, torch, dist, ctx, rank, world, K_total=8192, N=32, reps=2, orth="mgs"):
     """Config 5: ensemble of K_total independent 2D Brusselator problems, contiguous blocks sharded over the ranks
     (strong scaling, no data-path collective during the solve); after the solve one all-gather of the solutions and one
     all-reduce of the status counters over NCCL, both inside the timed region."""
@@ -174,7 +178,7 @@ def run_ensemble(nls, torch, dist, ctx, rank, world, K_total=8192, N=32, reps=2)
     dp = nls._DeviceProblem(ctx, nls.NonlinearProblem(nls.Brusselator2D(N), None, (3.4, 1.0, 10.0), ctx=ctx))
     u0 = np.tile(dp.u0().to_host(), K)
     d_u0, d_A, d_B = ctx.to_device(u0), ctx.to_device(A[lo:hi]), ctx.to_device(B[lo:hi])
-    alg = nls.NewtonRaphson(linsolve=nls.KrylovJL_GMRES(orth="cgs2"))
+    alg = nls.NewtonRaphson(linsolve=nls.KrylovJL_GMRES(orth=orth))
     cache = nls.EnsembleCache(ctx, N, K, 10.0, alg, abstol=1e-8)
     gathered = torch.empty(K_total * n if world > 1 else 0, dtype=torch.float64, device="cuda")
     u_loc = torch.as_tensor(cache.u_out, device="cuda")
@@ -206,7 +210,7 @@ def run_ensemble(nls, torch, dist, ctx, rank, world, K_total=8192, N=32, reps=2)
             times.append(t.item())
     ms = sum(times) / len(times)
     nsucc, tot_steps, tot_jvp, worst = stats.tolist()
-    return {"workload": "ensemble_%d_x_bruss2d_N%d_newtonraphson_gmres" % (K_total, N), "n_problems": K_total, "scaling": "strong",
+    return {"workload": "ensemble_%d_x_bruss2d_N%d_newtonraphson_gmres" % (K_total, N), "n_problems": K_total, "scaling": "strong", "orth": orth,
             "problems_per_s": K_total / (ms * 1e-3), "ms": ms, "n_success": int(nsucc), "newton_steps": int(tot_steps), "gmres_jvps": int(tot_jvp),
             "jvps_per_s": tot_jvp / (ms * 1e-3), "worst_resid_inf": worst, "collectives": "all_gather(u) + all_reduce(stats) via NCCL" if dist is not None else "none (1 rank)"}
 
@@ -237,7 +241,7 @@ def run_b200(args):
     u0_pinned[:] = u0_dev.to_host()
     u_out, r_out = ctx.pinned_empty(n), ctx.pinned_empty(n)
     prob = nls.NonlinearProblem(f, u0_dev, (3.4, 1.0, 10.0), ctx=ctx)
-    alg = nls.NewtonRaphson(linsolve=nls.KrylovJL_GMRES())
+    alg = nls.NewtonRaphson(linsolve=nls.KrylovJL_GMRES(orth=args.orth))
     cache = nls.init(prob, alg, abstol=1e-8, store_trace=True)
 
     def barrier():
@@ -300,7 +304,7 @@ def run_b200(args):
     ens = None
     if not args.no_ensemble:
         del cache  # release the Krylov basis before the ensemble workspaces are allocated
-        ens = run_ensemble(nls, torch, dist, ctx, rank, world)
+        ens = run_ensemble(nls, torch, dist, ctx, rank, world, orth=args.orth)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -308,10 +312,11 @@ def run_b200(args):
     peak, peak_src = peaks()
     # dominant kernel family = the Gram-Schmidt streaming pair (multi-dot + update), timed live with CUDA events
     if prof.get("resident", {}).get("ms", 0.0) > prof.get("multidot", {}).get("ms", 0.0):
-        dom, dom_name = ("resident",), ("resident_arnoldi_kernel (one cooperative kernel per Arnoldi step: JVP in registers + twice-applied MGS with the "
-                                        "basis TMA-streamed once per pass + norm + Givens); algorithmic bytes (2k+3)*Bv per step")
+        dom, dom_name = ("resident",), ("resident_arnoldi_kernel (one cooperative kernel per Arnoldi step: JVP in registers + modified Gram-Schmidt with "
+                                        "the basis TMA-streamed once per pass + norm + Givens); algorithmic bytes (passes*k+3)*Bv per step, passes = %d" % (
+                                            1 if args.orth == "mgs" else 2))
     else:
-        dom, dom_name = ("multidot", "update"), "gmres CGS2 orthogonalisation: multidot_kernel + update_kernel; algorithmic bytes (4k+6)*Bv per step"
+        dom, dom_name = ("multidot", "update"), "gmres orthogonalisation kernels of the multi-kernel engine (multidot_kernel + update_kernel)"
     dom_ms = sum(prof[k]["ms"] for k in dom if k in prof)
     dom_bytes = sum(prof[k]["bytes"] for k in dom if k in prof)
     dom_launches = sum(prof[k]["launches"] for k in dom if k in prof)
@@ -323,14 +328,14 @@ def run_b200(args):
                 "whole_step_gbs": bytes_moved / (ms * 1e-3) / 1e9,
                 "families": {k: {"gbs": round(v["gbs"], 1), "ms": round(v["ms"], 2), "launches": v["launches"]} for k, v in prof.items()}}
     count = 4
-    times, cores, sample, k0 = cpu_sample(N, 1, count)
+    times, cores, sample, k0 = cpu_sample(N, 1, count, args.orth)
     cpu_val = count / sum(times)
     value = njvp_all / (ms * 1e-3)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": workload_name(N), "unknowns": n, "cells": N ** 3, "step": "one full Newton solve (%d Newton iterations, %d Arnoldi iterations)" % (
-                nsteps // args.steps, njvp // args.steps), "orth": "cgs2 (reorthogonalised Gram-Schmidt)", "gmres_engine": "resident" if "resident" in dom else "multikernel", "parallelism": "replicas x%d (single system does not shard)" % world,
+                nsteps // args.steps, njvp // args.steps), "orth": args.orth + (" (Krylov.jl default: modified Gram-Schmidt, no reorthogonalisation)" if args.orth == "mgs" else " (reorthogonalised)"), "gmres_engine": "resident" if "resident" in dom else "multikernel", "parallelism": "replicas x%d (single system does not shard)" % world,
                 "l2": "inputs_exceed_l2 (Krylov basis %.1f GB per solve)" % (max(t_.lin_iters for t_ in sol.trace) * 8.0 * n / 1e9)},
             "newton_steps_per_s": nsteps_all / (ms * 1e-3),
             "e2e": {"value": njvp_e2e_all / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 16 * n,
@@ -353,6 +358,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--N", type=int, default=100)
+    ap.add_argument("--orth", default="mgs", choices=["mgs", "cgs2"], help="GMRES orthogonalisation: mgs = Krylov.jl default (reference), cgs2 = reorthogonalised")
     ap.add_argument("--no-ensemble", dest="no_ensemble", action="store_true", help="skip the config-5 ensemble leg")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -25,6 +25,13 @@ from ._abi import check, lib
 
 
 # ----------------------------------------------------------------------------- context / device memory
+def _destroy_context(handle, children):
+    for fin in reversed(children):
+        fin()  # idempotent: a finalizer that already ran is a no-op
+    children.clear()
+    lib().b200_ctx_destroy(handle)
+
+
 class Context:
     """One CUDA device + stream + library workspaces (b200_ctx).  Not thread-safe (one per host thread)."""
 
@@ -36,11 +43,21 @@ class Context:
         if st != abi.OK:
             raise abi.B200Error(st, "b200_ctx_create failed")
         self.device = device
-        self._fin = weakref.finalize(self, lib().b200_ctx_destroy, self._h)
+        self._children = []  # finalizers of every library object created on this context
+        self._fin = weakref.finalize(self, _destroy_context, self._h, self._children)
 
     @property
     def handle(self):
         return self._h
+
+    def _adopt(self, fin):
+        """Register a child object's finalizer: whatever the garbage collector's order, the context destroys every
+        object created on it (newest first) before it destroys itself, so no child ever runs against a dead context."""
+        ch = self._children
+        ch.append(fin)
+        if len(ch) > 4096:
+            ch[:] = [f for f in ch if f.alive]
+        return fin
 
     def sync(self):
         check(self._h, lib().b200_ctx_sync(self._h))
@@ -127,7 +144,7 @@ class DeviceVector:
             p = C.c_void_p()
             check(ctx.handle, lib().b200_malloc(ctx.handle, max(self.nbytes, 16), C.byref(p)))
             self.ptr = p
-            self._fin = weakref.finalize(self, lib().b200_free, ctx.handle, p)
+            self._fin = ctx._adopt(weakref.finalize(self, lib().b200_free, ctx.handle, p))
         else:
             self.ptr = C.c_void_p(ptr if isinstance(ptr, int) else ptr.value)
 
@@ -510,7 +527,7 @@ class _DeviceProblem:
             self._jvp_cb = abi.JVP_CB(jvp_cb) if f.jvp is not None else C.cast(None, abi.JVP_CB)
             self._vjp_cb = abi.JVP_CB(vjp_cb) if f.vjp is not None else C.cast(None, abi.JVP_CB)
             check(ctx.handle, L.b200_problem_create_callback(ctx.handle, n, self._f_cb, self._jvp_cb, self._vjp_cb, None, C.byref(self._h)))
-        self._fin = weakref.finalize(self, L.b200_problem_destroy, self._h)
+        self._fin = ctx._adopt(weakref.finalize(self, L.b200_problem_destroy, self._h))
 
     @property
     def handle(self):
@@ -589,7 +606,7 @@ class SparseJacobian:
         self._h = C.c_void_p()
         check(self.ctx.handle, lib().b200_sparse_jac_create(dprob.handle, colptr.ctypes.data_as(C.c_void_p), rowval.ctypes.data_as(C.c_void_p),
                                                             index_base, colors.ctypes.data_as(C.c_void_p), ncolors, C.byref(self._h)))
-        self._fin = weakref.finalize(self, lib().b200_sparse_jac_destroy, self._h)
+        self._fin = self.ctx._adopt(weakref.finalize(self, lib().b200_sparse_jac_destroy, self._h))
 
     def fill(self, u, nzval=None):
         nzval = nzval or self.ctx.empty(self.nnz)
@@ -631,7 +648,7 @@ class GmresSolver:
         g.atol, g.rtol = float(atol), float(rtol)
         self._h = C.c_void_p()
         check(ctx.handle, lib().b200_gmres_create(ctx.handle, n, C.byref(g), C.byref(self._h)))
-        self._fin = weakref.finalize(self, lib().b200_gmres_destroy, self._h)
+        self._fin = ctx._adopt(weakref.finalize(self, lib().b200_gmres_destroy, self._h))
         self.keep = keep_hessenberg
         if keep_hessenberg:
             check(ctx.handle, lib().b200_gmres_keep_hessenberg(self._h, keep_hessenberg))
@@ -697,7 +714,7 @@ class NonlinearSolveCache:
         self.opts = _build_opts(prob, alg, abstol, reltol, maxiters, termination_condition, store_trace)
         self._h = C.c_void_p()
         check(self.ctx.handle, lib().b200_newton_create(self.dprob.handle, C.byref(self.opts), C.byref(self._h)))
-        self._fin = weakref.finalize(self, lib().b200_newton_destroy, self._h)
+        self._fin = self.ctx._adopt(weakref.finalize(self, lib().b200_newton_destroy, self._h))
         self.n = self.dprob.n
         self._host_u0 = not isinstance(prob.u0, DeviceVector)
         self.reinit(prob.u0)
@@ -827,7 +844,7 @@ class EnsembleCache:
         self.opts = _build_opts(dummy, alg, abstol, reltol, maxiters, None, False)
         self._h = C.c_void_p()
         check(ctx.handle, lib().b200_ens_create(ctx.handle, N, nprob_local, float(alpha), C.byref(self.opts), C.byref(self._h)))
-        self._fin = weakref.finalize(self, lib().b200_ens_destroy, self._h)
+        self._fin = ctx._adopt(weakref.finalize(self, lib().b200_ens_destroy, self._h))
         self.u_out = ctx.empty(self.K * self.n)
         self.resid = ctx.empty(self.K)
         self.rc = ctx.empty(self.K, np.int32)
