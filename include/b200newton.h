@@ -82,7 +82,7 @@ enum { B200_ORTH_MGS = 0, B200_ORTH_CGS = 1, B200_ORTH_CGS2 = 2 };
 enum { B200_ENGINE_AUTO = 0, B200_ENGINE_MULTIKERNEL = 1, B200_ENGINE_RESIDENT = 2 };
 enum { B200_LINSOLVE_GMRES = 0, B200_LINSOLVE_DENSE_LU = 1, B200_LINSOLVE_SPARSE_GMRES = 2 };
 enum { B200_JVP_EXACT = 0, B200_JVP_FINITE_DIFF = 1 };
-enum { B200_GLOBALIZATION_NONE = 0, B200_GLOBALIZATION_TRUST_REGION = 1 };
+enum { B200_GLOBALIZATION_NONE = 0, B200_GLOBALIZATION_TRUST_REGION = 1, B200_GLOBALIZATION_LINESEARCH = 2 };
 enum { B200_FORCING_NONE = 0, B200_FORCING_EW2 = 1 };
 enum { B200_TERM_ABS_NORM_SAFE_BEST = 0, B200_TERM_ABS_NORM = 1, B200_TERM_ABS_NORM_SAFE = 2 };
 enum { B200_U0_REFERENCE = 0, B200_U0_PERTURBED_Z = 1 };
@@ -149,6 +149,11 @@ typedef struct b200_newton_opts {
   /* trust region, RadiusUpdateSchemes.Simple defaults (trust_region.jl:320-384) ; 0 => default */
   double tr_step_threshold, tr_shrink_threshold, tr_expand_threshold, tr_shrink_factor, tr_expand_factor;
   double tr_max_trust_radius, tr_initial_trust_radius;
+  /* BackTracking line search (globalization = LINESEARCH; solve.jl:249-273, 392-408; LineSearch.jl BackTracking, cubic
+     interpolation): sufficient-decrease constant, step contraction bounds, max backtracks.  0 => 1e-4, 0.5, 0.1, 1000 */
+  double ls_c1, ls_rho_hi, ls_rho_lo;
+  int32_t ls_maxiters;
+  int32_t ls_reserved;
 } b200_newton_opts;
 
 typedef struct b200_newton_result {

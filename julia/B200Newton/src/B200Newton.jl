@@ -175,6 +175,7 @@ struct NewtonOpts
     ew_safeguard::Int32; max_shrink_times::Int32
     tr_step_threshold::Float64; tr_shrink_threshold::Float64; tr_expand_threshold::Float64; tr_shrink_factor::Float64
     tr_expand_factor::Float64; tr_max_trust_radius::Float64; tr_initial_trust_radius::Float64
+    ls_c1::Float64; ls_rho_hi::Float64; ls_rho_lo::Float64; ls_maxiters::Int32; ls_reserved::Int32
 end
 struct NewtonResult
     retcode::Int32; nsteps::Int32; nf::Int32; njacs::Int32; nfactors::Int32; nsolve::Int32; njvp::Int32; ntrace::Int32
@@ -278,7 +279,7 @@ function SciMLBase.__solve(prob::SciMLBase.NonlinearProblem, alg::B200NewtonKryl
     o = NewtonOpts(something(abstol, 0.0), something(reltol, 0.0), maxiters,
         alg.linsolve === :gmres ? 0 : alg.linsolve === :dense_lu ? 1 : 2, 0, alg.globalization === :trust_region ? 1 : 0,
         alg.forcing ? 1 : 0, 0, 0, 1, g, o.ew_eta0, o.ew_eta_max, o.ew_gamma, o.ew_alpha, o.ew_safeguard_threshold, o.ew_safeguard,
-        o.max_shrink_times, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0)
+        o.max_shrink_times, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, Int32(0), Int32(0))
     nw = Ref{Ptr{Cvoid}}(C_NULL)
     check(ctx.handle, @ccall libb200.b200_newton_create(dp.handle::Ptr{Cvoid}, Ref(o)::Ref{NewtonOpts}, nw::Ref{Ptr{Cvoid}})::Int32)
     try
@@ -332,7 +333,7 @@ function SciMLBase.__solve(ens::SciMLBase.AbstractEnsembleProblem, alg::B200Newt
     N = round(Int, sqrt(length(first(probs).u0) ÷ 2)); n = 2N^2; K = length(idx)
     u0 = reduce(hcat, (vec(p.u0) for p in probs)); A = [p.p[1] for p in probs]; B = [p.p[2] for p in probs]
     d_u0, d_A, d_B, d_u = B200Vector(ctx, u0), B200Vector(ctx, A), B200Vector(ctx, B), B200Vector(ctx, n * K)
-    o = Ref(NewtonOpts(something(abstol, 0.0), 0.0, 1000, 0, 0, 0, 0, 0, 0, 1, default_newton_opts().gmres, 0.5, 0.9, 0.9, 2.0, 0.1, 1, 32, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0))
+    o = Ref(NewtonOpts(something(abstol, 0.0), 0.0, 1000, 0, 0, 0, 0, 0, 0, 1, default_newton_opts().gmres, 0.5, 0.9, 0.9, 2.0, 0.1, 1, 32, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, Int32(0), Int32(0)))
     h = Ref{Ptr{Cvoid}}(C_NULL)
     check(ctx.handle, @ccall libb200.b200_ens_create(ctx.handle::Ctx, N::Int32, K::Int32, Float64(first(probs).p[3])::Float64, o::Ref{NewtonOpts}, h::Ref{Ptr{Cvoid}})::Int32)
     d_res = B200Vector(ctx, K); rc = Vector{Int32}(undef, K)

@@ -23,7 +23,7 @@ ORTH_MGS, ORTH_CGS, ORTH_CGS2 = 0, 1, 2
 ENGINE_AUTO, ENGINE_MULTIKERNEL, ENGINE_RESIDENT = 0, 1, 2
 LINSOLVE_GMRES, LINSOLVE_DENSE_LU, LINSOLVE_SPARSE_GMRES = 0, 1, 2
 JVP_EXACT, JVP_FINITE_DIFF = 0, 1
-GLOB_NONE, GLOB_TRUST_REGION = 0, 1
+GLOB_NONE, GLOB_TRUST_REGION, GLOB_LINESEARCH = 0, 1, 2
 FORCING_NONE, FORCING_EW2 = 0, 1
 TERM_ABS_NORM_SAFE_BEST, TERM_ABS_NORM, TERM_ABS_NORM_SAFE = 0, 1, 2
 U0_REFERENCE, U0_PERTURBED_Z = 0, 1
@@ -50,7 +50,8 @@ class NewtonOpts(C.Structure):
                 ("ew_safeguard_threshold", C.c_double), ("ew_safeguard", C.c_int32), ("max_shrink_times", C.c_int32),
                 ("tr_step_threshold", C.c_double), ("tr_shrink_threshold", C.c_double), ("tr_expand_threshold", C.c_double),
                 ("tr_shrink_factor", C.c_double), ("tr_expand_factor", C.c_double), ("tr_max_trust_radius", C.c_double),
-                ("tr_initial_trust_radius", C.c_double)]
+                ("tr_initial_trust_radius", C.c_double), ("ls_c1", C.c_double), ("ls_rho_hi", C.c_double), ("ls_rho_lo", C.c_double),
+                ("ls_maxiters", C.c_int32), ("ls_reserved", C.c_int32)]
 
 
 class NewtonResult(C.Structure):

@@ -391,13 +391,21 @@ class AbsNormTerminationMode:
     code = abi.TERM_ABS_NORM
 
 
+class BackTracking:
+    """LineSearch.BackTracking(; c_1 = 1e-4, rho_hi = 0.5, rho_lo = 0.1, maxiters = 1000), cubic interpolation."""
+
+    def __init__(self, c_1=1e-4, rho_hi=0.5, rho_lo=0.1, maxiters=1000):
+        self.c_1, self.rho_hi, self.rho_lo, self.maxiters = c_1, rho_hi, rho_lo, maxiters
+
+
 class _FirstOrder:
     name = "GeneralizedFirstOrderAlgorithm"
     globalization = abi.GLOB_NONE
 
-    def __init__(self, concrete_jac=None, linsolve=None, autodiff=None, jvp_autodiff=None, vjp_autodiff=None, forcing=None):
+    def __init__(self, concrete_jac=None, linsolve=None, autodiff=None, jvp_autodiff=None, vjp_autodiff=None, forcing=None, linesearch=None):
         self.concrete_jac, self.linsolve, self.autodiff = concrete_jac, linsolve, autodiff
         self.jvp_autodiff, self.vjp_autodiff, self.forcing = jvp_autodiff, vjp_autodiff, forcing
+        self.linesearch = linesearch
 
 
 class NewtonRaphson(_FirstOrder):
@@ -455,6 +463,10 @@ def _build_opts(prob, alg, abstol, reltol, maxiters, termination_condition, stor
         o.forcing = abi.FORCING_EW2
         o.ew_eta0, o.ew_eta_max, o.ew_gamma, o.ew_alpha = f.eta0, f.eta_max, f.gamma, f.alpha
         o.ew_safeguard, o.ew_safeguard_threshold = (1 if f.safeguard else 0), f.safeguard_threshold
+    ls_ = getattr(alg, "linesearch", None)
+    if ls_ is not None:  # has_linesearch (solve.jl:249-273): globalization = Val(:LineSearch)
+        o.globalization = abi.GLOB_LINESEARCH
+        o.ls_c1, o.ls_rho_hi, o.ls_rho_lo, o.ls_maxiters = float(ls_.c_1), float(ls_.rho_hi), float(ls_.rho_lo), int(ls_.maxiters)
     if isinstance(alg, TrustRegion):
         for k, v in alg.tr.items():
             setattr(o, k, float(v))

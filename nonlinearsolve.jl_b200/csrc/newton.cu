@@ -148,6 +148,7 @@ int32_t b200_newton_create(b200_problem* prob, const b200_newton_opts* opts, b20
   if (opts->globalization == B200_GLOBALIZATION_TRUST_REGION) {
     A(&nw->u_trial); A(&nw->fu_trial); A(&nw->Jdu); A(&nw->JTfu); A(&nw->du_c); A(&nw->c1); A(&nw->c2);
   }
+  if (opts->globalization == B200_GLOBALIZATION_LINESEARCH) { A(&nw->u_trial); A(&nw->fu_trial); A(&nw->Jdu); }
   if (s != B200_OK) { b200_newton_destroy(nw); return s; }
   memset(&nw->op, 0, sizeof(nw->op));
   nw->op.ctx = ctx; nw->op.n = n;
@@ -340,7 +341,59 @@ static int32_t newton_step_inner(b200_newton* nw) {
     nw->make_new_jacobian = 1;
     int accepted = 1;
     double objective, du_norm;
-    if (!tr_on) {  // solve.jl:436-445 : u += du ; fu = f(u) ; with ||du||^2 and ||fu||_inf produced by the kernels' epilogues
+    double ls_alpha = 1.0;
+    if (o.globalization == B200_GLOBALIZATION_LINESEARCH) {
+      // solve.jl:392-408 with LineSearch.jl BackTracking (cubic interpolation; external package restated, see oracle.c):
+      // phi(a) = ||f(u + a du)||^2 / 2, phi'(0) = <fu, J du> by one JVP; every trial is one axpby + one residual + one norm.
+      const double c1 = o.ls_c1 > 0 ? o.ls_c1 : 1e-4, rho_hi = o.ls_rho_hi > 0 ? o.ls_rho_hi : 0.5, rho_lo = o.ls_rho_lo > 0 ? o.ls_rho_lo : 0.1;
+      const int ls_max = o.ls_maxiters > 0 ? o.ls_maxiters : 1000;
+      double nf0, dphi0;
+      B200_TRY(h_nrm2(nw, nw->fu, &nf0));
+      const double phi0 = 0.5 * nf0 * nf0;
+      B200_TRY(b200_jvp(nw->prob, nw->u, nw->du, nw->Jdu));
+      B200_TRY(h_dot(nw, nw->fu, nw->Jdu, &dphi0));
+      auto phi = [&](double alpha, double* out) -> int32_t {
+        B200_TRY(b200_copy(ctx, n, nw->u, nw->u_trial));
+        B200_TRY(b200_axpy(ctx, n, alpha, nw->du, nw->u_trial));
+        B200_TRY(b200_residual(nw->prob, nw->u_trial, nw->fu_trial));
+        nw->res.nf += 1;
+        double t;
+        B200_TRY(h_nrm2(nw, nw->fu_trial, &t));
+        *out = 0.5 * t * t;
+        return B200_OK;
+      };
+      double a1 = 1.0, a2 = 1.0, phx0 = phi0, phx1;
+      B200_TRY(phi(a1, &phx1));
+      int itf = 0;
+      while (!std::isfinite(phx1) && itf < 50) { ++itf; a1 = a2; a2 = a1 / 2.0; B200_TRY(phi(a2, &phx1)); }
+      int it = 0, ls_failed = 0;
+      while (phx1 > phi0 + c1 * a2 * dphi0) {
+        if (++it > ls_max) { ls_failed = 1; break; }
+        double at;
+        if (it == 1) at = -(dphi0 * a2 * a2) / (2.0 * (phx1 - phi0 - dphi0 * a2));
+        else {
+          const double div = 1.0 / (a1 * a1 * a2 * a2 * (a2 - a1));
+          const double ca = (a1 * a1 * (phx1 - phi0 - dphi0 * a2) - a2 * a2 * (phx0 - phi0 - dphi0 * a1)) * div;
+          const double cb = (-a1 * a1 * a1 * (phx1 - phi0 - dphi0 * a2) + a2 * a2 * a2 * (phx0 - phi0 - dphi0 * a1)) * div;
+          if (fabs(ca) <= 1e-14 * fabs(cb) || ca == 0.0) at = dphi0 / (2.0 * cb);
+          else { const double dd = std::max(cb * cb - 3.0 * ca * dphi0, 0.0); at = (-cb + sqrt(dd)) / (3.0 * ca); }
+        }
+        a1 = a2;
+        at = std::min(at, a2 * rho_hi);
+        a2 = std::max(at, a2 * rho_lo);
+        phx0 = phx1;
+        B200_TRY(phi(a2, &phx1));
+      }
+      if (ls_failed) { nw->retcode = B200_RC_INTERNAL_LINESEARCH_FAILED; nw->force_stop = 1; }
+      ls_alpha = a2;
+      CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_scalars, 0, sizeof(double) * 2, ctx->stream));
+      B200_TRY(b200i_axpy_norm(ctx, n, a2, nw->du, nw->u, ctx->d_scalars + 1));   // @bb axpy!(alpha, du, u)   solve.jl:403
+      B200_TRY(b200i_residual_norm(nw->prob, nw->u, nw->fu, ctx->d_scalars));     // evaluate_f!               solve.jl:407
+      nw->res.nf += 1;
+      B200_TRY(b200i_fetch_scalars(ctx, 2));
+      objective = ctx->h_scalars[0];
+      du_norm = sqrt(ctx->h_scalars[1]);
+    } else if (!tr_on) {  // solve.jl:436-445 : u += du ; fu = f(u) ; with ||du||^2 and ||fu||_inf produced by the kernels' epilogues
       CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_scalars, 0, sizeof(double) * 2, ctx->stream));
       B200_TRY(b200i_axpy_norm(ctx, n, 1.0, nw->du, nw->u, ctx->d_scalars + 1));
       B200_TRY(b200i_residual_norm(nw->prob, nw->u, nw->fu, ctx->d_scalars));
@@ -393,7 +446,7 @@ static int32_t newton_step_inner(b200_newton* nw) {
     if (o.store_trace) {
       b200_trace_rec t;
       t.iter = nw->nsteps + 1; t.lin_iters = gs.iters; t.lin_status = gs.status; t.accepted = accepted;
-      t.fnorm_inf = objective; t.step_norm2 = du_norm; t.lin_rnorm = gs.rnorm; t.trust_radius = nw->trust_region;
+      t.fnorm_inf = objective; t.step_norm2 = du_norm; t.lin_rnorm = gs.rnorm; t.trust_radius = (o.globalization == B200_GLOBALIZATION_LINESEARCH) ? ls_alpha : nw->trust_region;
       nw->trace.push_back(t);
     }
     // copyto!(u_cache, u) (solve.jl:460) is only ever read back as `uprev` for the stall norm, which the update kernel

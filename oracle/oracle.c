@@ -778,6 +778,8 @@ void orc_newton_solve(const orc_problem* p, const double* u0, const b200_newton_
   double* u_cache = (double*)malloc((size_t)n * 8); double* du = (double*)calloc((size_t)n, 8);
   double* xlin = (double*)calloc((size_t)n, 8);
   double *u_trial = NULL, *fu_trial = NULL, *Jdu = NULL, *JTfu = NULL, *du_c = NULL, *c1 = NULL, *c2 = NULL;
+  double *c1v = NULL, *c2v = NULL; /* line-search trial iterate / residual */
+  if (o->globalization == B200_GLOBALIZATION_LINESEARCH) { c1v = (double*)malloc((size_t)n * 8); c2v = (double*)malloc((size_t)n * 8); }
   if (tr_on) {
     u_trial = (double*)malloc((size_t)n * 8); fu_trial = (double*)malloc((size_t)n * 8); Jdu = (double*)malloc((size_t)n * 8);
     JTfu = (double*)malloc((size_t)n * 8); du_c = (double*)malloc((size_t)n * 8); c1 = (double*)malloc((size_t)n * 8); c2 = (double*)malloc((size_t)n * 8);
@@ -909,7 +911,48 @@ void orc_newton_solve(const orc_problem* p, const double* u0, const b200_newton_
     if (o->forcing == B200_FORCING_EW2 && o->linsolve != B200_LINSOLVE_DENSE_LU) { rnorm_prev = rnorm; rnorm = v_nrm2(n, fu); } /* post_step_forcing! :83-87 */
     make_new_jacobian = 1;
     int accepted = 1;
-    if (!tr_on) { /* solve.jl:436-445 */
+    double ls_alpha = 1.0;
+    if (o->globalization == B200_GLOBALIZATION_LINESEARCH) {
+      /* solve.jl:392-408 with LineSearch.jl BackTracking (external package, no version pinned: the LineSearches.jl
+       * BackTracking algorithm, cubic interpolation, restated; "parity unpinned"): phi(a) = ||f(u + a du)||^2 / 2,
+       * phi'(0) = <fu, J du> by one JVP; accept when phi(a) <= phi(0) + c1 a phi'(0). */
+      const double c1 = o->ls_c1 > 0 ? o->ls_c1 : 1e-4, rho_hi = o->ls_rho_hi > 0 ? o->ls_rho_hi : 0.5, rho_lo = o->ls_rho_lo > 0 ? o->ls_rho_lo : 0.1;
+      const int ls_max = o->ls_maxiters > 0 ? o->ls_maxiters : 1000;
+      double* ut = c1v; double* ft = c2v;
+      double nf0 = v_nrm2(n, fu);
+      const double phi0 = 0.5 * nf0 * nf0;
+      orc_jvp(p, u, du, ft);
+      const double dphi0 = v_dot(n, fu, ft);
+      double a1 = 1.0, a2 = 1.0, phx0 = phi0, phx1;
+#define ORC_PHI(alpha, out) do { for (int64_t i_ = 0; i_ < n; ++i_) ut[i_] = u[i_] + (alpha) * du[i_]; orc_residual(p, ut, ft); res->nf += 1; \
+                                 double t_ = v_nrm2(n, ft); (out) = 0.5 * t_ * t_; } while (0)
+      ORC_PHI(a1, phx1);
+      int itf = 0;
+      while (!isfinite(phx1) && itf < 50) { ++itf; a1 = a2; a2 = a1 / 2.0; ORC_PHI(a2, phx1); }
+      int it = 0, ls_failed = 0;
+      while (phx1 > phi0 + c1 * a2 * dphi0) {
+        if (++it > ls_max) { ls_failed = 1; break; }
+        double at;
+        if (it == 1) at = -(dphi0 * a2 * a2) / (2.0 * (phx1 - phi0 - dphi0 * a2));
+        else {
+          const double div = 1.0 / (a1 * a1 * a2 * a2 * (a2 - a1));
+          const double ca = (a1 * a1 * (phx1 - phi0 - dphi0 * a2) - a2 * a2 * (phx0 - phi0 - dphi0 * a1)) * div;
+          const double cb = (-a1 * a1 * a1 * (phx1 - phi0 - dphi0 * a2) + a2 * a2 * a2 * (phx0 - phi0 - dphi0 * a1)) * div;
+          if (fabs(ca) <= 1e-14 * fabs(cb) || ca == 0.0) at = dphi0 / (2.0 * cb);
+          else { const double dd = fmax(cb * cb - 3.0 * ca * dphi0, 0.0); at = (-cb + sqrt(dd)) / (3.0 * ca); }
+        }
+        a1 = a2;
+        at = fmin(at, a2 * rho_hi);
+        a2 = fmax(at, a2 * rho_lo);
+        phx0 = phx1;
+        ORC_PHI(a2, phx1);
+      }
+#undef ORC_PHI
+      if (ls_failed) { retcode = B200_RC_INTERNAL_LINESEARCH_FAILED; force_stop = 1; }
+      v_axpy(n, a2, du, u);                    /* @bb axpy!(alpha, du, u)   solve.jl:403 */
+      orc_residual(p, u, fu); res->nf += 1;  /* evaluate_f!               solve.jl:407 */
+      accepted = 1; ls_alpha = a2;
+    } else if (!tr_on) { /* solve.jl:436-445 */
       v_axpy(n, 1.0, du, u);
       orc_residual(p, u, fu); res->nf += 1;
     } else { /* GenericTrustRegionScheme solve!  trust_region.jl:396-430, 511-513 */
@@ -933,7 +976,7 @@ void orc_newton_solve(const orc_problem* p, const double* u0, const b200_newton_
     if (trace && ntrace < trace_cap) {
       b200_trace_rec* t = &trace[ntrace];
       t->iter = nsteps + 1; t->lin_iters = gs.iters; t->lin_status = gs.status; t->accepted = accepted;
-      t->fnorm_inf = v_norminf(n, fu); t->step_norm2 = v_diffnrm2(n, u, u_cache); t->lin_rnorm = gs.rnorm; t->trust_radius = trust_region;
+      t->fnorm_inf = v_norminf(n, fu); t->step_norm2 = v_diffnrm2(n, u, u_cache); t->lin_rnorm = gs.rnorm; t->trust_radius = (o->globalization == B200_GLOBALIZATION_LINESEARCH) ? ls_alpha : trust_region;
     }
     ++ntrace;
     v_copy(n, u, u_cache);
@@ -951,7 +994,7 @@ void orc_newton_solve(const orc_problem* p, const double* u0, const b200_newton_
   res->resid_inf = v_norminf(n, fu);
   if (u_out) v_copy(n, u, u_out);
   if (fu_out) v_copy(n, fu, fu_out);
-  free(u); free(fu); free(u_cache); free(du); free(xlin); free(u_trial); free(fu_trial); free(Jdu); free(JTfu); free(du_c); free(c1); free(c2);
+  free(u); free(fu); free(u_cache); free(du); free(xlin); free(u_trial); free(fu_trial); free(Jdu); free(JTfu); free(du_c); free(c1); free(c2); free(c1v); free(c2v);
   free(tc.best_u); free(Jdense); free(LU); free(ipiv); free(colptr); free(rowval); free(colors); free(nzval);
 }
 
