@@ -473,7 +473,10 @@ constexpr int RS_RR = 28;  // max rows per thread -> at most 28 * 512 = 14336 ro
 
 struct ResidentParams {
   int dim, N, k, passes, G, late_issue;
-  int64_t NC;       // cells
+  int opkind;       // 0: built-in Brusselator J(u) v, 1: assembled sparse matrix through its CSR view
+  const int64_t *rowptr, *csr_col, *csr_map;
+  const double* nzval;
+  int64_t NC;       // cells (opkind 1: half of the rows — the row set is split in two contiguous segments the same way)
   int cpc;          // cells per CTA (even)
   double a, A;
   const double* u;
@@ -613,7 +616,13 @@ __global__ void __launch_bounds__(RS_THREADS, 1) resident_arnoldi_kernel(Residen
   for (int q = 0; q < RS_RR; ++q) {
     const int lr = tid + RS_THREADS * q;
     w[q] = 0.0;
-    if (lr < nrow) {
+    if (lr < nrow && P.opkind == 1) {
+      const int s = lr >= ncell;
+      const int64_t r = (int64_t)s * NC + c0 + (lr - s * ncell);
+      double acc = 0.0;
+      for (int64_t e = P.rowptr[r], e1 = P.rowptr[r + 1]; e < e1; ++e) acc = fma(P.nzval[P.csr_map[e]], vk[P.csr_col[e]], acc);
+      w[q] = acc;
+    } else if (lr < nrow) {
       const int s = lr >= ncell;
       const int64_t c = c0 + (lr - s * ncell);
       int64_t cim, cip, cjm, cjp, ckm = 0, ckp = 0;
@@ -1039,8 +1048,9 @@ int32_t b200_gmres_solve(b200_gmres* gm, b200_linop* op, const double* b, double
   int rs_G = 0, rs_cpc = 0, rs_passes = (orth == B200_ORTH_CGS2) ? 2 : 1;
   int64_t rs_NC = 0;
   size_t rs_smem = 0;
-  if (o.engine != B200_ENGINE_MULTIKERNEL && op->kind == LINOP_PROBLEM && op->jvp_mode == B200_JVP_EXACT &&
-      (op->prob->kind == B200_PROB_BRUSS2D || op->prob->kind == B200_PROB_BRUSS3D)) {
+  const bool rs_builtin = op->kind == LINOP_PROBLEM && op->jvp_mode == B200_JVP_EXACT && (op->prob->kind == B200_PROB_BRUSS2D || op->prob->kind == B200_PROB_BRUSS3D);
+  const bool rs_csr = op->kind == LINOP_SPARSE_JAC && n % 2 == 0;
+  if (o.engine != B200_ENGINE_MULTIKERNEL && (rs_builtin || rs_csr)) {
     rs_NC = n / 2;
     rs_G = ctx->sm_count;
     int64_t cpc = (rs_NC + rs_G - 1) / rs_G;
@@ -1056,7 +1066,7 @@ int32_t b200_gmres_solve(b200_gmres* gm, b200_linop* op, const double* b, double
       return ctx->fail(B200_ERR_UNSUPPORTED, "resident GMRES engine: problem does not fit (needs an even cell count and <= 7168 cells per SM)", __FILE__, __LINE__);
     }
   } else if (o.engine == B200_ENGINE_RESIDENT) {
-    return ctx->fail(B200_ERR_UNSUPPORTED, "resident GMRES engine needs a built-in Brusselator operator with the exact JVP", __FILE__, __LINE__);
+    return ctx->fail(B200_ERR_UNSUPPORTED, "resident GMRES engine needs a built-in Brusselator operator with the exact JVP or an assembled sparse Jacobian", __FILE__, __LINE__);
   }
   const int64_t itmax = o.itmax > 0 ? o.itmax : n;
   const int restart_len = o.restart > 0 ? (int)std::min<int64_t>(o.restart, n) : 0;
@@ -1117,9 +1127,17 @@ int32_t b200_gmres_solve(b200_gmres* gm, b200_linop* op, const double* b, double
       if (resident) {
         // one cooperative kernel: JVP -> (iterated) MGS with TMA-staged basis -> norm -> Givens -> v_{k+1}
         ResidentParams RP;
-        RP.dim = op->prob->kind == B200_PROB_BRUSS2D ? 2 : 3;
-        RP.N = op->prob->N; RP.k = k; RP.passes = rs_passes; RP.G = rs_G; RP.NC = rs_NC; RP.cpc = rs_cpc;
-        RP.a = op->prob->a; RP.A = op->prob->A; RP.u = op->u; RP.V = (const double* const*)gm->d_Vptrs; RP.vnew = gm->V[k];
+        memset(&RP, 0, sizeof(RP));
+        if (rs_csr) {
+          RP.opkind = 1;
+          b200i_sparse_jac_csr(op->sj, &RP.rowptr, &RP.csr_col, &RP.csr_map);
+          RP.nzval = op->nzval;
+        } else {
+          RP.dim = op->prob->kind == B200_PROB_BRUSS2D ? 2 : 3;
+          RP.N = op->prob->N; RP.a = op->prob->a; RP.A = op->prob->A; RP.u = op->u;
+        }
+        RP.k = k; RP.passes = rs_passes; RP.G = rs_G; RP.NC = rs_NC; RP.cpc = rs_cpc;
+        RP.V = (const double* const*)gm->d_Vptrs; RP.vnew = gm->V[k];
         if (gm->ll_epoch > 0xfff00000u) {  // epoch space nearly exhausted: start over with clean slots
           CUDA_TRY(ctx, cudaMemsetAsync(gm->d_slots, 0, sizeof(unsigned long long) * 4 * LL_MAXG * LL_MAXG, ctx->stream));
           gm->ll_epoch = 0;

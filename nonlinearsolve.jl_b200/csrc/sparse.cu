@@ -92,6 +92,10 @@ struct b200_sparse_jac {
   double *seed, *comp;
 };
 
+void b200i_sparse_jac_csr(b200_sparse_jac* sj, const int64_t** rowptr, const int64_t** csr_col, const int64_t** csr_map) {
+  *rowptr = sj->d_rowptr; *csr_col = sj->d_csr_col; *csr_map = sj->d_csr_map;
+}
+
 extern "C" {
 int32_t b200_pattern_nnz(b200_problem* p, int64_t* nnz) {
   B200_REQUIRE(p->ctx, p->kind != B200_PROB_CALLBACK, "pattern: callback problems must bring their own jac_prototype");

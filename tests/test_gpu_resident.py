@@ -67,3 +67,26 @@ def test_resident_newton_vs_oracle(nls, ctx, po):
     assert np.abs(sol.u - uo).max() <= 1e-6 * np.abs(uo).max() and np.abs(sol.resid).max() < 1e-8
     for tg, t in zip(sol.trace, tro):
         assert abs(tg.lin_iters - t.lin_iters) <= 2
+
+
+@pytest.mark.parametrize("kind,N,orth", [("2d", 12, "mgs"), ("3d", 8, "cgs2"), ("2d", 40, "cgs2")])
+def test_resident_gmres_on_assembled_sparse_jacobian(nls, ctx, po, kind, N, orth):
+    """The resident engine with the matvec taken from the CSR view of the coloured sparse Jacobian (BASELINE config 4's
+    operator): same Krylov iteration as the matrix-free operator and as the multi-kernel engine on the same matrix."""
+    f, P, dp = _setup(nls, ctx, po, kind, N)
+    u = P.u0(1)
+    b = P.residual(u)
+    sj = nls.SparseJacobian(dp)
+    du = ctx.to_device(u)
+    nz = sj.fill(du)
+    ocode = po.ORTH_MGS if orth == "mgs" else po.ORTH_CGS2
+    xo, so = po.gmres(b, prob=P, u=u, opts=po.default_gmres_opts(atol=1e-10, rtol=1e-10, orth=ocode))
+    gm = nls.GmresSolver(ctx, P.n, nls.KrylovJL_GMRES(orth=orth, engine="resident"), atol=1e-10, rtol=1e-10)
+    x, st = gm.solve(("sparse_jac", sj, nz), ctx.to_device(b))
+    assert st.status == nls.abi.LS_SOLVED == so.status and abs(st.iters - so.iters) <= 1
+    assert np.abs(x.to_host() - xo).max() <= 1e-7 * np.abs(xo).max()
+    gm2 = nls.GmresSolver(ctx, P.n, nls.KrylovJL_GMRES(orth=orth, engine="multikernel"), atol=1e-10, rtol=1e-10)
+    x2, st2 = gm2.solve(("sparse_jac", sj, nz), ctx.to_device(b))
+    assert abs(st2.iters - st.iters) <= 1 and np.abs(x.to_host() - x2.to_host()).max() <= 1e-7 * np.abs(xo).max()
+    x3, st3 = gm.solve(("sparse_jac", sj, nz), ctx.to_device(b))
+    assert st3.iters == st.iters and np.array_equal(x3.to_host(), x.to_host())

@@ -15,7 +15,7 @@ if which == "dense":
     alg = nls.NewtonRaphson()
 else:
     f = nls.NonlinearFunction(nls.Brusselator3D(N), sparsity=nls.TracerSparsityDetector())
-    alg = nls.TrustRegion(linsolve=nls.KrylovJL_GMRES())
+    alg = nls.TrustRegion(linsolve=nls.KrylovJL_GMRES(orth=sys.argv[3] if len(sys.argv) > 3 else "cgs2", engine=sys.argv[4] if len(sys.argv) > 4 else "auto"))
 base = f.f if isinstance(f, nls.NonlinearFunction) else f
 dp = nls._DeviceProblem(ctx, nls.NonlinearProblem(base, None, (3.4, 1.0, 10.0), ctx=ctx))
 u0 = dp.u0(1)
