@@ -586,6 +586,41 @@ __device__ __forceinline__ void tma_bulk_load(void* smem_dst, const void* gsrc, 
                : "memory");
 }
 
+// CTA 0, one thread: Hessenberg column -> packed R with the stored Givens rotations, new rotation, residual norm, status
+// (same recurrence as givens_kernel)
+__device__ __forceinline__ void resident_givens_tail(const ResidentParams& P, double hbis, double inv) {
+  const int k = P.k;
+      GmresState* st = P.st;
+    double* Rk = P.R + (int64_t)(k - 1) * k / 2;
+    if (P.hraw) {
+      double* hr = P.hraw + (int64_t)(k - 1) * (k + 2) / 2;
+      for (int i = 0; i < k; ++i) hr[i] = P.h[i];
+      hr[k] = hbis;
+    }
+    for (int i = 0; i < k; ++i) Rk[i] = P.h[i];
+    for (int i = 0; i + 1 < k; ++i) {
+      const double rt = P.cs[i] * Rk[i] + P.sn[i] * Rk[i + 1];
+      Rk[i + 1] = P.sn[i] * Rk[i] - P.cs[i] * Rk[i + 1];
+      Rk[i] = rt;
+    }
+    double c, s_, rho;
+    sym_givens(Rk[k - 1], hbis, c, s_, rho);
+    P.cs[k - 1] = c; P.sn[k - 1] = s_; Rk[k - 1] = rho;
+    const double zeta = s_ * P.z[k - 1];
+    P.z[k - 1] = c * P.z[k - 1];
+    P.z[k] = zeta;
+    const double rnorm = fabs(zeta);
+    st->rnorm = rnorm; st->hbis = hbis; st->k = k; st->inv_h = inv;
+    int status = 0;
+    if (*P.err) status = B200_LS_NONFINITE;
+    else if (!(rnorm == rnorm) || isinf(rnorm) || !(hbis == hbis) || isinf(hbis)) status = B200_LS_NONFINITE;
+    else if (rnorm <= st->tol) status = B200_LS_SOLVED;
+    else if (st->iter_base + k >= st->itmax) status = B200_LS_MAXITERS;
+    else if (hbis <= 1.8189894035458565e-12) status = B200_LS_BREAKDOWN;
+    else if (k >= st->kmax_cycle) status = -1;
+    st->status = status;
+  }
+
 __global__ void __launch_bounds__(RS_THREADS, 1) resident_arnoldi_kernel(ResidentParams P) {
   if (P.st->status != 0) return;  // uniform across the grid: nobody reaches a barrier
   extern __shared__ __align__(16) double rsm[];
@@ -734,37 +769,302 @@ __global__ void __launch_bounds__(RS_THREADS, 1) resident_arnoldi_kernel(Residen
       P.vnew[(int64_t)s * NC + c0 + (lr - s * ncell)] = w[q] * inv;
     }
   }
-  if (b == 0 && tid == 0) {  // same recurrence as givens_kernel
-    GmresState* st = P.st;
-    double* Rk = P.R + (int64_t)(k - 1) * k / 2;
-    if (P.hraw) {
-      double* hr = P.hraw + (int64_t)(k - 1) * (k + 2) / 2;
-      for (int i = 0; i < k; ++i) hr[i] = P.h[i];
-      hr[k] = hbis;
-    }
-    for (int i = 0; i < k; ++i) Rk[i] = P.h[i];
-    for (int i = 0; i + 1 < k; ++i) {
-      const double rt = P.cs[i] * Rk[i] + P.sn[i] * Rk[i + 1];
-      Rk[i + 1] = P.sn[i] * Rk[i] - P.cs[i] * Rk[i + 1];
-      Rk[i] = rt;
-    }
-    double c, s_, rho;
-    sym_givens(Rk[k - 1], hbis, c, s_, rho);
-    P.cs[k - 1] = c; P.sn[k - 1] = s_; Rk[k - 1] = rho;
-    const double zeta = s_ * P.z[k - 1];
-    P.z[k - 1] = c * P.z[k - 1];
-    P.z[k] = zeta;
-    const double rnorm = fabs(zeta);
-    st->rnorm = rnorm; st->hbis = hbis; st->k = k; st->inv_h = inv;
-    int status = 0;
-    if (*P.err) status = B200_LS_NONFINITE;
-    else if (!(rnorm == rnorm) || isinf(rnorm) || !(hbis == hbis) || isinf(hbis)) status = B200_LS_NONFINITE;
-    else if (rnorm <= st->tol) status = B200_LS_SOLVED;
-    else if (st->iter_base + k >= st->itmax) status = B200_LS_MAXITERS;
-    else if (hbis <= 1.8189894035458565e-12) status = B200_LS_BREAKDOWN;
-    else if (k >= st->kmax_cycle) status = -1;
-    st->status = status;
+  if (b == 0 && tid == 0) resident_givens_tail(P, hbis, inv);
+}
+// =====================================================================================================================
+// Three-stage, lag-1 variant of the resident Arnoldi step (engine RESIDENT, chosen when the rows of one SM fit 54 per
+// thread at 256 threads): the two shared-memory stages are joined by a THIRD stage held in registers (54 more doubles per
+// thread, filled by 128-bit global loads that stay in flight for a whole step), so three basis vectors are on chip and the
+// exchange of vector t overlaps the dot products of vector t+1:
+//     h_{t+1} = <v_{t+1}, w_t> - h_t <v_{t+1}, v_t>          (w_t: w before the update with v_t)
+// which are the modified Gram-Schmidt coefficients exactly (the cross product restores the missing update); the pair
+// (<v_{t+1}, w_t>, <v_{t+1}, v_t>) is published before h_t is known.  Stage roles rotate with t mod 3 (0, 1: shared memory
+// via TMA bulk copies, 2: registers).  Exchange: replicated pull tables (16 replicas, 32-byte entries {a, c} with the epoch
+// in every 64-bit word), one entry per polling thread; four table buffers rotate.
+constexpr int R3_THREADS = 256;
+constexpr int R3_RP = 27;            // row pairs per thread
+constexpr int R3_ROWS = 2 * R3_RP;   // 54 rows per thread -> at most 13824 rows (6912 cells) per CTA
+constexpr int R3_RPR = 24;           // pairs of the third stage held in registers; the last R3_RP - R3_RPR pairs of each thread
+constexpr int R3_VR = 2 * R3_RPR;    //   sit in a small shared-memory annex filled by cp.async (register budget: 255)
+constexpr size_t R3_ANNEX_BYTES = (size_t)(R3_RP - R3_RPR) * R3_THREADS * 16;
+constexpr int R3_REPL = 16;
+constexpr size_t R3_BUF_WORDS = (size_t)R3_REPL * LL_MAXG * 4;
+
+__device__ __forceinline__ void r3_post(unsigned long long* buf, int b, double a, double c, unsigned epoch) {
+  const int lane = threadIdx.x;  // warp 0 only
+  if (lane < R3_REPL) {
+    const unsigned long long ba = (unsigned long long)__double_as_longlong(a), bc = (unsigned long long)__double_as_longlong(c);
+    const unsigned long long e = (unsigned long long)epoch << 32;
+    unsigned long long* dst = buf + ((size_t)lane * LL_MAXG + b) * 4;
+    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"((ba & 0xffffffffull) | e), "l"((ba >> 32) | e) : "memory");
+    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(dst + 2), "l"((bc & 0xffffffffull) | e), "l"((bc >> 32) | e) : "memory");
   }
+}
+// threads 0..159 poll one entry each; per-warp partial sums land in gA / gC (5 each); caller synchronises
+__device__ __forceinline__ void r3_poll(const unsigned long long* buf, int b, int G, unsigned epoch, int* err, double* gA, double* gC) {
+  const int tid = threadIdx.x;
+  if (tid < 160) {
+    double xa = 0.0, xc = 0.0;
+    if (tid < G) {
+      const unsigned long long* src = buf + ((size_t)(b & (R3_REPL - 1)) * LL_MAXG + tid) * 4;
+      unsigned long long a0, a1, c0, c1;
+      unsigned spins = 0;
+      bool ok;
+      do {
+        asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a0), "=l"(a1) : "l"(src) : "memory");
+        asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(c0), "=l"(c1) : "l"(src + 2) : "memory");
+        ok = ((unsigned)(a0 >> 32) == epoch) && ((unsigned)(a1 >> 32) == epoch) && ((unsigned)(c0 >> 32) == epoch) && ((unsigned)(c1 >> 32) == epoch);
+        if (++spins > (1u << 22)) { *err = 1; break; }
+      } while (!ok);
+      xa = __longlong_as_double((long long)((a0 & 0xffffffffull) | (a1 << 32)));
+      xc = __longlong_as_double((long long)((c0 & 0xffffffffull) | (c1 << 32)));
+    }
+    xa = warp_sum(xa);
+    xc = warp_sum(xc);
+    if ((tid & 31) == 0) { gA[tid >> 5] = xa; gC[tid >> 5] = xc; }
+  }
+}
+
+struct R3Shared {
+  uint64_t mbar[2];
+  double redA[8], redC[8], gA[8], gC[8];
+  long long acc[4], tl;  // debug phase timers (thread 0)
+};
+
+// block reduction of (da, dc) over 8 warps; result valid in every lane of warp 0.  One __syncthreads.
+__device__ __forceinline__ void r3_reduce2(double& da, double& dc, R3Shared& sh) {
+  const int tid = threadIdx.x;
+  da = warp_sum(da);
+  dc = warp_sum(dc);
+  if ((tid & 31) == 0) { sh.redA[tid >> 5] = da; sh.redC[tid >> 5] = dc; }
+  __syncthreads();
+  if (tid < 32) {
+    da = (tid < R3_THREADS / 32) ? sh.redA[tid] : 0.0;
+    dc = (tid < R3_THREADS / 32) ? sh.redC[tid] : 0.0;
+    da = warp_sum(da);
+    dc = warp_sum(dc);
+  }
+}
+
+#ifdef B200_R3_TIMERS
+#define R3_TICK(ph) do { if (P.dbg && threadIdx.x == 0) { const long long c_ = clock64(); sh.acc[ph] += c_ - sh.tl; sh.tl = c_; } } while (0)
+#else
+#define R3_TICK(ph) do { } while (0)
+#endif
+struct R3Ctx {
+  double *stage0, *stage1;
+  double2* annex;
+  int nrow, ncell, total, k, b, G;
+};
+
+__device__ __forceinline__ void r3_issue_smem(const ResidentParams& P, const R3Ctx& cx, R3Shared& sh, int t, int stage) {
+  if (threadIdx.x == 0 && cx.nrow > 0) {
+    const double* src = P.V[t % cx.k];
+    double* dst = stage ? cx.stage1 : cx.stage0;
+    const unsigned seg_bytes = (unsigned)cx.ncell * 8u;
+    const int64_t c0 = (int64_t)cx.b * P.cpc;
+    mbar_expect_tx(&sh.mbar[stage], 2u * seg_bytes);
+    tma_bulk_load(dst, src + c0, seg_bytes, &sh.mbar[stage]);
+    tma_bulk_load(dst + cx.ncell, src + P.NC + c0, seg_bytes, &sh.mbar[stage]);
+  }
+}
+__device__ __forceinline__ void r3_issue_regs(const ResidentParams& P, const R3Ctx& cx, int t, double (&vr)[R3_VR]) {
+  const double* src = P.V[t % cx.k] + (int64_t)cx.b * P.cpc;
+#pragma unroll
+  for (int q = 0; q < R3_RP; ++q) {
+    const int lr = 2 * ((int)threadIdx.x + R3_THREADS * q);
+    const double* p = src + ((lr >= cx.ncell) ? (P.NC - cx.ncell) : (int64_t)0) + lr;
+    if (q < R3_RPR) {
+      if (lr < cx.nrow) asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(vr[2 * (q < R3_RPR ? q : 0)]), "=d"(vr[2 * (q < R3_RPR ? q : 0) + 1]) : "l"(p));
+    } else if (lr < cx.nrow) {
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(cx.annex + (q - R3_RPR) * R3_THREADS + threadIdx.x)), "l"(p) : "memory");
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+// element pair q of the third stage (compile-time q after unrolling)
+#define R3_VRGET(q, o0, o1)                                                                            \
+  do {                                                                                                 \
+    if ((q) < R3_RPR) { o0 = vr[2 * ((q) < R3_RPR ? (q) : 0)]; o1 = vr[2 * ((q) < R3_RPR ? (q) : 0) + 1]; } \
+    else { const double2 z_ = cx.annex[((q) - R3_RPR) * R3_THREADS + threadIdx.x]; o0 = z_.x; o1 = z_.y; }     \
+  } while (0)
+
+// One Gram-Schmidt step for the vector of step t whose stage role is ROLE = t % 3.
+template <int ROLE>
+__device__ __forceinline__ void r3_step(const ResidentParams& P, R3Ctx& cx, R3Shared& sh, int t, double (&w)[R3_ROWS], double (&vr)[R3_VR], double& hprev) {
+  constexpr int NEXT = (ROLE + 1) % 3;
+  const int tid = threadIdx.x;
+  const double* sc = ROLE == 0 ? cx.stage0 : cx.stage1;   // current vector if it lives in shared memory
+  const double* sn = NEXT == 0 ? cx.stage0 : cx.stage1;   // next vector if it lives in shared memory
+  if (t + 1 < cx.total) {
+    if (NEXT != 2 && cx.nrow > 0 && (P.late_issue != 7 || t < 2)) mbar_wait(&sh.mbar[NEXT], (unsigned)(((t + 1) / 3) & 1));
+    if (NEXT == 2) asm volatile("cp.async.wait_group 0;" ::: "memory");
+    R3_TICK(0);
+    double da = 0.0, dc = 0.0;
+#pragma unroll
+    for (int q = 0; q < R3_RP; ++q) {
+      const int lr = 2 * (tid + R3_THREADS * q);
+      if (lr < cx.nrow) {
+        double x0, x1, y0, y1;
+        if (NEXT == 2) { R3_VRGET(q, x0, x1); }
+        else { const double2 x = *reinterpret_cast<const double2*>(sn + lr); x0 = x.x; x1 = x.y; }
+        if (ROLE == 2) { R3_VRGET(q, y0, y1); }
+        else { const double2 y = *reinterpret_cast<const double2*>(sc + lr); y0 = y.x; y1 = y.y; }
+        da = fma(x0, w[2 * q], da); da = fma(x1, w[2 * q + 1], da);
+        dc = fma(x0, y0, dc); dc = fma(x1, y1, dc);
+      }
+    }
+    r3_reduce2(da, dc, sh);
+    if (tid < 32) r3_post(P.slots + (size_t)((t + 1) & 3) * R3_BUF_WORDS, cx.b, da, dc, P.epoch_base + (unsigned)(t + 1) + 1u);
+    R3_TICK(1);
+  }
+  r3_poll(P.slots + (size_t)(t & 3) * R3_BUF_WORDS, cx.b, cx.G, P.epoch_base + (unsigned)t + 1u, P.err, sh.gA, sh.gC);
+  __syncthreads();
+  R3_TICK(2);
+  const double sa = ((sh.gA[0] + sh.gA[1]) + (sh.gA[2] + sh.gA[3])) + sh.gA[4];
+  const double scs = ((sh.gC[0] + sh.gC[1]) + (sh.gC[2] + sh.gC[3])) + sh.gC[4];
+  const double h = sa - hprev * scs;
+  hprev = h;
+#pragma unroll
+  for (int q = 0; q < R3_RP; ++q) {
+    const int lr = 2 * (tid + R3_THREADS * q);
+    if (lr < cx.nrow) {
+      double y0, y1;
+      if (ROLE == 2) { R3_VRGET(q, y0, y1); }
+      else { const double2 y = *reinterpret_cast<const double2*>(sc + lr); y0 = y.x; y1 = y.y; }
+      w[2 * q] = fma(-h, y0, w[2 * q]);
+      w[2 * q + 1] = fma(-h, y1, w[2 * q + 1]);
+    }
+  }
+  if (cx.b == 0 && tid == 0) { const int i = t % cx.k; P.h[i] = (t < cx.k) ? h : P.h[i] + h; }
+  if (ROLE != 2) {
+    __syncthreads();  // every thread is done with this shared-memory stage
+    if (t + 3 < cx.total && P.late_issue != 7) r3_issue_smem(P, cx, sh, t + 3, ROLE);
+  } else {
+    if (t + 3 < cx.total && P.late_issue != 7) r3_issue_regs(P, cx, t + 3, vr);
+  }
+  R3_TICK(3);
+}
+
+__global__ void __launch_bounds__(R3_THREADS, 1) resident3_arnoldi_kernel(ResidentParams P) {
+  if (P.st->status != 0) return;
+  extern __shared__ __align__(16) double rsm[];
+  __shared__ R3Shared sh;
+  R3Ctx cx;
+  const int cpc = P.cpc;
+  cx.stage0 = rsm;
+  cx.stage1 = rsm + 2 * cpc;
+  cx.annex = reinterpret_cast<double2*>(rsm + 4 * cpc);
+  const int tid = threadIdx.x, b = blockIdx.x, G = P.G;
+  cx.b = b; cx.G = G; cx.k = P.k; cx.total = P.passes * P.k;
+  cx.ncell = (int)max((int64_t)0, min((int64_t)cpc, P.NC - (int64_t)b * cpc));
+  cx.nrow = 2 * cx.ncell;
+  if (tid == 0) {
+    mbar_init(&sh.mbar[0], 1);
+    mbar_init(&sh.mbar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  // the first two basis vectors start travelling while the operator is applied
+  r3_issue_smem(P, cx, sh, 0, 0);
+  if (cx.total > 1) r3_issue_smem(P, cx, sh, 1, 1);
+  // ---- 1. w = J(u) v_k (or the assembled sparse matrix times v_k) for this CTA's rows, into registers
+  const double* vk = P.V[P.k - 1];
+  double w[R3_ROWS];
+  double vr[R3_VR];
+  const int N = P.N;
+  const int64_t N2 = (int64_t)N * N, NC = P.NC;
+  const int ncell = cx.ncell, nrow = cx.nrow;
+  const int64_t c0 = (int64_t)b * cpc;
+#pragma unroll
+  for (int qq = 0; qq < R3_ROWS; ++qq) {
+    const int lr = 2 * (tid + R3_THREADS * (qq >> 1)) + (qq & 1);
+    w[qq] = 0.0;
+    if (lr < nrow && P.opkind == 1) {
+      const int s = lr >= ncell;
+      const int64_t r = (int64_t)s * NC + c0 + (lr - s * ncell);
+      double acc = 0.0;
+      for (int64_t e = P.rowptr[r], e1 = P.rowptr[r + 1]; e < e1; ++e) acc = fma(P.nzval[P.csr_map[e]], vk[P.csr_col[e]], acc);
+      w[qq] = acc;
+    } else if (lr < nrow) {
+      const int s = lr >= ncell;
+      const int64_t c = c0 + (lr - s * ncell);
+      int64_t cim, cip, cjm, cjp, ckm = 0, ckp = 0;
+      if (P.dim == 3) {
+        const int kk = (int)(c / N2);
+        const int r = (int)(c - (int64_t)kk * N2);
+        const int j = r / N, i = r - j * N;
+        cim = c + ((i == 0) ? (N - 1) : -1); cip = c + ((i + 1 == N) ? -(N - 1) : 1);
+        cjm = c + ((j == 0) ? (int64_t)(N - 1) * N : -N); cjp = c + ((j + 1 == N) ? -(int64_t)(N - 1) * N : N);
+        ckm = c + ((kk == 0) ? (int64_t)(N - 1) * N2 : -N2); ckp = c + ((kk + 1 == N) ? -(int64_t)(N - 1) * N2 : N2);
+      } else {
+        const int j = (int)(c / N), i = (int)(c - (int64_t)j * N);
+        cim = c + ((i == 0) ? (N - 1) : -1); cip = c + ((i + 1 == N) ? -(N - 1) : 1);
+        cjm = c + ((j == 0) ? (int64_t)(N - 1) * N : -N); cjp = c + ((j + 1 == N) ? -(int64_t)(N - 1) * N : N);
+      }
+      const double* x = vk + (int64_t)s * NC;
+      const double xc = x[c];
+      double lap = x[cim] + x[cip] + x[cjp] + x[cjm] - 4.0 * xc;
+      if (P.dim == 3) lap = lap + (x[ckp] + x[ckm] - 2.0 * xc);
+      const double uc = P.u[c], vc = P.u[c + NC], dc = vk[c], ec = vk[c + NC];
+      const double uv2 = 2.0 * uc * vc, uu = uc * uc;
+      w[qq] = s ? (P.a * lap + (P.A - uv2) * dc - uu * ec) : (P.a * lap + (uv2 - (P.A + 1.0)) * dc + uu * ec);
+    }
+  }
+  // ---- 2. lag-1 modified Gram-Schmidt over three rotating stages
+  const int total = cx.total;
+  if (total > 2) r3_issue_regs(P, cx, 2, vr);
+  {
+    if (nrow > 0) mbar_wait(&sh.mbar[0], 0u);
+    double da = 0.0, dc = 0.0;
+#pragma unroll
+    for (int q = 0; q < R3_RP; ++q) {
+      const int lr = 2 * (tid + R3_THREADS * q);
+      if (lr < nrow) {
+        const double2 x = *reinterpret_cast<const double2*>(cx.stage0 + lr);
+        da = fma(x.x, w[2 * q], da); da = fma(x.y, w[2 * q + 1], da);
+      }
+    }
+    r3_reduce2(da, dc, sh);
+    if (tid < 32) r3_post(P.slots, b, da, 0.0, P.epoch_base + 1u);
+  }
+  double hprev = 0.0;
+#ifdef B200_R3_TIMERS
+  if (P.dbg && tid == 0) { sh.acc[0] = sh.acc[1] = sh.acc[2] = sh.acc[3] = 0; sh.tl = clock64(); }
+#endif
+  for (int t = 0; t < total; t += 3) {
+    r3_step<0>(P, cx, sh, t, w, vr, hprev);
+    if (t + 1 < total) r3_step<1>(P, cx, sh, t + 1, w, vr, hprev);
+    if (t + 2 < total) r3_step<2>(P, cx, sh, t + 2, w, vr, hprev);
+  }
+#ifdef B200_R3_TIMERS
+  if (P.dbg && tid == 0) {
+    for (int i = 0; i < 4; ++i) P.dbg[4 * b + i] += (double)sh.acc[i];
+    if (b == 0) P.dbg[4 * G] += (double)total;
+  }
+#endif
+  // ---- 3. ||w||, Givens (CTA 0), normalise, store v_{k+1}
+  double nacc = 0.0, zero = 0.0;
+#pragma unroll
+  for (int qq = 0; qq < R3_ROWS; ++qq) nacc = fma(w[qq], w[qq], nacc);
+  __syncthreads();
+  r3_reduce2(nacc, zero, sh);
+  if (tid < 32) r3_post(P.slots + (size_t)(total & 3) * R3_BUF_WORDS, b, nacc, 0.0, P.epoch_base + (unsigned)total + 1u);
+  r3_poll(P.slots + (size_t)(total & 3) * R3_BUF_WORDS, b, G, P.epoch_base + (unsigned)total + 1u, P.err, sh.gA, sh.gC);
+  __syncthreads();
+  const double hbis = sqrt(((sh.gA[0] + sh.gA[1]) + (sh.gA[2] + sh.gA[3])) + sh.gA[4]);
+  const double inv = hbis > 0.0 ? 1.0 / hbis : 0.0;
+#pragma unroll
+  for (int q = 0; q < R3_RP; ++q) {
+    const int lr = 2 * (tid + R3_THREADS * q);
+    if (lr < nrow) {
+      const int s = lr >= ncell;
+      double2 o;
+      o.x = w[2 * q] * inv; o.y = w[2 * q + 1] * inv;
+      *reinterpret_cast<double2*>(P.vnew + (int64_t)s * NC + c0 + (lr - s * ncell)) = o;
+    }
+  }
+  if (b == 0 && tid == 0) resident_givens_tail(P, hbis, inv);
 }
 }  // namespace
 
@@ -1044,7 +1344,7 @@ int32_t b200_gmres_solve(b200_gmres* gm, b200_linop* op, const double* b, double
   if (blk > JT) blk = JT;
   if (orth == B200_ORTH_MGS) blk = 0;
   // resident engine: built-in Brusselator operator with the exact JVP, even cell count, one CTA per SM holds its rows
-  bool resident = false;
+  bool resident = false, resident3 = false;
   int rs_G = 0, rs_cpc = 0, rs_passes = (orth == B200_ORTH_CGS2) ? 2 : 1;
   int64_t rs_NC = 0;
   size_t rs_smem = 0;
@@ -1061,7 +1361,11 @@ int32_t b200_gmres_solve(b200_gmres* gm, b200_linop* op, const double* b, double
     const bool wanted = (o.engine == B200_ENGINE_RESIDENT) || (o.engine == B200_ENGINE_AUTO && n >= 200000);
     if (fits && wanted) {
       resident = true;
+      static const int r3env = getenv("B200_RS3") ? atoi(getenv("B200_RS3")) : 1;  // B200_RS3=0: two-stage kernel (A/B runs)
+      resident3 = r3env != 0 && (2 * cpc <= (int64_t)R3_ROWS * R3_THREADS) && (rs_smem + R3_ANNEX_BYTES + 2048 <= ctx->smem_optin);
+      if (resident3) rs_smem += R3_ANNEX_BYTES;
       CUDA_TRY(ctx, cudaFuncSetAttribute(resident_arnoldi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem));
+      CUDA_TRY(ctx, cudaFuncSetAttribute(resident3_arnoldi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem));
     } else if (o.engine == B200_ENGINE_RESIDENT) {
       return ctx->fail(B200_ERR_UNSUPPORTED, "resident GMRES engine: problem does not fit (needs an even cell count and <= 7168 cells per SM)", __FILE__, __LINE__);
     }
@@ -1151,7 +1455,10 @@ int32_t b200_gmres_solve(b200_gmres* gm, b200_linop* op, const double* b, double
         RP.st = gm->d_state;
         void* args[] = {&RP};
         if (ctx->prof_on) ctx->prof_begin(B200_KID_RESIDENT, (rs_passes * (double)k + 3.0) * Bv);
-        CUDA_TRY(ctx, cudaLaunchCooperativeKernel((const void*)resident_arnoldi_kernel, dim3(rs_G), dim3(RS_THREADS), args, rs_smem, ctx->stream));
+        if (resident3)
+          CUDA_TRY(ctx, cudaLaunchCooperativeKernel((const void*)resident3_arnoldi_kernel, dim3(rs_G), dim3(R3_THREADS), args, rs_smem, ctx->stream));
+        else
+          CUDA_TRY(ctx, cudaLaunchCooperativeKernel((const void*)resident_arnoldi_kernel, dim3(rs_G), dim3(RS_THREADS), args, rs_smem, ctx->stream));
         ctx->launches++;
         if (ctx->prof_on) ctx->prof_end();
       } else {
