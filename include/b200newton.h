@@ -83,6 +83,7 @@ enum { B200_ENGINE_AUTO = 0, B200_ENGINE_MULTIKERNEL = 1, B200_ENGINE_RESIDENT =
 enum { B200_LINSOLVE_GMRES = 0, B200_LINSOLVE_DENSE_LU = 1, B200_LINSOLVE_SPARSE_GMRES = 2 };
 enum { B200_JVP_EXACT = 0, B200_JVP_FINITE_DIFF = 1 };
 enum { B200_GLOBALIZATION_NONE = 0, B200_GLOBALIZATION_TRUST_REGION = 1, B200_GLOBALIZATION_LINESEARCH = 2 };
+enum { B200_PRECOND_NONE = 0, B200_PRECOND_BLOCK_JACOBI_LEFT = 1, B200_PRECOND_BLOCK_JACOBI_RIGHT = 2 };
 enum { B200_FORCING_NONE = 0, B200_FORCING_EW2 = 1 };
 enum { B200_TERM_ABS_NORM_SAFE_BEST = 0, B200_TERM_ABS_NORM = 1, B200_TERM_ABS_NORM_SAFE = 2 };
 enum { B200_U0_REFERENCE = 0, B200_U0_PERTURBED_Z = 1 };
@@ -153,7 +154,7 @@ typedef struct b200_newton_opts {
      interpolation): sufficient-decrease constant, step contraction bounds, max backtracks.  0 => 1e-4, 0.5, 0.1, 1000 */
   double ls_c1, ls_rho_hi, ls_rho_lo;
   int32_t ls_maxiters;
-  int32_t ls_reserved;
+  int32_t precond; /* B200_PRECOND_*: built-in preconditioner handed to GMRES each step (LinearSolve `precs(A, p)`) */
 } b200_newton_opts;
 
 typedef struct b200_newton_result {
@@ -255,6 +256,14 @@ void b200_gmres_opts_default(b200_gmres_opts* opts);
 int32_t b200_gmres_create(b200_ctx* ctx, int64_t n, const b200_gmres_opts* opts, b200_gmres** gm);
 int32_t b200_gmres_destroy(b200_gmres* gm);
 int32_t b200_gmres_set_tolerances(b200_gmres* gm, double atol, double rtol); /* LinearSolve.update_tolerances! */
+/* Preconditioning (`KrylovJL_GMRES(precs = (A, p) -> (Pl, Pr))`, test/Core/core_tests__item21.jl;
+ * Krylov.jl gmres!(…; M = Pl, N = Pr, ldiv = false)): each operator APPLIES the inverse, y = M^-1 x.  Left: the Krylov
+ * method runs on M^-1 A x = M^-1 b and its stopping test sees the preconditioned residual; right: A N^-1 y = b, x = N^-1 y.
+ * NULL clears a side.  The operators are borrowed (caller keeps them alive until the solve returns). */
+int32_t b200_gmres_set_precond(b200_gmres* gm, b200_linop* left_inv, b200_linop* right_inv);
+/* Built-in block-Jacobi preconditioner of the Brusselator Jacobian at u: inverse of the 2x2 species blocks on the diagonal
+ * (large_systems.md:244-316 uses an incomplete LU / multigrid of the same matrix through `precs`). */
+int32_t b200_linop_block_jacobi(b200_problem* prob, const double* u, b200_linop** out);
 int32_t b200_gmres_solve(b200_gmres* gm, b200_linop* op, const double* b, double* x_inout, b200_gmres_stats* stats_host);
 
 /* ---------------------------------------------------------------- dense fallback (a5) */

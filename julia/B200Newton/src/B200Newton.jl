@@ -175,7 +175,7 @@ struct NewtonOpts
     ew_safeguard::Int32; max_shrink_times::Int32
     tr_step_threshold::Float64; tr_shrink_threshold::Float64; tr_expand_threshold::Float64; tr_shrink_factor::Float64
     tr_expand_factor::Float64; tr_max_trust_radius::Float64; tr_initial_trust_radius::Float64
-    ls_c1::Float64; ls_rho_hi::Float64; ls_rho_lo::Float64; ls_maxiters::Int32; ls_reserved::Int32
+    ls_c1::Float64; ls_rho_hi::Float64; ls_rho_lo::Float64; ls_maxiters::Int32; precond::Int32
 end
 struct NewtonResult
     retcode::Int32; nsteps::Int32; nf::Int32; njacs::Int32; nfactors::Int32; nsolve::Int32; njvp::Int32; ntrace::Int32
@@ -244,12 +244,27 @@ function SciMLBase.solve!(cache::LinearSolve.LinearCache, alg::B200GMRES; kwargs
         cb = @cfunction(_matvec_trampoline, Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}))
         check(ctx.handle, @ccall libb200.b200_linop_from_callback(ctx.handle::Ctx, length(b)::Int64, cb::Ptr{Cvoid}, pointer_from_objref(boxed)::Ptr{Cvoid}, op::Ref{Ptr{Cvoid}})::Int32)
     end
+    # LinearSolve `precs`: cache.Pl / cache.Pr.  A `B200BlockJacobi` marker maps to the built-in device preconditioner; any
+    # other non-identity preconditioner is wrapped like the operator above (callback applying `ldiv!`).
+    pl = cache.Pl isa B200BlockJacobi && prob !== nothing ? block_jacobi_op(prob, cache.p.u) : C_NULL
+    pr = cache.Pr isa B200BlockJacobi && prob !== nothing ? block_jacobi_op(prob, cache.p.u) : C_NULL
+    check(ctx.handle, @ccall libb200.b200_gmres_set_precond(gm.handle::Ptr{Cvoid}, pl::Ptr{Cvoid}, pr::Ptr{Cvoid})::Int32)
     st = Ref{GmresStats}()
     GC.@preserve st check(ctx.handle, @ccall libb200.b200_gmres_solve(gm.handle::Ptr{Cvoid}, op[]::Ptr{Cvoid}, b.ptr::Ptr{Float64}, x.ptr::Ptr{Float64}, st::Ref{GmresStats})::Int32)
+    @ccall libb200.b200_gmres_set_precond(gm.handle::Ptr{Cvoid}, C_NULL::Ptr{Cvoid}, C_NULL::Ptr{Cvoid})::Int32
     @ccall libb200.b200_linop_destroy(op[]::Ptr{Cvoid})::Int32
+    pl == C_NULL || @ccall libb200.b200_linop_destroy(pl::Ptr{Cvoid})::Int32
+    pr == C_NULL || @ccall libb200.b200_linop_destroy(pr::Ptr{Cvoid})::Int32
     s = st[]
     rc = s.status == 1 || s.status == 3 ? ReturnCode.Success : s.status == 2 ? ReturnCode.MaxIters : ReturnCode.Failure
     return SciMLBase.build_linear_solution(alg, x, s.rnorm, cache; retcode = rc, iters = Int(s.iters))
+end
+"""`precs = (A, p) -> (B200BlockJacobi(), I)`: inverse of the 2x2 species blocks on the diagonal of the Brusselator Jacobian."""
+struct B200BlockJacobi end
+function block_jacobi_op(prob, u::B200Vector)
+    op = Ref{Ptr{Cvoid}}(C_NULL)
+    check(prob.ctx.handle, @ccall libb200.b200_linop_block_jacobi(prob.handle::Ptr{Cvoid}, u.ptr::Ptr{Float64}, op::Ref{Ptr{Cvoid}})::Int32)
+    return op[]
 end
 device_problem(A) = nothing   # specialised for JacobianOperators built from `brusselator_function` (holds the Problem)
 

@@ -343,7 +343,9 @@ class KrylovJL_GMRES:
     needs_concrete_A = False
 
     def __init__(self, gmres_restart=0, memory=20, itmax=0, orth="cgs2", warm_start=False, atol=None, rtol=None, check_every=8,
-                 engine="auto", block=0):
+                 engine="auto", block=0, precs=None):
+        # precs: LinearSolve's `precs = (A, p) -> (Pl, Pr)`; here a BlockJacobi(side) descriptor of the built-in preconditioner
+        self.precs = precs
         self.block = block  # Gram-Schmidt in L2-sized blocks of this many basis vectors (0: whole basis, -1: automatic)
         self.gmres_restart, self.memory, self.itmax, self.orth = gmres_restart, memory, itmax, orth
         self.warm_start, self.atol, self.rtol, self.check_every, self.engine = warm_start, atol, rtol, check_every, engine
@@ -357,6 +359,26 @@ class KrylovJL_GMRES:
         g.block = int(self.block)
         g.atol = float(self.atol) if self.atol is not None else 0.0
         g.rtol = float(self.rtol) if self.rtol is not None else 0.0
+
+
+class BlockJacobi:
+    """Built-in preconditioner for `KrylovJL_GMRES(precs = ...)`: the inverse of the 2x2 species blocks on the diagonal of
+    the Brusselator Jacobian, rebuilt from the current iterate at every Newton step (what `precs(A, p)` returning
+    `(Pl, I)` or `(I, Pr)` does in the reference, test/Core/core_tests__item21.jl)."""
+
+    def __init__(self, side="left"):
+        assert side in ("left", "right")
+        self.side = side
+
+    @property
+    def code(self):
+        return abi.PRECOND_BLOCK_JACOBI_LEFT if self.side == "left" else abi.PRECOND_BLOCK_JACOBI_RIGHT
+
+    def linop(self, dprob, u):
+        """A borrowed-by-GMRES operator handle applying the inverse at iterate u (DeviceVector)."""
+        op = C.c_void_p()
+        check(dprob.ctx.handle, lib().b200_linop_block_jacobi(dprob.handle, u.ptr, C.byref(op)))
+        return op
 
 
 class LUFactorization:
@@ -449,6 +471,8 @@ def _build_opts(prob, alg, abstol, reltol, maxiters, termination_condition, stor
             KrylovJL_GMRES().fill(o.gmres)
     elif isinstance(ls, KrylovJL_GMRES):
         ls.fill(o.gmres)
+        if getattr(ls, "precs", None) is not None:
+            o.precond = ls.precs.code
         if alg.concrete_jac or sparse:  # needs_concrete_A false but concrete_jac = Val(true)  (jacobian.jl:43-47)
             o.linsolve = abi.LINSOLVE_SPARSE_GMRES
         else:
@@ -698,14 +722,20 @@ class GmresSolver:
             raise TypeError("unsupported operator")
         return op, keep
 
-    def solve(self, A, b, x=None):
+    def solve(self, A, b, x=None, Pl=None, Pr=None):
+        """Pl / Pr: operator handles that apply the inverse of the left / right preconditioner (e.g. BlockJacobi().linop)."""
         x = x or self.ctx.zeros(self.n)
         op, keep = self._op(A)
         st = abi.GmresStats()
         try:
+            check(self.ctx.handle, lib().b200_gmres_set_precond(self._h, Pl, Pr))
             check(self.ctx.handle, lib().b200_gmres_solve(self._h, op, b.ptr, x.ptr, C.byref(st)))
         finally:
+            lib().b200_gmres_set_precond(self._h, None, None)
             lib().b200_linop_destroy(op)
+            for q in (Pl, Pr):
+                if q is not None:
+                    lib().b200_linop_destroy(q)
         return x, st
 
     def hessenberg(self, iters):

@@ -158,7 +158,7 @@ struct b200_linop {
   void* user;
   b200_sparse_jac* sj;
 };
-enum { LINOP_PROBLEM = 0, LINOP_CSC = 1, LINOP_DENSE = 2, LINOP_CALLBACK = 3, LINOP_SPARSE_JAC = 4 };
+enum { LINOP_PROBLEM = 0, LINOP_CSC = 1, LINOP_DENSE = 2, LINOP_CALLBACK = 3, LINOP_SPARSE_JAC = 4, LINOP_BLOCK_JACOBI = 5 };
 
 // internal (non-ABI) helpers implemented across the .cu files
 int32_t b200i_linop_apply(b200_linop* op, const double* x, double* y);

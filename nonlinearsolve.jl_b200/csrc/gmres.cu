@@ -1087,6 +1087,8 @@ struct b200_gmres {
   unsigned long long* d_slots;  // resident engine: LL publication slots [2][160][2]
   unsigned ll_epoch;
   int dbg_on;
+  b200_linop *Pl, *Pr;   // borrowed preconditioners (apply the inverse)
+  double *pt1, *pt2;     // scratch vectors for preconditioned solves (allocated on first use)
 };
 
 namespace {
@@ -1177,6 +1179,21 @@ int32_t gm_fetch_state(b200_gmres* gm) {
 }  // namespace
 
 // ------------------------------------------------------------------ operator application (K2/K3)
+namespace {
+// y = D^-1 x, D = the 2x2 species blocks on the diagonal of the Brusselator Jacobian at u (cell c couples rows c and NC + c)
+__global__ void __launch_bounds__(GM_THREADS) block_jacobi_kernel(int64_t NC, double lapdiag, double A, const double* __restrict__ u, const double* __restrict__ x,
+                                                                   double* __restrict__ y) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= NC) return;
+  const double uc = u[c], vc = u[c + NC];
+  const double d00 = lapdiag + (2.0 * uc * vc - (A + 1.0)), d01 = uc * uc, d10 = A - 2.0 * uc * vc, d11 = lapdiag - uc * uc;
+  const double det = d00 * d11 - d01 * d10;
+  const double x0 = x[c], x1 = x[c + NC];
+  y[c] = (d11 * x0 - d01 * x1) / det;
+  y[c + NC] = (d00 * x1 - d10 * x0) / det;
+}
+}  // namespace
+
 int32_t b200i_linop_apply(b200_linop* op, const double* x, double* y) {
   b200_ctx* ctx = op->ctx;
   switch (op->kind) {
@@ -1195,6 +1212,13 @@ int32_t b200i_linop_apply(b200_linop* op, const double* x, double* y) {
       return op->mv(op->user, x, y) == 0 ? B200_OK : ctx->fail(B200_ERR_CALLBACK, "matvec callback failed", __FILE__, __LINE__);
     case LINOP_SPARSE_JAC:
       return b200_spmv(op->sj, op->nzval, x, y);
+    case LINOP_BLOCK_JACOBI: {
+      const int64_t NC = op->n / 2;
+      const double lapdiag = -(op->prob->kind == B200_PROB_BRUSS3D ? 6.0 : 4.0) * op->prob->a;
+      LAUNCH(ctx, block_jacobi_kernel, (int)((NC + GM_THREADS - 1) / GM_THREADS), GM_THREADS, 0, NC, lapdiag, op->prob->A, op->u, x, y);
+      CHECK_LAUNCH(ctx);
+      return B200_OK;
+    }
   }
   return ctx->fail(B200_ERR_INVALID, "unknown linop kind", __FILE__, __LINE__);
 }
@@ -1262,7 +1286,7 @@ int32_t b200_gmres_create(b200_ctx* ctx, int64_t n, const b200_gmres_opts* opts,
   gm->kcap = 0; gm->d_Vptrs = nullptr; gm->vptr_cap = 0;
   gm->d_h = gm->d_hacc = gm->d_R = gm->d_cs = gm->d_sn = gm->d_z = gm->d_y = gm->d_partial = nullptr;
   gm->d_hraw = nullptr; gm->hraw_cap = 0;
-  gm->d_bar = nullptr; gm->d_slots = nullptr; gm->ll_epoch = 0; gm->dbg_on = 0;
+  gm->d_bar = nullptr; gm->d_slots = nullptr; gm->ll_epoch = 0; gm->dbg_on = 0; gm->Pl = gm->Pr = nullptr; gm->pt1 = gm->pt2 = nullptr;
   // streaming grid: 4 CTAs of 256 threads per SM, fewer for small n (at least 512 rows per CTA)
   int64_t g = std::min<int64_t>((int64_t)ctx->sm_count * 4, std::max<int64_t>(1, n / 512));
   gm->G = (int)g;
@@ -1295,6 +1319,8 @@ int32_t b200_gmres_destroy(b200_gmres* gm) {
   cudaFreeHost(gm->h_state);
   if (gm->d_bar) cudaFree(gm->d_bar);
   if (gm->d_slots) cudaFree(gm->d_slots);
+  if (gm->pt1) cudaFree(gm->pt1);
+  if (gm->pt2) cudaFree(gm->pt2);
   gm_free_arrays(gm);
   delete gm;
   return B200_OK;
@@ -1303,6 +1329,24 @@ int32_t b200_gmres_destroy(b200_gmres* gm) {
 int32_t b200_gmres_set_tolerances(b200_gmres* gm, double atol, double rtol) {
   if (atol >= 0) gm->opts.atol = atol;
   if (rtol >= 0) gm->opts.rtol = rtol;
+  return B200_OK;
+}
+int32_t b200_gmres_set_precond(b200_gmres* gm, b200_linop* left_inv, b200_linop* right_inv) {
+  b200_ctx* ctx = gm->ctx;
+  B200_REQUIRE(ctx, (!left_inv || left_inv->n == gm->n) && (!right_inv || right_inv->n == gm->n), "gmres_set_precond: operator size mismatch");
+  gm->Pl = left_inv; gm->Pr = right_inv;
+  if ((left_inv || right_inv) && !gm->pt1) {
+    CUDA_TRY(ctx, cudaMalloc(&gm->pt1, sizeof(double) * (gm->n + 2)));
+    CUDA_TRY(ctx, cudaMalloc(&gm->pt2, sizeof(double) * (gm->n + 2)));
+  }
+  return B200_OK;
+}
+int32_t b200_linop_block_jacobi(b200_problem* prob, const double* u, b200_linop** out) {
+  B200_REQUIRE(prob->ctx, prob->kind == B200_PROB_BRUSS2D || prob->kind == B200_PROB_BRUSS3D, "block-Jacobi preconditioner: built-in Brusselator problems only");
+  b200_linop* op = new b200_linop();
+  memset(op, 0, sizeof(*op));
+  op->ctx = prob->ctx; op->kind = LINOP_BLOCK_JACOBI; op->n = prob->n; op->prob = prob; op->u = u;
+  *out = op;
   return B200_OK;
 }
 
@@ -1350,7 +1394,10 @@ int32_t b200_gmres_solve(b200_gmres* gm, b200_linop* op, const double* b, double
   size_t rs_smem = 0;
   const bool rs_builtin = op->kind == LINOP_PROBLEM && op->jvp_mode == B200_JVP_EXACT && (op->prob->kind == B200_PROB_BRUSS2D || op->prob->kind == B200_PROB_BRUSS3D);
   const bool rs_csr = op->kind == LINOP_SPARSE_JAC && n % 2 == 0;
-  if (o.engine != B200_ENGINE_MULTIKERNEL && (rs_builtin || rs_csr)) {
+  b200_linop *Pl = gm->Pl, *Pr = gm->Pr;
+  if ((Pl || Pr) && o.engine == B200_ENGINE_RESIDENT)
+    return ctx->fail(B200_ERR_UNSUPPORTED, "resident GMRES engine does not take preconditioners (use engine = auto / multikernel)", __FILE__, __LINE__);
+  if (o.engine != B200_ENGINE_MULTIKERNEL && (rs_builtin || rs_csr) && !Pl && !Pr) {
     rs_NC = n / 2;
     rs_G = ctx->sm_count;
     int64_t cpc = (rs_NC + rs_G - 1) / rs_G;
@@ -1413,6 +1460,11 @@ int32_t b200_gmres_solve(b200_gmres* gm, b200_linop* op, const double* b, double
       bytes += 3 * Bv;
     }
     LAUNCH(ctx, residual_init_kernel, std::min(G, B200_RED_MAX_BLOCKS), GM_THREADS, 0, n, b, Ax, gm->r0, gm->d_norm_partial);
+    if (Pl) {  // r0 <- M^-1 (b - A x): the iteration and its stopping test live in the left-preconditioned space
+      B200_TRY(b200i_linop_apply(Pl, gm->r0, gm->pt1));
+      LAUNCH(ctx, residual_init_kernel, std::min(G, B200_RED_MAX_BLOCKS), GM_THREADS, 0, n, (const double*)gm->pt1, (const double*)nullptr, gm->r0, gm->d_norm_partial);
+      bytes += 5 * Bv;
+    }
     LAUNCH(ctx, init_finish_kernel, 1, GM_THREADS, 0, gm->d_state, std::min(G, B200_RED_MAX_BLOCKS), gm->d_norm_partial, gm->d_z,
            first_cycle ? 1 : 0);
     LAUNCH(ctx, normalize_kernel, ew_grid, GM_THREADS, 0, gm->d_state, 0, gm->r0, gm->V[0], n);
@@ -1462,8 +1514,18 @@ int32_t b200_gmres_solve(b200_gmres* gm, b200_linop* op, const double* b, double
         ctx->launches++;
         if (ctx->prof_on) ctx->prof_end();
       } else {
-      // w = A v_k
-      B200_TRY(b200i_linop_apply(op, gm->V[k - 1], gm->w));
+      // w = M^-1 A N^-1 v_k
+      {
+        const double* in = gm->V[k - 1];
+        if (Pr) { B200_TRY(b200i_linop_apply(Pr, in, gm->pt1)); in = gm->pt1; bytes += 3 * Bv; }
+        if (Pl) {
+          B200_TRY(b200i_linop_apply(op, in, gm->pt2));
+          B200_TRY(b200i_linop_apply(Pl, gm->pt2, gm->w));
+          bytes += 3 * Bv;
+        } else {
+          B200_TRY(b200i_linop_apply(op, in, gm->w));
+        }
+      }
       if (orth == B200_ORTH_MGS) {
         double* pin = gm->d_norm_partial;
         double* pout = gm->d_norm_partial2;
@@ -1533,8 +1595,17 @@ int32_t b200_gmres_solve(b200_gmres* gm, b200_linop* op, const double* b, double
     // x += V_k y
     if (k > 0 && cycle_status != B200_LS_NONFINITE) {
       LAUNCH(ctx, backsolve_kernel, 1, GM_THREADS, sizeof(double) * (k + 1), gm->d_state, gm->d_R, gm->d_z, gm->d_y, gm->kcap);
+      if (Pr) {  // x += N^-1 (V_k y)
+        CUDA_TRY(ctx, cudaMemsetAsync(gm->pt1, 0, sizeof(double) * n, ctx->stream));
+        PLAUNCH(ctx, B200_KID_UPDATE, (k + 2.0) * Bv, update_kernel, G, GM_THREADS, sizeof(double) * (k + 32), gm->d_state, 1, (const double* const*)gm->d_Vptrs, k, gm->d_y, 1.0,
+               gm->pt1, gm->pt1, n, (double*)nullptr);
+        B200_TRY(b200i_linop_apply(Pr, gm->pt1, gm->pt2));
+        B200_TRY(b200_axpy(ctx, n, 1.0, gm->pt2, x));
+        bytes += 6 * Bv;
+      } else {
       PLAUNCH(ctx, B200_KID_UPDATE, (k + 2.0) * Bv, update_kernel, G, GM_THREADS, sizeof(double) * (k + 32), gm->d_state, 1, (const double* const*)gm->d_Vptrs, k, gm->d_y, 1.0,
              x, x, n, (double*)nullptr);
+      }
       CHECK_LAUNCH(ctx);
       bytes += (k + 2.0) * Bv;
       have_x = true;

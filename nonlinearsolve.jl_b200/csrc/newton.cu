@@ -37,6 +37,7 @@ struct b200_newton {
   double *u_trial, *fu_trial, *Jdu, *JTfu, *du_c, *c1, *c2;
   b200_gmres* gm;
   b200_linop op;
+  b200_linop prec;  // built-in preconditioner (opts.precond), re-pointed at the current iterate every step
   // dense
   double* Jdense;
   int64_t* ipiv;
@@ -131,6 +132,10 @@ int32_t b200_newton_destroy(b200_newton* nw) {
 int32_t b200_newton_create(b200_problem* prob, const b200_newton_opts* opts, b200_newton** out) {
   b200_ctx* ctx = prob->ctx;
   B200_REQUIRE(ctx, opts && out, "newton_create: bad arguments");
+  B200_REQUIRE(ctx, opts->precond == B200_PRECOND_NONE ||
+                        ((opts->linsolve == B200_LINSOLVE_GMRES || opts->linsolve == B200_LINSOLVE_SPARSE_GMRES) &&
+                         (prob->kind == B200_PROB_BRUSS2D || prob->kind == B200_PROB_BRUSS3D)),
+               "newton_create: the built-in block-Jacobi preconditioner needs a Krylov linsolve and a built-in Brusselator problem");
   b200_newton* nw = new b200_newton();
   nw->ctx = ctx; nw->prob = prob; nw->o = *opts; nw->n = prob->n;
   nw->abstol = opts->abstol > 0 ? opts->abstol : 3.0e-13;  // common_defaults.jl:44-48
@@ -290,6 +295,12 @@ static int32_t newton_step_inner(b200_newton* nw) {
     } else {
       // `linu` aliases the du buffer: it is the initial guess only when warm_start is requested
       if (o.gmres.warm_start) CUDA_TRY(ctx, cudaMemcpyAsync(nw->xlin, nw->du, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+      if (o.precond != B200_PRECOND_NONE) {  // precs(A, p): rebuilt from the current iterate, like update_A! does for Pl / Pr
+        memset(&nw->prec, 0, sizeof(nw->prec));
+        nw->prec.ctx = ctx; nw->prec.kind = LINOP_BLOCK_JACOBI; nw->prec.n = n; nw->prec.prob = nw->prob; nw->prec.u = nw->u;
+        B200_TRY(b200_gmres_set_precond(nw->gm, o.precond == B200_PRECOND_BLOCK_JACOBI_LEFT ? &nw->prec : nullptr,
+                                        o.precond == B200_PRECOND_BLOCK_JACOBI_RIGHT ? &nw->prec : nullptr));
+      }
       B200_TRY(b200_gmres_solve(nw->gm, &nw->op, nw->fu, nw->xlin, &gs));
       nw->res.njvp += gs.nmatvec;
       nw->bytes += gs.bytes;

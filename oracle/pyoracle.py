@@ -46,7 +46,7 @@ class NewtonOpts(C.Structure):
                 ("tr_step_threshold", C.c_double), ("tr_shrink_threshold", C.c_double), ("tr_expand_threshold", C.c_double),
                 ("tr_shrink_factor", C.c_double), ("tr_expand_factor", C.c_double), ("tr_max_trust_radius", C.c_double),
                 ("tr_initial_trust_radius", C.c_double), ("ls_c1", C.c_double), ("ls_rho_hi", C.c_double), ("ls_rho_lo", C.c_double),
-                ("ls_maxiters", C.c_int32), ("ls_reserved", C.c_int32)]
+                ("ls_maxiters", C.c_int32), ("precond", C.c_int32)]
 
 
 class NewtonResult(C.Structure):
