@@ -115,102 +115,6 @@ __device__ __forceinline__ void block_argmax(double& best, int64_t& bidx, double
   }
 }
 
-// arg-max partials of |A[i, col]|, i in [col, n)
-__global__ void __launch_bounds__(DT) pivot_search_kernel(int64_t n, const double* __restrict__ A, int64_t ld, int64_t col, PanelScratch* __restrict__ ps) {
-  __shared__ double smax[32];
-  __shared__ int64_t sidx[32];
-  const double* c = A + col * ld;
-  double best = -1.0;
-  int64_t bidx = INT64_MAX;
-  for (int64_t i = col + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const double v = fabs(c[i]);
-    if (v > best) { best = v; bidx = i; }
-  }
-  block_argmax(best, bidx, smax, sidx);
-  if (threadIdx.x == 0) {
-    ps->pmax[blockIdx.x] = best;
-    ps->pidx[blockIdx.x] = bidx;
-    if (blockIdx.x == 0) ps->nparts = gridDim.x;
-  }
-}
-
-// single CTA: final arg-max, ipiv, info, swap rows col <-> piv inside the outer panel [pc0, pc0 + pw), 1/pivot
-__global__ void __launch_bounds__(128) pivot_apply_kernel(double* __restrict__ A, int64_t ld, int64_t col, int64_t pc0, int pw,
-                                                           int64_t* __restrict__ ipiv, PanelScratch* __restrict__ ps) {
-  __shared__ int64_t piv_s;
-  if (threadIdx.x < 32) {
-    double best = -2.0;
-    int64_t bidx = INT64_MAX;
-    for (int b = threadIdx.x; b < ps->nparts; b += 32) argmax_combine(best, bidx, ps->pmax[b], ps->pidx[b]);
-    for (int o = 16; o > 0; o >>= 1) {
-      const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-      const int64_t oi = __shfl_xor_sync(0xffffffffu, bidx, o);
-      argmax_combine(best, bidx, ob, oi);
-    }
-    if (threadIdx.x == 0) {
-      if (bidx == INT64_MAX) bidx = col;  // all-NaN column: keep the diagonal
-      piv_s = bidx;
-      ps->piv = bidx;
-      ipiv[col] = bidx + 1;
-      const double pv = A[col * ld + bidx];
-      ps->inv_pivot = (pv == 0.0) ? 0.0 : 1.0 / pv;
-      if (pv == 0.0 && ps->info == 0) ps->info = (int)(col + 1);
-    }
-  }
-  __syncthreads();
-  const int64_t piv = piv_s;
-  if (piv != col) {
-    for (int c = threadIdx.x; c < pw; c += blockDim.x) {
-      double* cp = A + (pc0 + c) * ld;
-      const double t = cp[col];
-      cp[col] = cp[piv];
-      cp[piv] = t;
-    }
-  }
-}
-
-// rows i > col: l = A[i,col] / pivot ; A[i, col+1 .. ce) -= l * A[col, col+1 .. ce) ; fused arg-max partials of column col+1
-__global__ void __launch_bounds__(DT) column_update_kernel(int64_t n, double* __restrict__ A, int64_t ld, int64_t col, int64_t ce, int search_next,
-                                                            PanelScratch* __restrict__ ps) {
-  __shared__ double urow[NBI];
-  __shared__ double smax[32];
-  __shared__ int64_t sidx[32];
-  const double inv = ps->inv_pivot;
-  const int nc = (int)(ce - col - 1);
-  for (int c = threadIdx.x; c < nc; c += blockDim.x) urow[c] = A[(col + 1 + c) * ld + col];
-  __syncthreads();
-  double best = -1.0;
-  int64_t bidx = INT64_MAX;
-  if (inv != 0.0) {
-    for (int64_t i = col + 1 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-      const double l = A[col * ld + i] * inv;
-      A[col * ld + i] = l;
-      for (int c = 0; c < nc; ++c) {
-        double* p = A + (col + 1 + c) * ld + i;
-        const double v = fma(-l, urow[c], *p);
-        *p = v;
-        if (c == 0) {
-          const double av = fabs(v);
-          if (av > best) { best = av; bidx = i; }
-        }
-      }
-    }
-  } else if (search_next) {
-    for (int64_t i = col + 1 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-      const double av = fabs(A[(col + 1) * ld + i]);
-      if (av > best) { best = av; bidx = i; }
-    }
-  }
-  if (search_next) {
-    block_argmax(best, bidx, smax, sidx);
-    if (threadIdx.x == 0) {
-      ps->pmax[blockIdx.x] = best;
-      ps->pidx[blockIdx.x] = bidx;
-      if (blockIdx.x == 0) ps->nparts = gridDim.x;
-    }
-  }
-}
-
 // ---- cooperative inner panel: the kbi (<= 32) columns [c0, c0+kbi), rows [c0, n), factored by ONE kernel.  Every CTA keeps
 // its contiguous chunk of panel rows in shared memory (column-major, so a thread-per-row sweep is conflict free) for the
 // whole panel; per column only the arg-max partials and two 32-double rows cross CTAs, through two grid-wide barriers.
@@ -531,7 +435,6 @@ int32_t b200_getrf(b200_ctx* ctx, int64_t n, double* A, int64_t ld, int64_t* ipi
     CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_b, cudaEventDisableTiming));
   }
   cudaStream_t s_main = ctx->stream, s_panel = ctx->aux_stream;
-  auto nparts = [&](int64_t rows) { return (int)std::min<int64_t>(PS_MAX, std::max<int64_t>(1, (rows + 4 * DT - 1) / (4 * DT))); };
 
   // factor the outer panel A[k0:n, k0:k0+kbo] (inner panels of NBI columns); issued on whatever ctx->stream currently is
   auto factor_panel = [&](int64_t k0, int kbo) -> int32_t {
