@@ -83,6 +83,9 @@ enum { B200_ENGINE_AUTO = 0, B200_ENGINE_MULTIKERNEL = 1, B200_ENGINE_RESIDENT =
 enum { B200_LINSOLVE_GMRES = 0, B200_LINSOLVE_DENSE_LU = 1, B200_LINSOLVE_SPARSE_GMRES = 2 };
 enum { B200_JVP_EXACT = 0, B200_JVP_FINITE_DIFF = 1 };
 enum { B200_GLOBALIZATION_NONE = 0, B200_GLOBALIZATION_TRUST_REGION = 1, B200_GLOBALIZATION_LINESEARCH = 2 };
+/* descent: NewtonDescent (descent/newton.jl) or DampedNewtonDescent + SwitchedEvolutionRelaxation = PseudoTransient
+   (descent/damped_newton.jl:234-340, NonlinearSolveFirstOrder/src/pseudo_transient.jl:37-170): (J + I/alpha) du = -f */
+enum { B200_DESCENT_NEWTON = 0, B200_DESCENT_PSEUDO_TRANSIENT = 1 };
 enum { B200_PRECOND_NONE = 0, B200_PRECOND_BLOCK_JACOBI_LEFT = 1, B200_PRECOND_BLOCK_JACOBI_RIGHT = 2 };
 enum { B200_FORCING_NONE = 0, B200_FORCING_EW2 = 1 };
 enum { B200_TERM_ABS_NORM_SAFE_BEST = 0, B200_TERM_ABS_NORM = 1, B200_TERM_ABS_NORM_SAFE = 2 };
@@ -155,6 +158,9 @@ typedef struct b200_newton_opts {
   double ls_c1, ls_rho_hi, ls_rho_lo;
   int32_t ls_maxiters;
   int32_t precond; /* B200_PRECOND_*: built-in preconditioner handed to GMRES each step (LinearSolve `precs(A, p)`) */
+  int32_t descent; /* B200_DESCENT_* */
+  int32_t reserved0;
+  double pt_alpha_initial; /* PseudoTransient(alpha_initial = 1e-3); 0 => 1e-3 */
 } b200_newton_opts;
 
 typedef struct b200_newton_result {
@@ -250,6 +256,8 @@ int32_t b200_linop_from_csc(b200_ctx* ctx, int64_t n, const int64_t* colptr_dev,
 int32_t b200_linop_from_dense(b200_ctx* ctx, int64_t n, const double* A_dev, int64_t ld, b200_linop** op);
 int32_t b200_linop_from_callback(b200_ctx* ctx, int64_t n, b200_matvec_cb mv, void* user, b200_linop** op);
 int32_t b200_linop_apply(b200_linop* op, const double* x, double* y);
+/* A + shift I  (dampen_jacobian!!(cache, J::AbstractSciMLOperator, D) = J + D, descent/damped_newton.jl) */
+int32_t b200_linop_set_shift(b200_linop* op, double shift);
 int32_t b200_linop_destroy(b200_linop* op);
 
 void b200_gmres_opts_default(b200_gmres_opts* opts);

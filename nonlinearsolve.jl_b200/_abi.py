@@ -25,6 +25,7 @@ LINSOLVE_GMRES, LINSOLVE_DENSE_LU, LINSOLVE_SPARSE_GMRES = 0, 1, 2
 JVP_EXACT, JVP_FINITE_DIFF = 0, 1
 GLOB_NONE, GLOB_TRUST_REGION, GLOB_LINESEARCH = 0, 1, 2
 PRECOND_NONE, PRECOND_BLOCK_JACOBI_LEFT, PRECOND_BLOCK_JACOBI_RIGHT = 0, 1, 2
+DESCENT_NEWTON, DESCENT_PSEUDO_TRANSIENT = 0, 1
 FORCING_NONE, FORCING_EW2 = 0, 1
 TERM_ABS_NORM_SAFE_BEST, TERM_ABS_NORM, TERM_ABS_NORM_SAFE = 0, 1, 2
 U0_REFERENCE, U0_PERTURBED_Z = 0, 1
@@ -52,7 +53,8 @@ class NewtonOpts(C.Structure):
                 ("tr_step_threshold", C.c_double), ("tr_shrink_threshold", C.c_double), ("tr_expand_threshold", C.c_double),
                 ("tr_shrink_factor", C.c_double), ("tr_expand_factor", C.c_double), ("tr_max_trust_radius", C.c_double),
                 ("tr_initial_trust_radius", C.c_double), ("ls_c1", C.c_double), ("ls_rho_hi", C.c_double), ("ls_rho_lo", C.c_double),
-                ("ls_maxiters", C.c_int32), ("precond", C.c_int32)]
+                ("ls_maxiters", C.c_int32), ("precond", C.c_int32), ("descent", C.c_int32), ("reserved0", C.c_int32),
+                ("pt_alpha_initial", C.c_double)]
 
 
 class NewtonResult(C.Structure):
@@ -140,6 +142,7 @@ SIGNATURES = {
     "b200_gmres_destroy": (I32, [P]),
     "b200_gmres_set_tolerances": (I32, [P, F64, F64]),
     "b200_gmres_set_precond": (I32, [P, P, P]),
+    "b200_linop_set_shift": (I32, [P, F64]),
     "b200_linop_block_jacobi": (I32, [P, P, PP]),
     "b200_gmres_solve": (I32, [P, P, P, P, C.POINTER(GmresStats)]),
     "b200_dense_jac_fill": (I32, [P, P, P, I64]),

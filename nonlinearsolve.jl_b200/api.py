@@ -435,6 +435,17 @@ class NewtonRaphson(_FirstOrder):
     name = "NewtonRaphson"
 
 
+class PseudoTransient(_FirstOrder):
+    """PseudoTransient(; alpha_initial = 1e-3, linsolve, linesearch, ...): DampedNewtonDescent with switched evolution
+    relaxation, (J + I/alpha) du = -f, alpha_{n+1} = alpha_n ||f_{n-1}|| / ||f_n||  (pseudo_transient.jl:37-56, 157-170)."""
+    name = "PseudoTransient"
+    descent = abi.DESCENT_PSEUDO_TRANSIENT
+
+    def __init__(self, concrete_jac=None, linsolve=None, autodiff=None, jvp_autodiff=None, vjp_autodiff=None, linesearch=None, alpha_initial=1.0e-3):
+        super().__init__(concrete_jac, linsolve, autodiff, jvp_autodiff, vjp_autodiff, None, linesearch)
+        self.alpha_initial = float(alpha_initial)
+
+
 class TrustRegion(_FirstOrder):
     """TrustRegion(; ...) with RadiusUpdateSchemes.Simple and Dogleg descent  trust_region.jl:25-43."""
     name = "TrustRegion"
@@ -458,6 +469,8 @@ def _build_opts(prob, alg, abstol, reltol, maxiters, termination_condition, stor
     o.maxiters = int(maxiters)
     o.store_trace = 1 if store_trace else 0
     o.globalization = alg.globalization
+    o.descent = getattr(alg, "descent", abi.DESCENT_NEWTON)
+    o.pt_alpha_initial = getattr(alg, "alpha_initial", 0.0)
     if termination_condition is not None:
         o.termination = termination_condition.code
     ls = alg.linsolve

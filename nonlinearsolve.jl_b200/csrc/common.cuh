@@ -157,11 +157,13 @@ struct b200_linop {
   b200_matvec_cb mv;
   void* user;
   b200_sparse_jac* sj;
+  double shift;  // operator is A + shift I
 };
 enum { LINOP_PROBLEM = 0, LINOP_CSC = 1, LINOP_DENSE = 2, LINOP_CALLBACK = 3, LINOP_SPARSE_JAC = 4, LINOP_BLOCK_JACOBI = 5 };
 
 // internal (non-ABI) helpers implemented across the .cu files
 int32_t b200i_linop_apply(b200_linop* op, const double* x, double* y);
+int32_t b200i_diag_shift(b200_ctx* ctx, int64_t n, double* A, int64_t ld, double shift);  // A[i,i] += shift
 void b200i_sparse_jac_csr(b200_sparse_jac* sj, const int64_t** rowptr, const int64_t** csr_col, const int64_t** csr_map);
 int32_t b200i_residual_norm(b200_problem* prob, const double* u, double* du, double* d_norminf /*device, pre-zeroed*/);
 int32_t b200i_axpy_norm(b200_ctx* ctx, int64_t n, double a, const double* x, double* y, double* d_sumsq /*device, pre-zeroed*/);

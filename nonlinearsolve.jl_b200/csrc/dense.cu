@@ -388,6 +388,18 @@ __global__ void __launch_bounds__(DT) trisolve_update_kernel(int lower, int64_t 
 }
 }  // namespace
 
+namespace {
+__global__ void __launch_bounds__(256) diag_shift_kernel(int64_t n, double* __restrict__ A, int64_t ld, double shift) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) A[i * ld + i] += shift;
+}
+}  // namespace
+int32_t b200i_diag_shift(b200_ctx* ctx, int64_t n, double* A, int64_t ld, double shift) {
+  LAUNCH(ctx, diag_shift_kernel, (int)((n + 255) / 256), 256, 0, n, A, ld, shift);
+  CHECK_LAUNCH(ctx);
+  return B200_OK;
+}
+
 extern "C" {
 int32_t b200_dense_jac_fill(b200_problem* p, const double* u, double* J, int64_t ld) {
   b200_ctx* ctx = p->ctx;

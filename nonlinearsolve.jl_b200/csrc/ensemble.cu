@@ -56,7 +56,8 @@ int32_t b200_ens_destroy(b200_ensemble* e) {
 
 int32_t b200_ens_create(b200_ctx* ctx, int32_t N, int32_t nprob_local, double alpha, const b200_newton_opts* opts, b200_ensemble** out) {
   B200_REQUIRE(ctx, N >= 3 && nprob_local > 0 && opts && out, "ens_create: bad arguments");
-  B200_REQUIRE(ctx, opts->linsolve == B200_LINSOLVE_GMRES && opts->globalization == B200_GLOBALIZATION_NONE && opts->precond == B200_PRECOND_NONE,
+  B200_REQUIRE(ctx, opts->linsolve == B200_LINSOLVE_GMRES && opts->globalization == B200_GLOBALIZATION_NONE && opts->precond == B200_PRECOND_NONE &&
+                        opts->descent == B200_DESCENT_NEWTON,
                "ensemble: only matrix-free NewtonRaphson(linsolve = GMRES) trajectories are batched");
   b200_ensemble* e = new b200_ensemble();
   memset(e, 0, sizeof(*e));

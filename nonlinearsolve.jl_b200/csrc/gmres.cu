@@ -466,8 +466,7 @@ __global__ void __launch_bounds__(GM_THREADS) dense_gemv_kernel(int trans, int64
 //      from the copy still in shared memory.  This is modified Gram-Schmidt (Krylov.jl's scheme), applied twice when
 //      reorthogonalisation is requested: `passes * k * Bv` of HBM traffic instead of the 2x of the multi-kernel engine;
 //   3. ||w||, Givens recurrence (CTA 0), normalisation and the store of v_{k+1} close the step.
-// Grid-wide barriers are a release/acquire counter in global memory (cooperative launch guarantees co-residency); spins
-// are bounded so a fault can never hang the GPU.
+// Cross-CTA exchanges poll with bounded spins so a fault can never hang the GPU (cooperative launch guarantees co-residency).
 constexpr int RS_THREADS = 512;
 constexpr int RS_RR = 28;  // max rows per thread -> at most 28 * 512 = 14336 rows (7168 cells) per CTA
 
@@ -491,31 +490,12 @@ struct ResidentParams {
   GmresState* st;
 };
 
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned target, int* err) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(bar, 1u);
-    unsigned spins = 0;
-    while (ld_acquire_u32(bar) < target) {
-      if (++spins > (1u << 24)) { *err = 1; break; }  // ~seconds: bounded, never a hang
-    }
-    __threadfence();
-  }
-  __syncthreads();
-}
 // Cross-CTA all-to-all of one double per CTA with the synchronisation folded into the data (the idea of NCCL's LL
 // protocol): each 64-bit word carries 32 data bits and a 32-bit epoch, and 64-bit stores are single transactions, so a
 // reader that sees the expected epoch in both words has the value — no fence, no atomic, no separate barrier, one L2 round
 // trip.  Two slot buffers alternate by step parity: a CTA can only overwrite a buffer two steps later, i.e. after every
 // other CTA has passed the step in between and therefore finished reading the older value.
 // Every slot sits in its own 256-byte block so that the all-to-all polls spread over the L2 slices instead of hammering one.
-constexpr int LL_STRIDE = 32;  // u64 words per slot
 constexpr int LL_MAXG = 160;
 // PUSH model (NCCL-LL all-gather style): CTA b posts its word pair into slot b of EVERY destination CTA's private receive
 // buffer (posted, uncoalesced stores that nobody waits on); each CTA then polls only its own dense buffer with coalesced
@@ -1194,7 +1174,13 @@ __global__ void __launch_bounds__(GM_THREADS) block_jacobi_kernel(int64_t NC, do
 }
 }  // namespace
 
+static int32_t linop_apply_unshifted(b200_linop* op, const double* x, double* y);
 int32_t b200i_linop_apply(b200_linop* op, const double* x, double* y) {
+  B200_TRY(linop_apply_unshifted(op, x, y));
+  if (op->shift != 0.0) B200_TRY(b200_axpy(op->ctx, op->n, op->shift, x, y));
+  return B200_OK;
+}
+static int32_t linop_apply_unshifted(b200_linop* op, const double* x, double* y) {
   b200_ctx* ctx = op->ctx;
   switch (op->kind) {
     case LINOP_PROBLEM:
@@ -1264,6 +1250,7 @@ int32_t b200_linop_from_callback(b200_ctx* ctx, int64_t n, b200_matvec_cb mv, vo
   return B200_OK;
 }
 int32_t b200_linop_apply(b200_linop* op, const double* x, double* y) { return b200i_linop_apply(op, x, y); }
+int32_t b200_linop_set_shift(b200_linop* op, double shift) { op->shift = shift; return B200_OK; }
 int32_t b200_linop_destroy(b200_linop* op) { delete op; return B200_OK; }
 
 void b200_gmres_opts_default(b200_gmres_opts* o) {
@@ -1397,7 +1384,9 @@ int32_t b200_gmres_solve(b200_gmres* gm, b200_linop* op, const double* b, double
   b200_linop *Pl = gm->Pl, *Pr = gm->Pr;
   if ((Pl || Pr) && o.engine == B200_ENGINE_RESIDENT)
     return ctx->fail(B200_ERR_UNSUPPORTED, "resident GMRES engine does not take preconditioners (use engine = auto / multikernel)", __FILE__, __LINE__);
-  if (o.engine != B200_ENGINE_MULTIKERNEL && (rs_builtin || rs_csr) && !Pl && !Pr) {
+  if (op->shift != 0.0 && o.engine == B200_ENGINE_RESIDENT)
+    return ctx->fail(B200_ERR_UNSUPPORTED, "resident GMRES engine does not take shifted operators (use engine = auto / multikernel)", __FILE__, __LINE__);
+  if (o.engine != B200_ENGINE_MULTIKERNEL && (rs_builtin || rs_csr) && !Pl && !Pr && op->shift == 0.0) {
     rs_NC = n / 2;
     rs_G = ctx->sm_count;
     int64_t cpc = (rs_NC + rs_G - 1) / rs_G;

@@ -52,6 +52,7 @@ struct b200_newton {
   double trust_region, max_tr;
   int shrink_counter;
   double eta, rnorm, rnorm_prev;
+  double alpha_inv, pt_res_norm;  // PseudoTransient: 1/alpha and the residual 2-norm of the previous step (SER)
   double fnorm_inf;  // ||f(u)||_inf of the current iterate
   double bytes;
 };
@@ -132,6 +133,8 @@ int32_t b200_newton_destroy(b200_newton* nw) {
 int32_t b200_newton_create(b200_problem* prob, const b200_newton_opts* opts, b200_newton** out) {
   b200_ctx* ctx = prob->ctx;
   B200_REQUIRE(ctx, opts && out, "newton_create: bad arguments");
+  B200_REQUIRE(ctx, opts->descent == B200_DESCENT_NEWTON || (opts->descent == B200_DESCENT_PSEUDO_TRANSIENT && opts->globalization != B200_GLOBALIZATION_TRUST_REGION),
+               "newton_create: descent must be Newton or PseudoTransient (the latter without a trust region)");
   B200_REQUIRE(ctx, opts->precond == B200_PRECOND_NONE ||
                         ((opts->linsolve == B200_LINSOLVE_GMRES || opts->linsolve == B200_LINSOLVE_SPARSE_GMRES) &&
                          (prob->kind == B200_PROB_BRUSS2D || prob->kind == B200_PROB_BRUSS3D)),
@@ -223,6 +226,11 @@ int32_t b200_newton_reinit(b200_newton* nw, const double* u0_dev) {
     nw->max_tr = o.tr_max_trust_radius > 0 ? o.tr_max_trust_radius : std::max(fu_norm, umax - umin);
     nw->trust_region = o.tr_initial_trust_radius > 0 ? o.tr_initial_trust_radius : nw->max_tr / 11.0;
   }
+  if (o.descent == B200_DESCENT_PSEUDO_TRANSIENT) {  // SwitchedEvolutionRelaxationCache init / reinit! (pseudo_transient.jl:105-130)
+    nw->alpha_inv = 1.0 / (o.pt_alpha_initial > 0 ? o.pt_alpha_initial : 1.0e-3);
+    B200_TRY(h_nrm2(nw, nw->fu, &nw->pt_res_norm));
+  }
+  nw->op.shift = 0.0;
   nw->eta = o.ew_eta0;
   if (o.forcing == B200_FORCING_EW2) {
     B200_TRY(h_nrm2(nw, nw->fu, &nw->rnorm));
@@ -261,6 +269,16 @@ static int32_t newton_step_inner(b200_newton* nw) {
     } else {
       new_jacobian = 0;
     }
+    if (o.descent == B200_DESCENT_PSEUDO_TRANSIENT && attempt == 0) {
+      // SER (pseudo_transient.jl:157-170): alpha^-1 *= ||f_n|| / ||f_{n-1}||  (2-norm); A = J + alpha^-1 I
+      double rn;
+      B200_TRY(h_nrm2(nw, nw->fu, &rn));
+      nw->alpha_inv *= rn / nw->pt_res_norm;
+      nw->pt_res_norm = rn;
+      nw->op.shift = nw->alpha_inv;
+    }
+    if (o.descent == B200_DESCENT_PSEUDO_TRANSIENT && o.linsolve == B200_LINSOLVE_DENSE_LU && new_jacobian)
+      B200_TRY(b200i_diag_shift(ctx, n, nw->Jdense, n, nw->alpha_inv));  // dampen_jacobian!!: J[i,i] += alpha^-1
     if (o.forcing == B200_FORCING_EW2 && krylov) {  // pre_step_forcing!   eisenstat_walker.jl:42-80
       if (nw->nsteps == 0) {
         nw->eta = o.ew_eta0;
@@ -457,7 +475,7 @@ static int32_t newton_step_inner(b200_newton* nw) {
     if (o.store_trace) {
       b200_trace_rec t;
       t.iter = nw->nsteps + 1; t.lin_iters = gs.iters; t.lin_status = gs.status; t.accepted = accepted;
-      t.fnorm_inf = objective; t.step_norm2 = du_norm; t.lin_rnorm = gs.rnorm; t.trust_radius = (o.globalization == B200_GLOBALIZATION_LINESEARCH) ? ls_alpha : nw->trust_region;
+      t.fnorm_inf = objective; t.step_norm2 = du_norm; t.lin_rnorm = gs.rnorm; t.trust_radius = (o.globalization == B200_GLOBALIZATION_LINESEARCH) ? ls_alpha : (o.descent == B200_DESCENT_PSEUDO_TRANSIENT) ? 1.0 / nw->alpha_inv : nw->trust_region;
       nw->trace.push_back(t);
     }
     // copyto!(u_cache, u) (solve.jl:460) is only ever read back as `uprev` for the stall norm, which the update kernel

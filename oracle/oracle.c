@@ -335,6 +335,8 @@ void orc_linop_apply(const orc_linop* op, const double* x, double* y) {
     } break;
     default: break;
   }
+  if (op->shift != 0.0) /* dampen_jacobian!!(cache, J::AbstractSciMLOperator, D) = J + D  (descent/damped_newton.jl) */
+    for (int64_t i = 0; i < op->n; ++i) y[i] += op->shift * x[i];
 }
 
 /* ------------------------------------------------------------------ GMRES
@@ -830,6 +832,12 @@ void orc_newton_solve(const orc_problem* p, const double* u0, const b200_newton_
     max_tr = o->tr_max_trust_radius > 0 ? o->tr_max_trust_radius : fmax(fu_norm, umax - umin);
     trust_region = o->tr_initial_trust_radius > 0 ? o->tr_initial_trust_radius : max_tr / 11.0;
   }
+  /* PseudoTransient = DampedNewtonDescent + SwitchedEvolutionRelaxation (pseudo_transient.jl:37-56, 105-170;
+     descent/damped_newton.jl:290-296 `:simple` mode): solve (J + alpha^-1 I) x = fu, du = -x;
+     alpha^-1 starts at 1/alpha_initial and is multiplied by ||f_n||_2 / ||f_{n-1}||_2 before every solve (ratio 1 at the first) */
+  const int pt_on = o->descent == B200_DESCENT_PSEUDO_TRANSIENT;
+  double alpha_inv = pt_on ? 1.0 / (o->pt_alpha_initial > 0 ? o->pt_alpha_initial : 1.0e-3) : 0.0;
+  double pt_res_norm = v_nrm2(n, fu);
   /* forcing init (eisenstat_walker.jl:90-98) */
   double eta = o->ew_eta0, rnorm = v_nrm2(n, fu), rnorm_prev = rnorm;
 
@@ -847,6 +855,12 @@ void orc_newton_solve(const orc_problem* p, const double* u0, const b200_newton_
       else if (o->linsolve == B200_LINSOLVE_SPARSE_GMRES) { res->njacs += 1; orc_sparse_jac_fill(p, u, colptr, rowval, 1, colors, ncolors, nzval); }
     } else new_jacobian = 0;
 
+    if (pt_on && !recompute_forced) {
+      const double rn = v_nrm2(n, fu);
+      alpha_inv *= rn / pt_res_norm;
+      pt_res_norm = rn;
+      op.shift = alpha_inv;
+    }
     if (o->forcing == B200_FORCING_EW2 && o->linsolve != B200_LINSOLVE_DENSE_LU) { /* pre_step_forcing!  :42-80 */
       if (nsteps == 0) { eta = o->ew_eta0; rnorm = rnorm_prev = v_nrm2(n, fu); }
       else {
@@ -866,7 +880,9 @@ void orc_newton_solve(const orc_problem* p, const double* u0, const b200_newton_
       int reuse = !new_jacobian;
       if (!(reuse && have_factor)) { /* update_A! for factorisations (NonlinearSolveBaseLinearSolveExt.jl:81-86) */
         res->nfactors += 1; int32_t info; /* copyto!(lincache.A, J) then lu!  (…LinearSolveExt.jl:102-111) */
-        memcpy(LU, Jdense, (size_t)n * n * 8); orc_getrf(n, LU, n, ipiv, &info); have_factor = 1;
+        memcpy(LU, Jdense, (size_t)n * n * 8);
+        if (pt_on) for (int64_t i = 0; i < n; ++i) LU[i * n + i] += alpha_inv; /* dampen_jacobian!!: diagonal += alpha^-1 */
+        orc_getrf(n, LU, n, ipiv, &info); have_factor = 1;
         if (info != 0) lin_success = 0;
       }
       v_copy(n, fu, xlin);
@@ -976,7 +992,7 @@ void orc_newton_solve(const orc_problem* p, const double* u0, const b200_newton_
     if (trace && ntrace < trace_cap) {
       b200_trace_rec* t = &trace[ntrace];
       t->iter = nsteps + 1; t->lin_iters = gs.iters; t->lin_status = gs.status; t->accepted = accepted;
-      t->fnorm_inf = v_norminf(n, fu); t->step_norm2 = v_diffnrm2(n, u, u_cache); t->lin_rnorm = gs.rnorm; t->trust_radius = (o->globalization == B200_GLOBALIZATION_LINESEARCH) ? ls_alpha : trust_region;
+      t->fnorm_inf = v_norminf(n, fu); t->step_norm2 = v_diffnrm2(n, u, u_cache); t->lin_rnorm = gs.rnorm; t->trust_radius = (o->globalization == B200_GLOBALIZATION_LINESEARCH) ? ls_alpha : pt_on ? 1.0 / alpha_inv : trust_region;
     }
     ++ntrace;
     v_copy(n, u, u_cache);

@@ -50,6 +50,7 @@ typedef struct orc_linop {
   const double* nzval;
   const double* A;
   int64_t ld;
+  double shift; /* operator is A + shift I (DampedNewtonDescent: J + D) */
 } orc_linop;
 
 void orc_set_threads(int32_t nthreads);
