@@ -85,6 +85,9 @@ enum { B200_JVP_EXACT = 0, B200_JVP_FINITE_DIFF = 1 };
 enum { B200_GLOBALIZATION_NONE = 0, B200_GLOBALIZATION_TRUST_REGION = 1, B200_GLOBALIZATION_LINESEARCH = 2 };
 /* descent: NewtonDescent (descent/newton.jl) or DampedNewtonDescent + SwitchedEvolutionRelaxation = PseudoTransient
    (descent/damped_newton.jl:234-340, NonlinearSolveFirstOrder/src/pseudo_transient.jl:37-170): (J + I/alpha) du = -f */
+/* RadiusUpdateSchemes.{Simple, NLsolve, NocedalWright, Hei, Yuan, Fan} (Bastin is not offered: its delta-u cache is never
+   filled in the reference, trust_region.jl:484-503) */
+enum { B200_TR_SIMPLE = 0, B200_TR_NLSOLVE = 1, B200_TR_NOCEDAL_WRIGHT = 2, B200_TR_HEI = 3, B200_TR_YUAN = 4, B200_TR_FAN = 5 };
 enum { B200_DESCENT_NEWTON = 0, B200_DESCENT_PSEUDO_TRANSIENT = 1 };
 enum { B200_PRECOND_NONE = 0, B200_PRECOND_BLOCK_JACOBI_LEFT = 1, B200_PRECOND_BLOCK_JACOBI_RIGHT = 2 };
 enum { B200_FORCING_NONE = 0, B200_FORCING_EW2 = 1 };
@@ -159,7 +162,7 @@ typedef struct b200_newton_opts {
   int32_t ls_maxiters;
   int32_t precond; /* B200_PRECOND_*: built-in preconditioner handed to GMRES each step (LinearSolve `precs(A, p)`) */
   int32_t descent; /* B200_DESCENT_* */
-  int32_t reserved0;
+  int32_t tr_scheme; /* B200_TR_*: RadiusUpdateSchemes (trust_region.jl:431-509); thresholds/factors of 0 take the scheme's defaults (:330-384) */
   double pt_alpha_initial; /* PseudoTransient(alpha_initial = 1e-3); 0 => 1e-3 */
 } b200_newton_opts;
 

@@ -176,7 +176,7 @@ struct NewtonOpts
     tr_step_threshold::Float64; tr_shrink_threshold::Float64; tr_expand_threshold::Float64; tr_shrink_factor::Float64
     tr_expand_factor::Float64; tr_max_trust_radius::Float64; tr_initial_trust_radius::Float64
     ls_c1::Float64; ls_rho_hi::Float64; ls_rho_lo::Float64; ls_maxiters::Int32; precond::Int32
-    descent::Int32; reserved0::Int32; pt_alpha_initial::Float64
+    descent::Int32; tr_scheme::Int32; pt_alpha_initial::Float64
 end
 struct NewtonResult
     retcode::Int32; nsteps::Int32; nf::Int32; njacs::Int32; nfactors::Int32; nsolve::Int32; njvp::Int32; ntrace::Int32

@@ -446,15 +446,24 @@ class PseudoTransient(_FirstOrder):
         self.alpha_initial = float(alpha_initial)
 
 
+class RadiusUpdateSchemes:
+    """RadiusUpdateSchemes.{Simple, NLsolve, NocedalWright, Hei, Yuan, Fan}  (trust_region.jl:431-509)."""
+    Simple, NLsolve, NocedalWright, Hei, Yuan, Fan = (abi.TR_SIMPLE, abi.TR_NLSOLVE, abi.TR_NOCEDAL_WRIGHT, abi.TR_HEI, abi.TR_YUAN, abi.TR_FAN)
+
+
 class TrustRegion(_FirstOrder):
-    """TrustRegion(; ...) with RadiusUpdateSchemes.Simple and Dogleg descent  trust_region.jl:25-43."""
+    """TrustRegion(; radius_update_scheme = RadiusUpdateSchemes.Simple, ...) with Dogleg descent  trust_region.jl:25-43.
+    Thresholds / factors left at `None` (or 0) take the scheme's defaults (trust_region.jl:330-384)."""
     name = "TrustRegion"
     globalization = abi.GLOB_TRUST_REGION
 
     def __init__(self, concrete_jac=None, linsolve=None, autodiff=None, jvp_autodiff=None, vjp_autodiff=None, max_trust_radius=0.0,
-                 initial_trust_radius=0.0, step_threshold=1.0 / 10000, shrink_threshold=0.25, expand_threshold=0.75, shrink_factor=0.25,
-                 expand_factor=2.0, max_shrink_times=32):
+                 initial_trust_radius=0.0, step_threshold=None, shrink_threshold=None, expand_threshold=None, shrink_factor=None,
+                 expand_factor=None, max_shrink_times=32, radius_update_scheme=abi.TR_SIMPLE):
         super().__init__(concrete_jac, linsolve, autodiff, jvp_autodiff, vjp_autodiff, None)
+        self.radius_update_scheme = int(radius_update_scheme)
+        step_threshold, shrink_threshold, expand_threshold, shrink_factor, expand_factor = (
+            0.0 if v is None else v for v in (step_threshold, shrink_threshold, expand_threshold, shrink_factor, expand_factor))
         self.tr = dict(tr_max_trust_radius=max_trust_radius, tr_initial_trust_radius=initial_trust_radius,
                        tr_step_threshold=step_threshold, tr_shrink_threshold=shrink_threshold, tr_expand_threshold=expand_threshold,
                        tr_shrink_factor=shrink_factor, tr_expand_factor=expand_factor)
@@ -508,6 +517,7 @@ def _build_opts(prob, alg, abstol, reltol, maxiters, termination_condition, stor
         for k, v in alg.tr.items():
             setattr(o, k, float(v))
         o.max_shrink_times = int(alg.max_shrink_times)
+        o.tr_scheme = int(alg.radius_update_scheme)
     return o
 
 

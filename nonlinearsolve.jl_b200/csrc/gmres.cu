@@ -1488,7 +1488,7 @@ int32_t b200_gmres_solve(b200_gmres* gm, b200_linop* op, const double* b, double
           gm->ll_epoch = 0;
         }
         RP.dbg = gm->dbg_on ? gm->d_norm_partial2 : nullptr;
-        { static const int li = getenv("B200_RS_LATE") ? atoi(getenv("B200_RS_LATE")) : 0; RP.late_issue = li; }
+        { static const int li = getenv("B200_RS_LATE") ? atoi(getenv("B200_RS_LATE")) : 0; RP.late_issue = (li == 1) ? 1 : 0; }  // A/B knob of the two-stage kernel: prefetch after the exchange
         RP.slots = gm->d_slots; RP.epoch_base = gm->ll_epoch; RP.err = reinterpret_cast<int*>(gm->d_bar + 1);
         gm->ll_epoch += (unsigned)(rs_passes * k + 2);
         RP.h = gm->d_h; RP.R = gm->d_R; RP.cs = gm->d_cs; RP.sn = gm->d_sn; RP.z = gm->d_z;

@@ -52,6 +52,7 @@ struct b200_newton {
   double trust_region, max_tr;
   int shrink_counter;
   double eta, rnorm, rnorm_prev;
+  double tp1, tp2, tp3, tp4;      // radius-update scheme parameters (get_parameters, trust_region.jl:372-379)
   double alpha_inv, pt_res_norm;  // PseudoTransient: 1/alpha and the residual 2-norm of the previous step (SER)
   double fnorm_inf;  // ||f(u)||_inf of the current iterate
   double bytes;
@@ -133,6 +134,7 @@ int32_t b200_newton_destroy(b200_newton* nw) {
 int32_t b200_newton_create(b200_problem* prob, const b200_newton_opts* opts, b200_newton** out) {
   b200_ctx* ctx = prob->ctx;
   B200_REQUIRE(ctx, opts && out, "newton_create: bad arguments");
+  B200_REQUIRE(ctx, opts->tr_scheme >= B200_TR_SIMPLE && opts->tr_scheme <= B200_TR_FAN, "newton_create: unknown radius update scheme");
   B200_REQUIRE(ctx, opts->descent == B200_DESCENT_NEWTON || (opts->descent == B200_DESCENT_PSEUDO_TRANSIENT && opts->globalization != B200_GLOBALIZATION_TRUST_REGION),
                "newton_create: descent must be Newton or PseudoTransient (the latter without a trust region)");
   B200_REQUIRE(ctx, opts->precond == B200_PRECOND_NONE ||
@@ -220,11 +222,29 @@ int32_t b200_newton_reinit(b200_newton* nw, const double* u0_dev) {
   nw->shrink_counter = 0; nw->bytes = 2.0 * 8.0 * n;
   if (o.linsolve == B200_LINSOLVE_DENSE_LU) nw->res.njacs += 1;  // jac_prototype === nothing: DI.jacobian at init (jacobian.jl:103-117)
   if (o.globalization == B200_GLOBALIZATION_TRUST_REGION) {  // trust_region.jl:204-258, 330-346 (Simple scheme)
-    double fu_norm, umin, umax;
+    double fu_norm, u0_norm, umin, umax;
+    const int sch = o.tr_scheme;
     B200_TRY(h_nrm2(nw, nw->fu, &fu_norm));
+    B200_TRY(h_nrm2(nw, nw->u, &u0_norm));
     B200_TRY(b200_extrema(ctx, n, nw->u, &umin, &umax));
-    nw->max_tr = o.tr_max_trust_radius > 0 ? o.tr_max_trust_radius : std::max(fu_norm, umax - umin);
-    nw->trust_region = o.tr_initial_trust_radius > 0 ? o.tr_initial_trust_radius : nw->max_tr / 11.0;
+    nw->tp1 = nw->tp2 = nw->tp3 = nw->tp4 = 0.0;
+    if (sch == B200_TR_NLSOLVE) { nw->tp1 = 0.5; }
+    else if (sch == B200_TR_HEI) { nw->tp1 = 5.0; nw->tp2 = 0.1; nw->tp3 = 0.15; nw->tp4 = 0.15; }
+    else if (sch == B200_TR_YUAN) { nw->tp1 = 2.0; nw->tp2 = 1.0 / 6; nw->tp3 = 6.0; }
+    else if (sch == B200_TR_FAN) { nw->tp1 = 0.1; nw->tp2 = 0.25; nw->tp3 = 12.0; nw->tp4 = 1.0e18; }
+    if (o.tr_max_trust_radius > 0) nw->max_tr = o.tr_max_trust_radius;  // max_trust_radius  :330-337
+    else nw->max_tr = (sch == B200_TR_SIMPLE || sch == B200_TR_NOCEDAL_WRIGHT) ? std::max(fu_norm, umax - umin) : INFINITY;
+    if (o.tr_initial_trust_radius > 0) nw->trust_region = o.tr_initial_trust_radius;  // initial_trust_radius  :339-346
+    else if (sch == B200_TR_NLSOLVE) nw->trust_region = u0_norm > 0 ? u0_norm : 1.0;
+    else if (sch == B200_TR_HEI) nw->trust_region = 1.0;
+    else if (sch == B200_TR_FAN) nw->trust_region = pow(fu_norm, 0.99) / 10.0;
+    else nw->trust_region = nw->max_tr / 11.0;
+    if (sch == B200_TR_YUAN) {  // itr = p1 ||J' fu||  :232-234
+      double g;
+      B200_TRY(b200_vjp(nw->prob, nw->u, nw->fu, nw->JTfu));
+      B200_TRY(h_nrm2(nw, nw->JTfu, &g));
+      nw->trust_region = nw->tp1 * g;
+    }
   }
   if (o.descent == B200_DESCENT_PSEUDO_TRANSIENT) {  // SwitchedEvolutionRelaxationCache init / reinit! (pseudo_transient.jl:105-130)
     nw->alpha_inv = 1.0 / (o.pt_alpha_initial > 0 ? o.pt_alpha_initial : 1.0e-3);
@@ -247,10 +267,11 @@ static int32_t newton_step_inner(b200_newton* nw) {
   const double Bv = 8.0 * (double)n;
   const bool tr_on = o.globalization == B200_GLOBALIZATION_TRUST_REGION;
   const bool krylov = o.linsolve != B200_LINSOLVE_DENSE_LU;
-  const double step_thr = o.tr_step_threshold > 0 ? o.tr_step_threshold : 1.0 / 10000;
-  const double shrink_thr = o.tr_shrink_threshold > 0 ? o.tr_shrink_threshold : 0.25;
-  const double expand_thr = o.tr_expand_threshold > 0 ? o.tr_expand_threshold : 0.75;
-  const double shrink_fac = o.tr_shrink_factor > 0 ? o.tr_shrink_factor : 0.25;
+  const int sch = o.tr_scheme;  // per-scheme defaults  trust_region.jl:348-381
+  const double step_thr = o.tr_step_threshold > 0 ? o.tr_step_threshold : (sch == B200_TR_HEI ? 0.0 : sch == B200_TR_YUAN ? 1.0 / 1000 : 1.0 / 10000);
+  const double shrink_thr = o.tr_shrink_threshold > 0 ? o.tr_shrink_threshold : (sch == B200_TR_HEI ? 0.0 : sch == B200_TR_NLSOLVE ? 1.0 / 20 : 0.25);
+  const double expand_thr = o.tr_expand_threshold > 0 ? o.tr_expand_threshold : (sch == B200_TR_NLSOLVE ? 0.9 : sch == B200_TR_HEI ? 0.0 : 0.75);
+  const double shrink_fac = o.tr_shrink_factor > 0 ? o.tr_shrink_factor : (sch == B200_TR_NLSOLVE ? 0.5 : sch == B200_TR_HEI ? 0.0 : 0.25);
   const double expand_fac = o.tr_expand_factor > 0 ? o.tr_expand_factor : 2.0;
   const int max_shrink = o.max_shrink_times > 0 ? o.max_shrink_times : 32;
 
@@ -452,11 +473,44 @@ static int32_t newton_step_inner(b200_newton* nw) {
       const double denom = dg + dJJd / 2.0;
       const double rho = num / denom;
       accepted = rho > step_thr;
-      if (rho < shrink_thr) { nw->trust_region *= shrink_fac; nw->shrink_counter += 1; }
-      else { nw->shrink_counter = 0; if (rho > expand_thr && rho > step_thr) nw->trust_region = expand_fac * nw->trust_region; }
+      double dun;  // internalnorm(du)
+      B200_TRY(h_nrm2(nw, nw->du, &dun));
+      double& tr = nw->trust_region;
+      if (sch == B200_TR_SIMPLE) {  // trust_region.jl:431-440
+        if (rho < shrink_thr) { tr *= shrink_fac; nw->shrink_counter += 1; }
+        else { nw->shrink_counter = 0; if (rho > expand_thr && rho > step_thr) tr = expand_fac * tr; }
+      } else if (sch == B200_TR_NLSOLVE) {  // :441-455
+        if (rho < shrink_thr) { tr *= shrink_fac; nw->shrink_counter += 1; }
+        else {
+          nw->shrink_counter = 0;
+          if (rho >= expand_thr) tr = expand_fac * dun;
+          else if (rho >= nw->tp1) tr = std::max(tr, expand_fac * dun);
+        }
+      } else if (sch == B200_TR_NOCEDAL_WRIGHT) {  // :456-466
+        if (rho < shrink_thr) { tr = shrink_fac * dun; nw->shrink_counter += 1; }
+        else { nw->shrink_counter = 0; if (rho > expand_thr && fabs(dun - tr) < 1.0e-6 * tr) tr = expand_fac * tr; }
+      } else if (sch == B200_TR_HEI) {  // :467-476, rfunc_adaptive_trust_region :383-391
+        const double M = nw->tp1, g1 = nw->tp3, g2 = nw->tp4, beta = nw->tp2;
+        const double rf = (rho >= shrink_thr) ? (2.0 * (M - 1.0 - g2) * atan(rho - shrink_thr) + (1.0 + g2)) / M_PI
+                                              : (1.0 - g1 - beta) * (exp(rho - shrink_thr) + beta / (1.0 - g1 - beta));
+        const double tr_new = rf * dun;
+        if (tr_new < tr) nw->shrink_counter += 1; else nw->shrink_counter = 0;
+        tr = tr_new;
+      } else if (sch == B200_TR_YUAN) {  // :477-490
+        if (rho < shrink_thr) { nw->tp1 = nw->tp2 * nw->tp1; nw->shrink_counter += 1; }
+        else { if (rho >= expand_thr && 2.0 * dun > tr) nw->tp1 = nw->tp3 * nw->tp1; nw->shrink_counter = 0; }
+        double g;
+        B200_TRY(b200_vjp(nw->prob, nw->u_trial, nw->fu_trial, nw->JTfu));
+        B200_TRY(h_nrm2(nw, nw->JTfu, &g));
+        tr = nw->tp1 * g;
+      } else if (sch == B200_TR_FAN) {  // :491-499
+        if (rho < shrink_thr) { nw->tp1 *= nw->tp2; nw->shrink_counter += 1; }
+        else { nw->shrink_counter = 0; if (rho > expand_thr) nw->tp1 = std::min(nw->tp1 * nw->tp3, nw->tp4); }
+        tr = nw->tp1 * pow(nt, 0.99);
+      }
       nw->trust_region = std::min(nw->trust_region, nw->max_tr);
       if (accepted) {
-        B200_TRY(h_nrm2(nw, nw->du, &du_norm));
+        du_norm = dun;
         std::swap(nw->u, nw->u_trial);      // copyto!(cache.u, u_new) as a pointer swap
         std::swap(nw->fu, nw->fu_trial);
         nw->op.u = nw->u;

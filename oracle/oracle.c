@@ -820,17 +820,31 @@ void orc_newton_solve(const orc_problem* p, const double* u0, const b200_newton_
 
   /* trust region init (trust_region.jl:204-258, 330-346): Simple scheme */
   double trust_region = 0, max_tr = 0; int shrink_counter = 0;
-  const double step_thr = o->tr_step_threshold > 0 ? o->tr_step_threshold : 1.0 / 10000;
-  const double shrink_thr = o->tr_shrink_threshold > 0 ? o->tr_shrink_threshold : 0.25;
-  const double expand_thr = o->tr_expand_threshold > 0 ? o->tr_expand_threshold : 0.75;
-  const double shrink_fac = o->tr_shrink_factor > 0 ? o->tr_shrink_factor : 0.25;
+  /* per-scheme defaults: trust_region.jl:330-384 (a value of 0 means "default", :320-328) */
+  const int sch = o->tr_scheme;
+  const double step_thr = o->tr_step_threshold > 0 ? o->tr_step_threshold : (sch == B200_TR_HEI ? 0.0 : sch == B200_TR_YUAN ? 1.0 / 1000 : 1.0 / 10000);
+  const double shrink_thr = o->tr_shrink_threshold > 0 ? o->tr_shrink_threshold : (sch == B200_TR_HEI ? 0.0 : sch == B200_TR_NLSOLVE ? 1.0 / 20 : 0.25);
+  const double expand_thr = o->tr_expand_threshold > 0 ? o->tr_expand_threshold : (sch == B200_TR_NLSOLVE ? 0.9 : sch == B200_TR_HEI ? 0.0 : 0.75);
+  const double shrink_fac = o->tr_shrink_factor > 0 ? o->tr_shrink_factor : (sch == B200_TR_NLSOLVE ? 0.5 : sch == B200_TR_HEI ? 0.0 : 0.25);
   const double expand_fac = o->tr_expand_factor > 0 ? o->tr_expand_factor : 2.0;
   const int max_shrink = o->max_shrink_times > 0 ? o->max_shrink_times : 32;
+  /* get_parameters  trust_region.jl:372-379 */
+  double tp1 = 0, tp2 = 0, tp3 = 0, tp4 = 0;
+  if (sch == B200_TR_NLSOLVE) { tp1 = 0.5; }
+  else if (sch == B200_TR_HEI) { tp1 = 5.0; tp2 = 0.1; tp3 = 0.15; tp4 = 0.15; }
+  else if (sch == B200_TR_YUAN) { tp1 = 2.0; tp2 = 1.0 / 6; tp3 = 6.0; }
+  else if (sch == B200_TR_FAN) { tp1 = 0.1; tp2 = 0.25; tp3 = 12.0; tp4 = 1.0e18; }
   if (tr_on) {
-    double fu_norm = v_nrm2(n, fu), umin = INFINITY, umax = -INFINITY;
+    double fu_norm = v_nrm2(n, fu), u0_norm = v_nrm2(n, u), umin = INFINITY, umax = -INFINITY;
     for (int64_t i = 0; i < n; ++i) { if (u[i] < umin) umin = u[i]; if (u[i] > umax) umax = u[i]; }
-    max_tr = o->tr_max_trust_radius > 0 ? o->tr_max_trust_radius : fmax(fu_norm, umax - umin);
-    trust_region = o->tr_initial_trust_radius > 0 ? o->tr_initial_trust_radius : max_tr / 11.0;
+    if (o->tr_max_trust_radius > 0) max_tr = o->tr_max_trust_radius;
+    else max_tr = (sch == B200_TR_SIMPLE || sch == B200_TR_NOCEDAL_WRIGHT) ? fmax(fu_norm, umax - umin) : INFINITY; /* :330-337 */
+    if (o->tr_initial_trust_radius > 0) trust_region = o->tr_initial_trust_radius;
+    else if (sch == B200_TR_NLSOLVE) trust_region = u0_norm > 0 ? u0_norm : 1.0; /* :339-346 */
+    else if (sch == B200_TR_HEI) trust_region = 1.0;
+    else if (sch == B200_TR_FAN) trust_region = pow(fu_norm, 0.99) / 10.0;
+    else trust_region = max_tr / 11.0;
+    if (sch == B200_TR_YUAN) { orc_vjp(p, u, fu, JTfu); trust_region = tp1 * v_nrm2(n, JTfu); } /* :232-234 */
   }
   /* PseudoTransient = DampedNewtonDescent + SwitchedEvolutionRelaxation (pseudo_transient.jl:37-56, 105-170;
      descent/damped_newton.jl:290-296 `:simple` mode): solve (J + alpha^-1 I) x = fu, du = -x;
@@ -981,8 +995,36 @@ void orc_newton_solve(const orc_problem* p, const double* u0, const b200_newton_
       double denom = v_dot(n, du, JTfu) + dJJd / 2.0;
       double rho = num / denom;
       accepted = rho > step_thr;
-      if (rho < shrink_thr) { trust_region *= shrink_fac; shrink_counter += 1; }
-      else { shrink_counter = 0; if (rho > expand_thr && rho > step_thr) trust_region = expand_fac * trust_region; }
+      const double dun = v_nrm2(n, du); /* internalnorm(du) */
+      if (sch == B200_TR_SIMPLE) { /* trust_region.jl:431-440 */
+        if (rho < shrink_thr) { trust_region *= shrink_fac; shrink_counter += 1; }
+        else { shrink_counter = 0; if (rho > expand_thr && rho > step_thr) trust_region = expand_fac * trust_region; }
+      } else if (sch == B200_TR_NLSOLVE) { /* :441-455 */
+        if (rho < shrink_thr) { trust_region *= shrink_fac; shrink_counter += 1; }
+        else {
+          shrink_counter = 0;
+          if (rho >= expand_thr) trust_region = expand_fac * dun;
+          else if (rho >= tp1) trust_region = fmax(trust_region, expand_fac * dun);
+        }
+      } else if (sch == B200_TR_NOCEDAL_WRIGHT) { /* :456-466 */
+        if (rho < shrink_thr) { trust_region = shrink_fac * dun; shrink_counter += 1; }
+        else { shrink_counter = 0; if (rho > expand_thr && fabs(dun - trust_region) < 1.0e-6 * trust_region) trust_region = expand_fac * trust_region; }
+      } else if (sch == B200_TR_HEI) { /* :467-476 with rfunc_adaptive_trust_region :383-391 (r, c2, M, g1, g2, beta) = (rho, shrink_thr, p1, p3, p4, p2) */
+        const double r = rho, c2_ = shrink_thr, M = tp1, g1 = tp3, g2 = tp4, beta = tp2;
+        const double rf = (r >= c2_) ? (2.0 * (M - 1.0 - g2) * atan(r - c2_) + (1.0 + g2)) / M_PI : (1.0 - g1 - beta) * (exp(r - c2_) + beta / (1.0 - g1 - beta));
+        const double tr_new = rf * dun;
+        if (tr_new < trust_region) shrink_counter += 1; else shrink_counter = 0;
+        trust_region = tr_new;
+      } else if (sch == B200_TR_YUAN) { /* :477-490 */
+        if (rho < shrink_thr) { tp1 = tp2 * tp1; shrink_counter += 1; }
+        else { if (rho >= expand_thr && 2.0 * dun > trust_region) tp1 = tp3 * tp1; shrink_counter = 0; }
+        orc_vjp(p, u_trial, fu_trial, JTfu);
+        trust_region = tp1 * v_nrm2(n, JTfu);
+      } else if (sch == B200_TR_FAN) { /* :491-499 */
+        if (rho < shrink_thr) { tp1 *= tp2; shrink_counter += 1; }
+        else { shrink_counter = 0; if (rho > expand_thr) tp1 = fmin(tp1 * tp3, tp4); }
+        trust_region = tp1 * pow(nt, 0.99);
+      }
       if (trust_region > max_tr) trust_region = max_tr;
       if (accepted) { v_copy(n, u_trial, u); v_copy(n, fu_trial, fu); }
       else make_new_jacobian = 0;

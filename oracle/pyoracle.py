@@ -19,6 +19,7 @@ LINSOLVE_GMRES, LINSOLVE_DENSE_LU, LINSOLVE_SPARSE_GMRES = 0, 1, 2
 JVP_EXACT, JVP_FINITE_DIFF = 0, 1
 GLOB_NONE, GLOB_TRUST_REGION, GLOB_LINESEARCH = 0, 1, 2
 DESCENT_NEWTON, DESCENT_PSEUDO_TRANSIENT = 0, 1
+TR_SIMPLE, TR_NLSOLVE, TR_NOCEDAL_WRIGHT, TR_HEI, TR_YUAN, TR_FAN = range(6)
 FORCING_NONE, FORCING_EW2 = 0, 1
 TERM_ABS_NORM_SAFE_BEST, TERM_ABS_NORM, TERM_ABS_NORM_SAFE = 0, 1, 2
 RC_SUCCESS, RC_MAXITERS, RC_STALLED = 1, 2, 4
@@ -47,7 +48,7 @@ class NewtonOpts(C.Structure):
                 ("tr_step_threshold", C.c_double), ("tr_shrink_threshold", C.c_double), ("tr_expand_threshold", C.c_double),
                 ("tr_shrink_factor", C.c_double), ("tr_expand_factor", C.c_double), ("tr_max_trust_radius", C.c_double),
                 ("tr_initial_trust_radius", C.c_double), ("ls_c1", C.c_double), ("ls_rho_hi", C.c_double), ("ls_rho_lo", C.c_double),
-                ("ls_maxiters", C.c_int32), ("precond", C.c_int32), ("descent", C.c_int32), ("reserved0", C.c_int32),
+                ("ls_maxiters", C.c_int32), ("precond", C.c_int32), ("descent", C.c_int32), ("tr_scheme", C.c_int32),
                 ("pt_alpha_initial", C.c_double)]
 
 
