@@ -14,12 +14,16 @@
  *   - core_tests__item3.jl:40-58       JVP/VJP vs analytic Jacobian, atol 1e-5
  *   - operator_jacobian.jl:17-30       linear tridiagonal, sol.u ~ W\b
  *   - core_tests__item6.jl:14-20       ensemble: all successful retcodes
+ *   - rootfind_tests__item5.jl:29-33   PseudoTransient(alpha_initial = 10) on u.*u .- 2, err < 1e-9
+ *   - rootfind tests over RadiusUpdateSchemes: every scheme solves u.*u .- 2 to err < 1e-9
  * and against an independent NumPy/SciPy restatement (tests/golden/make_golden.py, fixtures in
  * tests/golden/).  GMRES iteration counts, Hessenberg entries, sparsity index arrays, colour
  * vectors and NLStats on the Brusselator are **parity unpinned** in the reference itself (no
  * reference test reads them); for those the oracle restates the published algorithms of
  * Krylov.jl (gmres.jl: MGS Arnoldi + Givens reflections, no restart) and SparseMatrixColorings
  * 0.4 (GreedyColoringAlgorithm(LargestFirst()), column colouring) and IS the parity target.
+ * Also unpinned (external packages, no version recorded): LineSearch.jl / LineSearches.jl BackTracking (cubic
+ * interpolation) behind `linesearch = BackTracking()`; Krylov.jl's left / right preconditioning (M, N with ldiv = false).
  */
 #ifndef ORACLE_H
 #define ORACLE_H
