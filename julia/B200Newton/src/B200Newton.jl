@@ -280,11 +280,17 @@ nsolve, nsteps), original)`, as the wrapper algorithms in the reference do (ext/
 """
 Base.@kwdef struct B200NewtonKrylov <: NonlinearSolveBase.AbstractNonlinearSolveAlgorithm
     problem::Problem
-    linsolve::Symbol = :gmres
-    globalization::Symbol = :none
-    forcing::Bool = false
+    linsolve::Symbol = :gmres            # :gmres | :dense_lu | :sparse_gmres
+    globalization::Symbol = :none        # :none | :trust_region | :linesearch (BackTracking)
+    radius_update_scheme::Symbol = :simple  # :simple | :nlsolve | :nocedal_wright | :hei | :yuan | :fan
+    descent::Symbol = :newton            # :newton | :pseudo_transient
+    alpha_initial::Float64 = 1.0e-3      # PseudoTransient(alpha_initial)
+    forcing::Bool = false                # EisenstatWalkerForcing2()
+    precs::Symbol = :none                # :none | :block_jacobi_left | :block_jacobi_right
     orth::Symbol = :cgs2
 end
+
+const _TR_SCHEMES = (simple = 0, nlsolve = 1, nocedal_wright = 2, hei = 3, yuan = 4, fan = 5)
 
 function SciMLBase.__solve(prob::SciMLBase.NonlinearProblem, alg::B200NewtonKrylov, args...;
         abstol = nothing, reltol = nothing, maxiters = 1000, kwargs...)
@@ -293,9 +299,13 @@ function SciMLBase.__solve(prob::SciMLBase.NonlinearProblem, alg::B200NewtonKryl
     g = o.gmres
     g = GmresOpts(g.memory, g.restart, g.itmax, alg.orth === :mgs ? 0 : alg.orth === :cgs ? 1 : 2, g.warm_start, g.engine, g.check_every, 0, 0.0, 0.0)
     o = NewtonOpts(something(abstol, 0.0), something(reltol, 0.0), maxiters,
-        alg.linsolve === :gmres ? 0 : alg.linsolve === :dense_lu ? 1 : 2, 0, alg.globalization === :trust_region ? 1 : 0,
-        alg.forcing ? 1 : 0, 0, 0, 1, g, o.ew_eta0, o.ew_eta_max, o.ew_gamma, o.ew_alpha, o.ew_safeguard_threshold, o.ew_safeguard,
-        o.max_shrink_times, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, Int32(0), Int32(0))
+        alg.linsolve === :gmres ? 0 : alg.linsolve === :dense_lu ? 1 : 2, o.jvp_mode,
+        alg.globalization === :trust_region ? 1 : alg.globalization === :linesearch ? 2 : 0,
+        alg.forcing ? 1 : 0, o.termination, 0, 1, g, o.ew_eta0, o.ew_eta_max, o.ew_gamma, o.ew_alpha, o.ew_safeguard_threshold, o.ew_safeguard,
+        o.max_shrink_times, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0,      # tr_* : scheme defaults
+        0.0, 0.0, 0.0, Int32(0),                                    # ls_* : BackTracking defaults
+        Int32(alg.precs === :block_jacobi_left ? 1 : alg.precs === :block_jacobi_right ? 2 : 0),
+        Int32(alg.descent === :pseudo_transient ? 1 : 0), Int32(getfield(_TR_SCHEMES, alg.radius_update_scheme)), alg.alpha_initial)
     nw = Ref{Ptr{Cvoid}}(C_NULL)
     check(ctx.handle, @ccall libb200.b200_newton_create(dp.handle::Ptr{Cvoid}, Ref(o)::Ref{NewtonOpts}, nw::Ref{Ptr{Cvoid}})::Int32)
     try
