@@ -109,6 +109,9 @@ typedef struct b200_ensemble b200_ensemble;
 typedef int32_t (*b200_residual_cb)(void* user, const double* u, double* du);
 typedef int32_t (*b200_jvp_cb)(void* user, const double* u, const double* v, double* Jv);
 typedef int32_t (*b200_matvec_cb)(void* user, const double* x, double* y);
+/* b3 plug-in point `jac = jac!` (jacobian.jl:241-243): fills the concrete Jacobian in place — J is the dense column-major
+   n x n matrix (ld = n) for the dense path, or the nzval array of the CSC pattern given to b200_sparse_jac_create */
+typedef int32_t (*b200_jac_cb)(void* user, const double* u, double* J);
 
 /* ---------------------------------------------------------------- option / result structs */
 typedef struct b200_gmres_opts {
@@ -242,6 +245,11 @@ int32_t b200_problem_create_quadratic(b200_ctx* ctx, int64_t n, double p, b200_p
 int32_t b200_problem_create_tridiag_quad(b200_ctx* ctx, int64_t n, const double* p_dev, b200_problem** prob); /* rootfind_tests__item20.jl */
 int32_t b200_problem_create_callback(b200_ctx* ctx, int64_t n, b200_residual_cb f, b200_jvp_cb jvp, b200_jvp_cb vjp,
                                      void* user, b200_problem** prob);
+/* user Jacobian fills (either may be NULL): used by b200_dense_jac_fill / b200_sparse_jac_fill instead of JVP sweeps */
+int32_t b200_problem_set_jac(b200_problem* prob, b200_jac_cb jac_dense, b200_jac_cb jac_nzval);
+/* `jac_prototype = J0::SparseMatrixCSC` for problems without a built-in pattern (jacobian.jl:119-125): the structure that
+   b200_pattern(_nnz) — and therefore the sparse path of the Newton driver — report for this problem.  Copied. */
+int32_t b200_problem_set_jac_prototype(b200_problem* prob, const int64_t* colptr, const int64_t* rowval, int32_t index_base);
 int32_t b200_problem_destroy(b200_problem* prob);
 int32_t b200_problem_n(b200_problem* prob, int64_t* n);
 int32_t b200_problem_set_AB(b200_problem* prob, double A, double B);     /* remake(prob; p = ...) */

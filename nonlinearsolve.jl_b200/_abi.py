@@ -77,6 +77,7 @@ class EnsResult(C.Structure):
 RESIDUAL_CB = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p)
 JVP_CB = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p)
 MATVEC_CB = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p)
+JAC_CB = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p)
 
 P = C.c_void_p
 PP = C.POINTER(C.c_void_p)
@@ -123,6 +124,8 @@ SIGNATURES = {
     "b200_problem_create_quadratic": (I32, [P, I64, F64, PP]),
     "b200_problem_create_tridiag_quad": (I32, [P, I64, P, PP]),
     "b200_problem_create_callback": (I32, [P, I64, RESIDUAL_CB, JVP_CB, JVP_CB, P, PP]),
+    "b200_problem_set_jac": (I32, [P, JAC_CB, JAC_CB]),
+    "b200_problem_set_jac_prototype": (I32, [P, P, P, I32]),
     "b200_problem_destroy": (I32, [P]),
     "b200_problem_n": (I32, [P, PI64]),
     "b200_problem_set_AB": (I32, [P, F64, F64]),

@@ -307,8 +307,11 @@ class NonlinearFunction:
     its work on the context's stream or finish before returning.  `jvp(Jv, v, u, p)`, `vjp(Jtw, w, u, p)` likewise.
     """
 
-    def __init__(self, f, jvp=None, vjp=None, sparsity=None, jac_prototype=None, colorvec=None, n=None):
+    def __init__(self, f, jvp=None, vjp=None, sparsity=None, jac_prototype=None, colorvec=None, n=None, jac=None):
         self.f, self.jvp, self.vjp = f, jvp, vjp
+        # jac(J, u, p): fills the concrete Jacobian in place (b3; jacobian.jl:241-243).  J arrives as a DeviceVector over the
+        # dense column-major n*n matrix, or over `nzval` when jac_prototype = (colptr, rowval) describes a CSC pattern.
+        self.jac = jac
         self.sparsity, self.jac_prototype, self.colorvec = sparsity, jac_prototype, colorvec
         self._n = n
 
@@ -586,6 +589,29 @@ class _DeviceProblem:
             self._jvp_cb = abi.JVP_CB(jvp_cb) if f.jvp is not None else C.cast(None, abi.JVP_CB)
             self._vjp_cb = abi.JVP_CB(vjp_cb) if f.vjp is not None else C.cast(None, abi.JVP_CB)
             check(ctx.handle, L.b200_problem_create_callback(ctx.handle, n, self._f_cb, self._jvp_cb, self._vjp_cb, None, C.byref(self._h)))
+        self._jac_cb = None
+        if isinstance(f.jac_prototype, tuple):  # jac_prototype = (colptr, rowval[, index_base]) : CSC structure of J0
+            cp = np.ascontiguousarray(f.jac_prototype[0], dtype=np.int64)
+            rv = np.ascontiguousarray(f.jac_prototype[1], dtype=np.int64)
+            base = int(f.jac_prototype[2]) if len(f.jac_prototype) > 2 else 1
+            check(ctx.handle, L.b200_problem_set_jac_prototype(self._h, cp.ctypes.data_as(C.c_void_p), rv.ctypes.data_as(C.c_void_p), base))
+        if f.jac is not None:
+            sparse_proto = f.jac_prototype is not None or f.sparsity is not None
+            pp_, n_ = prob.p, self.n
+
+            def jac_cb(user, u, J):
+                try:
+                    cnt = self._jac_len if sparse_proto else n_ * n_
+                    f.jac(DeviceVector(ctx, cnt, np.float64, ptr=J), DeviceVector(ctx, n_, np.float64, ptr=u), pp_)
+                    return 0
+                except Exception:  # noqa: BLE001 - no exception may cross the ABI
+                    import traceback
+                    traceback.print_exc()
+                    return 1
+            self._jac_len = len(f.jac_prototype[1]) if isinstance(f.jac_prototype, tuple) else 0
+            self._jac_cb = abi.JAC_CB(jac_cb)
+            null = C.cast(None, abi.JAC_CB)
+            check(ctx.handle, L.b200_problem_set_jac(self._h, null if sparse_proto else self._jac_cb, self._jac_cb if sparse_proto else null))
         self._fin = ctx._adopt(weakref.finalize(self, L.b200_problem_destroy, self._h))
 
     @property

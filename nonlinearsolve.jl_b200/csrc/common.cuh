@@ -136,8 +136,10 @@ struct b200_problem {
   const double* pvec;  // device
   b200_residual_cb f_cb;
   b200_jvp_cb jvp_cb, vjp_cb;
+  b200_jac_cb jac_dense_cb, jac_nzval_cb;  // optional user jac! (b3)
   void* user;
   double* fd_scratch;  // n doubles, lazily allocated (callback finite differences)
+  int64_t *proto_colptr, *proto_rowval;  // host copy (0-based) of a user jac_prototype pattern, or null
 };
 
 struct b200_sparse_jac;

@@ -338,11 +338,32 @@ int32_t b200_problem_create_callback(b200_ctx* ctx, int64_t n, b200_residual_cb 
   (*prob)->user = user;
   return B200_OK;
 }
+int32_t b200_problem_set_jac(b200_problem* prob, b200_jac_cb jac_dense, b200_jac_cb jac_nzval) {
+  prob->jac_dense_cb = jac_dense;
+  prob->jac_nzval_cb = jac_nzval;
+  return B200_OK;
+}
+int32_t b200_problem_set_jac_prototype(b200_problem* prob, const int64_t* colptr, const int64_t* rowval, int32_t index_base) {
+  b200_ctx* ctx = prob->ctx;
+  B200_REQUIRE(ctx, colptr && rowval && (index_base == 0 || index_base == 1), "set_jac_prototype: bad arguments");
+  const int64_t n = prob->n, nnz = colptr[n] - index_base;
+  B200_REQUIRE(ctx, nnz >= 0 && colptr[0] == index_base, "set_jac_prototype: malformed column pointers");
+  free(prob->proto_colptr); free(prob->proto_rowval);
+  prob->proto_colptr = (int64_t*)malloc(sizeof(int64_t) * (n + 1));
+  prob->proto_rowval = (int64_t*)malloc(sizeof(int64_t) * (nnz > 0 ? nnz : 1));
+  for (int64_t c = 0; c <= n; ++c) prob->proto_colptr[c] = colptr[c] - index_base;
+  for (int64_t e = 0; e < nnz; ++e) {
+    prob->proto_rowval[e] = rowval[e] - index_base;
+    if (prob->proto_rowval[e] < 0 || prob->proto_rowval[e] >= n) return ctx->fail(B200_ERR_INVALID, "set_jac_prototype: row index out of range", __FILE__, __LINE__);
+  }
+  return B200_OK;
+}
 int32_t b200_problem_destroy(b200_problem* p) {
   if (!p) return B200_OK;
   cudaStreamSynchronize(p->ctx->stream);
   if (p->kind != B200_PROB_CALLBACK && p->pvec) cudaFree(const_cast<double*>(p->pvec));
   if (p->fd_scratch) cudaFree(p->fd_scratch);
+  free(p->proto_colptr); free(p->proto_rowval);
   delete p;
   return B200_OK;
 }

@@ -98,6 +98,7 @@ void b200i_sparse_jac_csr(b200_sparse_jac* sj, const int64_t** rowptr, const int
 
 extern "C" {
 int32_t b200_pattern_nnz(b200_problem* p, int64_t* nnz) {
+  if (p->proto_colptr) { *nnz = p->proto_colptr[p->n]; return B200_OK; }  // user jac_prototype
   B200_REQUIRE(p->ctx, p->kind != B200_PROB_CALLBACK, "pattern: callback problems must bring their own jac_prototype");
   int64_t rows[16], total = 0;
   for (int64_t c = 0; c < p->n; ++c) total += column_rows(p, c, rows);
@@ -105,6 +106,11 @@ int32_t b200_pattern_nnz(b200_problem* p, int64_t* nnz) {
   return B200_OK;
 }
 int32_t b200_pattern(b200_problem* p, int32_t base, int64_t* colptr, int64_t* rowval) {
+  if (p->proto_colptr) {
+    for (int64_t c = 0; c <= p->n; ++c) colptr[c] = p->proto_colptr[c] + base;
+    for (int64_t e = 0; e < p->proto_colptr[p->n]; ++e) rowval[e] = p->proto_rowval[e] + base;
+    return B200_OK;
+  }
   B200_REQUIRE(p->ctx, p->kind != B200_PROB_CALLBACK, "pattern: callback problems must bring their own jac_prototype");
   int64_t rows[16], pos = 0;
   for (int64_t c = 0; c < p->n; ++c) {
@@ -212,6 +218,8 @@ int32_t b200_sparse_jac_create(b200_problem* prob, const int64_t* colptr, const 
 // DI.jacobian! with AutoSparse(AutoForwardDiff): one exact JVP per colour + decompression (jacobian.jl:244-247)
 int32_t b200_sparse_jac_fill(b200_sparse_jac* sj, const double* u, double* nzval) {
   b200_ctx* ctx = sj->ctx;
+  if (sj->prob->jac_nzval_cb)  // jac!(J::SparseMatrixCSC, u, p) writes nzval directly
+    return sj->prob->jac_nzval_cb(sj->prob->user, u, nzval) == 0 ? B200_OK : ctx->fail(B200_ERR_CALLBACK, "jac! callback failed", __FILE__, __LINE__);
   const int grid = (int)((sj->n + ST - 1) / ST);
   for (int32_t color = 1; color <= (int32_t)sj->ncolors; ++color) {
     LAUNCH(ctx, seed_kernel, grid, ST, 0, sj->n, (const int32_t*)sj->d_colors, color, sj->seed);
