@@ -104,7 +104,8 @@ typedef struct b200_sparse_jac b200_sparse_jac;
 typedef struct b200_ensemble b200_ensemble;
 
 /* host callbacks invoked between kernels (b1 plug-in point: an arbitrary Julia f!/jvp!/vjp! closure
- * through @cfunction).  Pointers are device pointers; work must be enqueued on the ctx stream
+ * through @cfunction).  Pointers are device pointers.  The library drains its own (non-blocking) streams before every
+ * callback, so the arguments are ready on any stream; the callback's own device work must be enqueued on the ctx stream
  * (b200_ctx_stream) or be complete on return.  Return 0 on success. */
 typedef int32_t (*b200_residual_cb)(void* user, const double* u, double* du);
 typedef int32_t (*b200_jvp_cb)(void* user, const double* u, const double* v, double* Jv);

@@ -164,6 +164,14 @@ struct b200_linop {
 enum { LINOP_PROBLEM = 0, LINOP_CSC = 1, LINOP_DENSE = 2, LINOP_CALLBACK = 3, LINOP_SPARSE_JAC = 4, LINOP_BLOCK_JACOBI = 5 };
 
 // internal (non-ABI) helpers implemented across the .cu files
+// Host callbacks run user device code on streams the library knows nothing about (its own stream is non-blocking): drain
+// everything the library has enqueued before handing control to the callback.  The callback in turn must have finished its
+// device work (or enqueued it on the context's stream) when it returns.
+static inline int32_t b200i_sync_for_callback(b200_ctx* ctx) {
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return B200_ERR_CUDA;
+  if (ctx->aux_stream && cudaStreamSynchronize(ctx->aux_stream) != cudaSuccess) return B200_ERR_CUDA;
+  return B200_OK;
+}
 int32_t b200i_linop_apply(b200_linop* op, const double* x, double* y);
 int32_t b200i_diag_shift(b200_ctx* ctx, int64_t n, double* A, int64_t ld, double shift);  // A[i,i] += shift
 void b200i_sparse_jac_csr(b200_sparse_jac* sj, const int64_t** rowptr, const int64_t** csr_col, const int64_t** csr_map);

@@ -407,6 +407,7 @@ int32_t b200_dense_jac_fill(b200_problem* p, const double* u, double* J, int64_t
   B200_REQUIRE(ctx, ld >= n, "dense_jac_fill: ld < n");
   if (p->jac_dense_cb) {  // jac!(J, u, p)   jacobian.jl:241-243
     B200_REQUIRE(ctx, ld == n, "dense_jac_fill: a user jac! fills a contiguous n x n matrix (ld must equal n)");
+    B200_TRY(b200i_sync_for_callback(ctx));
     return p->jac_dense_cb(p->user, u, J) == 0 ? B200_OK : ctx->fail(B200_ERR_CALLBACK, "jac! callback failed", __FILE__, __LINE__);
   }
   if (p->kind != B200_PROB_CALLBACK) CUDA_TRY(ctx, cudaMemsetAsync(J, 0, sizeof(double) * ld * n, ctx->stream));

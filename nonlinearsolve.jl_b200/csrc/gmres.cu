@@ -1195,6 +1195,7 @@ static int32_t linop_apply_unshifted(b200_linop* op, const double* x, double* y)
     case LINOP_DENSE:
       return b200_gemv(ctx, 0, op->n, op->n, op->A, op->ld, x, y);
     case LINOP_CALLBACK:
+      B200_TRY(b200i_sync_for_callback(ctx));
       return op->mv(op->user, x, y) == 0 ? B200_OK : ctx->fail(B200_ERR_CALLBACK, "matvec callback failed", __FILE__, __LINE__);
     case LINOP_SPARSE_JAC:
       return b200_spmv(op->sj, op->nzval, x, y);

@@ -395,6 +395,7 @@ int32_t b200_jvp(b200_problem* p, const double* u, const double* v, double* Jv) 
       CHECK_LAUNCH(ctx);
       return B200_OK;
     case B200_PROB_CALLBACK:
+      if (p->jvp_cb) B200_TRY(b200i_sync_for_callback(ctx));
       if (p->jvp_cb) return p->jvp_cb(p->user, u, v, Jv) == 0 ? B200_OK : ctx->fail(B200_ERR_CALLBACK, "jvp callback failed", __FILE__, __LINE__);
       return b200_jvp_fd(p, u, v, Jv);  // no jvp supplied: AutoFiniteDiff fallback (autodiff.jl:52-84 last resort)
   }
@@ -413,6 +414,7 @@ int32_t b200_vjp(b200_problem* p, const double* u, const double* w, double* JTw)
       CHECK_LAUNCH(ctx);
       return B200_OK;
     case B200_PROB_CALLBACK:
+      if (p->vjp_cb) B200_TRY(b200i_sync_for_callback(ctx));
       if (p->vjp_cb) return p->vjp_cb(p->user, u, w, JTw) == 0 ? B200_OK : ctx->fail(B200_ERR_CALLBACK, "vjp callback failed", __FILE__, __LINE__);
       return ctx->fail(B200_ERR_UNSUPPORTED, "callback problem has no vjp", __FILE__, __LINE__);
   }
@@ -461,6 +463,7 @@ int32_t b200i_residual_norm(b200_problem* p, const double* u, double* du, double
       CHECK_LAUNCH(ctx);
       return B200_OK;
     case B200_PROB_CALLBACK:
+      B200_TRY(b200i_sync_for_callback(ctx));
       if (p->f_cb(p->user, u, du) != 0) return ctx->fail(B200_ERR_CALLBACK, "residual callback failed", __FILE__, __LINE__);
       if (d_norminf) return b200i_reduce_sum_dev(ctx, p->n, du, nullptr, RED_MAXABS, d_norminf);
       return B200_OK;

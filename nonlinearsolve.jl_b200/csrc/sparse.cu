@@ -218,6 +218,7 @@ int32_t b200_sparse_jac_create(b200_problem* prob, const int64_t* colptr, const 
 // DI.jacobian! with AutoSparse(AutoForwardDiff): one exact JVP per colour + decompression (jacobian.jl:244-247)
 int32_t b200_sparse_jac_fill(b200_sparse_jac* sj, const double* u, double* nzval) {
   b200_ctx* ctx = sj->ctx;
+  if (sj->prob->jac_nzval_cb) B200_TRY(b200i_sync_for_callback(ctx));
   if (sj->prob->jac_nzval_cb)  // jac!(J::SparseMatrixCSC, u, p) writes nzval directly
     return sj->prob->jac_nzval_cb(sj->prob->user, u, nzval) == 0 ? B200_OK : ctx->fail(B200_ERR_CALLBACK, "jac! callback failed", __FILE__, __LINE__);
   const int grid = (int)((sj->n + ST - 1) / ST);

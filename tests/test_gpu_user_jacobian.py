@@ -68,18 +68,18 @@ def test_user_jac_and_jac_prototype(nls, ctx, po, golden):
 
     # (a) dense jac! + LU
     f1 = nls.NonlinearFunction(F, jvp=JVP, n=n, jac=counted(JAC_DENSE, "dense"))
-    s1 = nls.solve(nls.NonlinearProblem(f1, pv, None, ctx=ctx), nls.NewtonRaphson(), abstol=1e-10)
+    s1 = nls.solve(nls.NonlinearProblem(f1, pv, None, ctx=ctx), nls.NewtonRaphson(), abstol=1e-11)
     assert nls.successful_retcode(s1.retcode) and np.abs(s1.u - root).max() < 1e-8
     assert calls["dense"] == s1.stats.njacs - 1 and s1.stats.nfactors == s1.stats.nsteps   # jac! is what fills J (init call excluded)
     # (b) sparse jac! writing nzval of the user pattern, GMRES on the assembled matrix
     f2 = nls.NonlinearFunction(F, jvp=JVP, n=n, jac=counted(JAC_NZ, "nz"), jac_prototype=(colptr, rowval, 1))
-    s2 = nls.solve(nls.NonlinearProblem(f2, pv, None, ctx=ctx), nls.NewtonRaphson(linsolve=nls.KrylovJL_GMRES()), abstol=1e-10)
+    s2 = nls.solve(nls.NonlinearProblem(f2, pv, None, ctx=ctx), nls.NewtonRaphson(linsolve=nls.KrylovJL_GMRES()), abstol=1e-11)
     assert nls.successful_retcode(s2.retcode) and np.abs(s2.u - root).max() < 1e-8 and calls["nz"] == s2.stats.njacs
     # (c) user pattern only: colouring (3 colours for a tridiagonal matrix) + compressed JVP sweeps through the callback
     f3 = nls.NonlinearFunction(F, jvp=JVP, n=n, jac_prototype=(colptr, rowval, 1))
-    s3 = nls.solve(nls.NonlinearProblem(f3, pv, None, ctx=ctx), nls.NewtonRaphson(linsolve=nls.KrylovJL_GMRES()), abstol=1e-10)
+    s3 = nls.solve(nls.NonlinearProblem(f3, pv, None, ctx=ctx), nls.NewtonRaphson(linsolve=nls.KrylovJL_GMRES()), abstol=1e-11)
     assert nls.successful_retcode(s3.retcode) and np.abs(s3.u - root).max() < 1e-8 and s3.stats.njacs == s3.stats.nsteps
     # the three routes agree with each other and with the matrix-free solve
-    s0 = nls.solve(nls.NonlinearProblem(nls.NonlinearFunction(F, jvp=JVP, n=n), pv, None, ctx=ctx), nls.NewtonRaphson(linsolve=nls.KrylovJL_GMRES()), abstol=1e-10)
+    s0 = nls.solve(nls.NonlinearProblem(nls.NonlinearFunction(F, jvp=JVP, n=n), pv, None, ctx=ctx), nls.NewtonRaphson(linsolve=nls.KrylovJL_GMRES()), abstol=1e-11)
     for s in (s1, s2, s3):
         assert np.abs(s.u - s0.u).max() < 1e-8
