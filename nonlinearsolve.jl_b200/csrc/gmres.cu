@@ -809,18 +809,39 @@ struct R3Shared {
   uint64_t mbar[2];
   double redA[8], redC[8], gA[8], gC[8];
   long long acc[4], tl;  // debug phase timers (thread 0)
+#ifdef B200_R3_HAZARD_FREE
+  // racecheck-clean variant (profiles/README.md, "compute-sanitizer"): the prologue reduces through its own scratch and
+  // the poll scratch alternates with the step parity, so no write can meet a read of the previous step without a barrier
+  // in between.  Not the default until it has been timed: the 255-register allocation of this kernel moves with any edit.
+  double redPA[8], redPC[8], gA2[8], gC2[8];
+#endif
 };
+#ifdef B200_R3_HAZARD_FREE
+#define R3_GA(t) (((t) & 1) ? sh.gA2 : sh.gA)
+#define R3_GC(t) (((t) & 1) ? sh.gC2 : sh.gC)
+#else
+#define R3_GA(t) (sh.gA)
+#define R3_GC(t) (sh.gC)
+#endif
 
 // block reduction of (da, dc) over 8 warps; result valid in every lane of warp 0.  One __syncthreads.
-__device__ __forceinline__ void r3_reduce2(double& da, double& dc, R3Shared& sh) {
+__device__ __forceinline__ void r3_reduce2(double& da, double& dc, R3Shared& sh, bool prologue = false) {
   const int tid = threadIdx.x;
+#ifdef B200_R3_HAZARD_FREE
+  double* const ra = prologue ? sh.redPA : sh.redA;
+  double* const rc = prologue ? sh.redPC : sh.redC;
+#else
+  double* const ra = sh.redA;
+  double* const rc = sh.redC;
+  (void)prologue;
+#endif
   da = warp_sum(da);
   dc = warp_sum(dc);
-  if ((tid & 31) == 0) { sh.redA[tid >> 5] = da; sh.redC[tid >> 5] = dc; }
+  if ((tid & 31) == 0) { ra[tid >> 5] = da; rc[tid >> 5] = dc; }
   __syncthreads();
   if (tid < 32) {
-    da = (tid < R3_THREADS / 32) ? sh.redA[tid] : 0.0;
-    dc = (tid < R3_THREADS / 32) ? sh.redC[tid] : 0.0;
+    da = (tid < R3_THREADS / 32) ? ra[tid] : 0.0;
+    dc = (tid < R3_THREADS / 32) ? rc[tid] : 0.0;
     da = warp_sum(da);
     dc = warp_sum(dc);
   }
@@ -898,11 +919,13 @@ __device__ __forceinline__ void r3_step(const ResidentParams& P, R3Ctx& cx, R3Sh
     if (tid < 32) r3_post(P.slots + (size_t)((t + 1) & 3) * R3_BUF_WORDS, cx.b, da, dc, P.epoch_base + (unsigned)(t + 1) + 1u);
     R3_TICK(1);
   }
-  r3_poll(P.slots + (size_t)(t & 3) * R3_BUF_WORDS, cx.b, cx.G, P.epoch_base + (unsigned)t + 1u, P.err, sh.gA, sh.gC);
+  double* const ga = R3_GA(t);
+  double* const gc = R3_GC(t);
+  r3_poll(P.slots + (size_t)(t & 3) * R3_BUF_WORDS, cx.b, cx.G, P.epoch_base + (unsigned)t + 1u, P.err, ga, gc);
   __syncthreads();
   R3_TICK(2);
-  const double sa = ((sh.gA[0] + sh.gA[1]) + (sh.gA[2] + sh.gA[3])) + sh.gA[4];
-  const double scs = ((sh.gC[0] + sh.gC[1]) + (sh.gC[2] + sh.gC[3])) + sh.gC[4];
+  const double sa = ((ga[0] + ga[1]) + (ga[2] + ga[3])) + ga[4];
+  const double scs = ((gc[0] + gc[1]) + (gc[2] + gc[3])) + gc[4];
   const double h = sa - hprev * scs;
   hprev = h;
 #pragma unroll
@@ -1005,7 +1028,7 @@ __global__ void __launch_bounds__(R3_THREADS, 1) resident3_arnoldi_kernel(Reside
         da = fma(x.x, w[2 * q], da); da = fma(x.y, w[2 * q + 1], da);
       }
     }
-    r3_reduce2(da, dc, sh);
+    r3_reduce2(da, dc, sh, true);
     if (tid < 32) r3_post(P.slots, b, da, 0.0, P.epoch_base + 1u);
   }
   double hprev = 0.0;
@@ -1030,9 +1053,10 @@ __global__ void __launch_bounds__(R3_THREADS, 1) resident3_arnoldi_kernel(Reside
   __syncthreads();
   r3_reduce2(nacc, zero, sh);
   if (tid < 32) r3_post(P.slots + (size_t)(total & 3) * R3_BUF_WORDS, b, nacc, 0.0, P.epoch_base + (unsigned)total + 1u);
-  r3_poll(P.slots + (size_t)(total & 3) * R3_BUF_WORDS, b, G, P.epoch_base + (unsigned)total + 1u, P.err, sh.gA, sh.gC);
+  double* const gaf = R3_GA(total);
+  r3_poll(P.slots + (size_t)(total & 3) * R3_BUF_WORDS, b, G, P.epoch_base + (unsigned)total + 1u, P.err, gaf, R3_GC(total));
   __syncthreads();
-  const double hbis = sqrt(((sh.gA[0] + sh.gA[1]) + (sh.gA[2] + sh.gA[3])) + sh.gA[4]);
+  const double hbis = sqrt(((gaf[0] + gaf[1]) + (gaf[2] + gaf[3])) + gaf[4]);
   const double inv = hbis > 0.0 ? 1.0 / hbis : 0.0;
 #pragma unroll
   for (int q = 0; q < R3_RP; ++q) {
