@@ -6,7 +6,7 @@ Only what the hot path needs lives here: `csrc/` (hand-written sm_100a CUDA + th
 """
 from . import _abi as abi  # noqa: F401
 from .api import *  # noqa: F401,F403
-from .api import (Context, DeviceVector, default_context, ReturnCode, successful_retcode, NLStats, NonlinearSolution,  # noqa: F401
+from .api import (Context, DeviceVector, default_context, device_count, ReturnCode, successful_retcode, NLStats, NonlinearSolution,  # noqa: F401
                   Brusselator2D, Brusselator3D, QuadraticFunction, TridiagQuadFunction, NonlinearFunction, TracerSparsityDetector,
                   NonlinearProblem, remake, KrylovJL_GMRES, LUFactorization, AutoForwardDiff, AutoFiniteDiff, EisenstatWalkerForcing2, BackTracking, BlockJacobi, PseudoTransient, RadiusUpdateSchemes,
                   AbsNormSafeBestTerminationMode, AbsNormSafeTerminationMode, AbsNormTerminationMode, NewtonRaphson, TrustRegion,

@@ -123,6 +123,13 @@ class Context:
         return v
 
 
+def device_count():
+    """Number of CUDA devices the library sees (0 without a GPU; the library never falls back to the CPU)."""
+    n = C.c_int32(0)
+    lib().b200_device_count(C.byref(n))
+    return n.value
+
+
 _default_ctx = {}
 
 

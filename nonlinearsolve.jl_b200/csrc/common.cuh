@@ -45,6 +45,16 @@ struct b200_ctx {
     if ((ctx)->prof_on) (ctx)->prof_end();                                              \
   } while (0)
 
+// Every extern "C" entry that takes a context or a handle makes the context's device current first: allocations, kernel
+// launches and event records below it otherwise land on whichever device the calling thread used last (one process may hold
+// contexts on several GPUs; api.default_context(device), a Julia host with one task per device).  Not restored on return.
+#define B200_DEVICE_GUARD(ctxexpr)                                                      \
+  do {                                                                                  \
+    const b200_ctx* g__ = (ctxexpr);                                                    \
+    int d__ = -1;                                                                       \
+    if (g__ && (cudaGetDevice(&d__) != cudaSuccess || d__ != g__->device)) cudaSetDevice(g__->device); \
+  } while (0)
+
 #define B200_RED_MAX_BLOCKS 2048
 enum { RED_DOT = 0, RED_SUMSQ = 1, RED_MAXABS = 2, RED_DIFFSQ = 3, RED_MIN = 4, RED_MAX = 5, RED_NEQ = 6 };
 

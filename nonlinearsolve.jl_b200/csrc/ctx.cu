@@ -47,16 +47,19 @@ extern "C" {
 int32_t b200_version(void) { return B200_VERSION; }
 
 int32_t b200_ctx_profile_enable(b200_ctx* ctx, int32_t on) {
+  B200_DEVICE_GUARD(ctx);
   ctx->prof_collect();
   ctx->prof_on = on != 0;
   return B200_OK;
 }
 int32_t b200_ctx_profile_reset(b200_ctx* ctx) {
+  B200_DEVICE_GUARD(ctx);
   ctx->prof_collect();
   for (auto& s : ctx->prof) s = b200_ctx::ProfSlot();
   return B200_OK;
 }
 int32_t b200_ctx_profile_get(b200_ctx* ctx, int32_t kid, double* ms, double* bytes, int64_t* launches) {
+  B200_DEVICE_GUARD(ctx);
   if (kid < 0 || kid >= B200_KID_COUNT) return ctx->fail(B200_ERR_INVALID, "bad kernel id", __FILE__, __LINE__);
   ctx->prof_collect();
   if (ms) *ms = ctx->prof[kid].ms;
@@ -103,6 +106,7 @@ int32_t b200_ctx_create(int32_t device, void* stream, b200_ctx** out) {
 }
 
 int32_t b200_ctx_destroy(b200_ctx* ctx) {
+  B200_DEVICE_GUARD(ctx);
   if (!ctx) return B200_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
@@ -119,6 +123,7 @@ int32_t b200_ctx_destroy(b200_ctx* ctx) {
 }
 
 int32_t b200_ctx_sync(b200_ctx* ctx) {
+  B200_DEVICE_GUARD(ctx);
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return B200_OK;
 }
@@ -128,44 +133,53 @@ int32_t b200_ctx_kernel_launches(b200_ctx* ctx, int64_t* count) { *count = ctx->
 int32_t b200_ctx_sm_count(b200_ctx* ctx, int32_t* count) { *count = ctx->sm_count; return B200_OK; }
 
 int32_t b200_malloc(b200_ctx* ctx, size_t bytes, void** dptr) {
+  B200_DEVICE_GUARD(ctx);
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   cudaError_t e = cudaMalloc(dptr, bytes ? bytes : 8);
   if (e != cudaSuccess) { cudaGetLastError(); *dptr = nullptr; return ctx->fail(B200_ERR_NOMEM, "cudaMalloc failed", __FILE__, __LINE__); }
   return B200_OK;
 }
 int32_t b200_free(b200_ctx* ctx, void* dptr) {
+  B200_DEVICE_GUARD(ctx);
   if (!dptr) return B200_OK;
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   CUDA_TRY(ctx, cudaFree(dptr));
   return B200_OK;
 }
 int32_t b200_host_alloc(b200_ctx* ctx, size_t bytes, void** hptr) {
+  B200_DEVICE_GUARD(ctx);
   CUDA_TRY(ctx, cudaMallocHost(hptr, bytes ? bytes : 8));
   return B200_OK;
 }
 int32_t b200_host_free(b200_ctx* ctx, void* hptr) {
+  B200_DEVICE_GUARD(ctx);
   if (hptr) CUDA_TRY(ctx, cudaFreeHost(hptr));
   return B200_OK;
 }
 int32_t b200_memcpy_h2d(b200_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  B200_DEVICE_GUARD(ctx);
   CUDA_TRY(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return B200_OK;
 }
 int32_t b200_memcpy_d2h(b200_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  B200_DEVICE_GUARD(ctx);
   CUDA_TRY(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return B200_OK;
 }
 int32_t b200_memcpy_d2d(b200_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  B200_DEVICE_GUARD(ctx);
   CUDA_TRY(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
   return B200_OK;
 }
 int32_t b200_memset(b200_ctx* ctx, void* dst, int32_t byte, size_t bytes) {
+  B200_DEVICE_GUARD(ctx);
   CUDA_TRY(ctx, cudaMemsetAsync(dst, byte, bytes, ctx->stream));
   return B200_OK;
 }
 int32_t b200_flush_l2(b200_ctx* ctx) {
+  B200_DEVICE_GUARD(ctx);
   if (!ctx->l2_flush) {
     ctx->l2_flush_bytes = ctx->l2_bytes ? 2 * ctx->l2_bytes : (size_t)256 << 20;
     CUDA_TRY(ctx, cudaMalloc(&ctx->l2_flush, ctx->l2_flush_bytes));
@@ -313,60 +327,71 @@ int32_t b200i_axpy_norm(b200_ctx* ctx, int64_t n, double a, const double* x, dou
 
 extern "C" {
 int32_t b200_fill(b200_ctx* ctx, int64_t n, double a, double* x) {
+  B200_DEVICE_GUARD(ctx);
   LAUNCH(ctx, (ew_kernel<EW_FILL>), ew_grid(ctx, n), EW_THREADS, 0, n, a, 0.0, nullptr, nullptr, x);
   CHECK_LAUNCH(ctx);
   return B200_OK;
 }
 int32_t b200_copy(b200_ctx* ctx, int64_t n, const double* x, double* y) {
+  B200_DEVICE_GUARD(ctx);
   LAUNCH(ctx, (ew_kernel<EW_COPY>), ew_grid(ctx, n), EW_THREADS, 0, n, 0.0, 0.0, x, nullptr, y);
   CHECK_LAUNCH(ctx);
   return B200_OK;
 }
 int32_t b200_scal(b200_ctx* ctx, int64_t n, double a, double* x) {
+  B200_DEVICE_GUARD(ctx);
   LAUNCH(ctx, (ew_kernel<EW_SCAL>), ew_grid(ctx, n), EW_THREADS, 0, n, a, 0.0, nullptr, nullptr, x);
   CHECK_LAUNCH(ctx);
   return B200_OK;
 }
 int32_t b200_axpy(b200_ctx* ctx, int64_t n, double a, const double* x, double* y) {
+  B200_DEVICE_GUARD(ctx);
   LAUNCH(ctx, (ew_kernel<EW_AXPY>), ew_grid(ctx, n), EW_THREADS, 0, n, a, 0.0, x, nullptr, y);
   CHECK_LAUNCH(ctx);
   return B200_OK;
 }
 int32_t b200_axpby(b200_ctx* ctx, int64_t n, double a, const double* x, double b, double* y) {
+  B200_DEVICE_GUARD(ctx);
   LAUNCH(ctx, (ew_kernel<EW_AXPBY>), ew_grid(ctx, n), EW_THREADS, 0, n, a, b, x, nullptr, y);
   CHECK_LAUNCH(ctx);
   return B200_OK;
 }
 int32_t b200_mul(b200_ctx* ctx, int64_t n, const double* x, const double* y, double* z) {
+  B200_DEVICE_GUARD(ctx);
   LAUNCH(ctx, (ew_kernel<EW_MUL>), ew_grid(ctx, n), EW_THREADS, 0, n, 0.0, 0.0, x, y, z);
   CHECK_LAUNCH(ctx);
   return B200_OK;
 }
 int32_t b200_dot(b200_ctx* ctx, int64_t n, const double* x, const double* y, double* out_host) {
+  B200_DEVICE_GUARD(ctx);
   B200_TRY(b200i_reduce_sum_dev(ctx, n, x, y, RED_DOT, ctx->d_scalars));
   B200_TRY(b200i_fetch_scalars(ctx, 1));
   *out_host = ctx->h_scalars[0];
   return B200_OK;
 }
 int32_t b200_nrm2(b200_ctx* ctx, int64_t n, const double* x, double* out_host) {
+  B200_DEVICE_GUARD(ctx);
   B200_TRY(b200i_reduce_sum_dev(ctx, n, x, nullptr, RED_SUMSQ, ctx->d_scalars));
   B200_TRY(b200i_fetch_scalars(ctx, 1));
   *out_host = sqrt(ctx->h_scalars[0]);
   return B200_OK;
 }
 int32_t b200_norminf(b200_ctx* ctx, int64_t n, const double* x, double* out_host) {
+  B200_DEVICE_GUARD(ctx);
   B200_TRY(b200i_reduce_sum_dev(ctx, n, x, nullptr, RED_MAXABS, ctx->d_scalars));
   B200_TRY(b200i_fetch_scalars(ctx, 1));
   *out_host = ctx->h_scalars[0];
   return B200_OK;
 }
 int32_t b200_diffnrm2(b200_ctx* ctx, int64_t n, const double* x, const double* y, double* out_host) {
+  B200_DEVICE_GUARD(ctx);
   B200_TRY(b200i_reduce_sum_dev(ctx, n, x, y, RED_DIFFSQ, ctx->d_scalars));
   B200_TRY(b200i_fetch_scalars(ctx, 1));
   *out_host = sqrt(ctx->h_scalars[0]);
   return B200_OK;
 }
 int32_t b200_extrema(b200_ctx* ctx, int64_t n, const double* x, double* min_host, double* max_host) {
+  B200_DEVICE_GUARD(ctx);
   B200_TRY(b200i_reduce_sum_dev(ctx, n, x, nullptr, RED_MIN, ctx->d_scalars));
   B200_TRY(b200i_reduce_sum_dev(ctx, n, x, nullptr, RED_MAX, ctx->d_scalars + 1));
   B200_TRY(b200i_fetch_scalars(ctx, 2));
@@ -375,6 +400,7 @@ int32_t b200_extrema(b200_ctx* ctx, int64_t n, const double* x, double* min_host
   return B200_OK;
 }
 int32_t b200_equal(b200_ctx* ctx, int64_t n, const double* x, const double* y, int32_t* equal_host) {
+  B200_DEVICE_GUARD(ctx);
   B200_TRY(b200i_reduce_sum_dev(ctx, n, x, y, RED_NEQ, ctx->d_scalars));
   B200_TRY(b200i_fetch_scalars(ctx, 1));
   *equal_host = (ctx->h_scalars[0] == 0.0) ? 1 : 0;

@@ -402,6 +402,7 @@ int32_t b200i_diag_shift(b200_ctx* ctx, int64_t n, double* A, int64_t ld, double
 
 extern "C" {
 int32_t b200_dense_jac_fill(b200_problem* p, const double* u, double* J, int64_t ld) {
+  B200_DEVICE_GUARD(p ? p->ctx : nullptr);
   b200_ctx* ctx = p->ctx;
   const int64_t n = p->n;
   B200_REQUIRE(ctx, ld >= n, "dense_jac_fill: ld < n");
@@ -440,6 +441,7 @@ int32_t b200_dense_jac_fill(b200_problem* p, const double* u, double* J, int64_t
 }
 
 int32_t b200_getrf(b200_ctx* ctx, int64_t n, double* A, int64_t ld, int64_t* ipiv, int32_t* info_host) {
+  B200_DEVICE_GUARD(ctx);
   B200_REQUIRE(ctx, n > 0 && ld >= n, "getrf: bad dimensions");
   static_assert(sizeof(PanelScratch) <= sizeof(double) * B200_RED_MAX_BLOCKS, "panel scratch must fit in d_partials");
   PanelScratch* ps = reinterpret_cast<PanelScratch*>(ctx->d_partials + 2 * B200_RED_MAX_BLOCKS);
@@ -532,6 +534,7 @@ int32_t b200_getrf(b200_ctx* ctx, int64_t n, double* A, int64_t ld, int64_t* ipi
 }
 
 int32_t b200_getrs(b200_ctx* ctx, int64_t n, int64_t nrhs, const double* A, int64_t ld, const int64_t* ipiv, double* B, int64_t ldb) {
+  B200_DEVICE_GUARD(ctx);
   B200_REQUIRE(ctx, n > 0 && nrhs > 0 && ld >= n && ldb >= n, "getrs: bad dimensions");
   LAUNCH(ctx, apply_pivots_kernel, (int)((nrhs + DT - 1) / DT), DT, 0, n, nrhs, ipiv, B, ldb);
   for (int64_t r = 0; r < nrhs; ++r) {

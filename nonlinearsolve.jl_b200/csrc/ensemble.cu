@@ -44,6 +44,7 @@ __global__ void ens_store_kernel(int32_t m, double resid, int32_t rc, int32_t ns
 
 extern "C" {
 int32_t b200_ens_destroy(b200_ensemble* e) {
+  B200_DEVICE_GUARD(e ? e->ctx : nullptr);
   if (!e) return B200_OK;
   cudaStreamSynchronize(e->ctx->stream);
   if (e->nw) b200_newton_destroy(e->nw);
@@ -55,6 +56,7 @@ int32_t b200_ens_destroy(b200_ensemble* e) {
 }
 
 int32_t b200_ens_create(b200_ctx* ctx, int32_t N, int32_t nprob_local, double alpha, const b200_newton_opts* opts, b200_ensemble** out) {
+  B200_DEVICE_GUARD(ctx);
   B200_REQUIRE(ctx, N >= 3 && nprob_local > 0 && opts && out, "ens_create: bad arguments");
   B200_REQUIRE(ctx, opts->linsolve == B200_LINSOLVE_GMRES && opts->globalization == B200_GLOBALIZATION_NONE && opts->precond == B200_PRECOND_NONE &&
                         opts->descent == B200_DESCENT_NEWTON,
@@ -78,6 +80,7 @@ int32_t b200_ens_create(b200_ctx* ctx, int32_t N, int32_t nprob_local, double al
 
 int32_t b200_ens_solve(b200_ensemble* e, const double* u0, const double* A, const double* B, double* u_out, double* resid_inf,
                        int32_t* retcodes, int32_t* nsteps, int32_t* njvp, b200_ens_result* result) {
+  B200_DEVICE_GUARD(e ? e->ctx : nullptr);
   b200_ctx* ctx = e->ctx;
   const int64_t n = 2 * (int64_t)e->N * e->N;
   const int32_t K = e->nprob;

@@ -22,6 +22,7 @@
 namespace {
 constexpr int GM_THREADS = 256;
 constexpr int JT = 8;  // basis columns streamed together by the multi-dot kernel
+constexpr int GM_KCAP = 16384;  // basis vectors per cycle: (GM_KCAP + 32) coefficients in shared memory, packed R = 1 GiB
 
 struct GmresState {  // device-resident scalars
   int32_t status;    // 0 = running, else B200_LS_*
@@ -486,6 +487,7 @@ struct ResidentParams {
   double* dbg;                // optional phase timers (cycles) of CTA 0: wait, dot, gather, update, steps
   int* err;
   double* h;        // Hessenberg column workspace (k + 1)
+  double* gsub;     // r3g kernel: gsub[i] = <v_i, v_{i-1}>, written by the step that creates v_i
   double *R, *cs, *sn, *z, *hraw;
   GmresState* st;
 };
@@ -858,26 +860,29 @@ struct R3Ctx {
   int nrow, ncell, total, k, b, G;
 };
 
-__device__ __forceinline__ void r3_issue_smem(const ResidentParams& P, const R3Ctx& cx, R3Shared& sh, int t, int stage) {
+__device__ __forceinline__ void r3_issue_smem(const ResidentParams& P, const R3Ctx& cx, uint64_t* mbar, int t, int stage) {
   if (threadIdx.x == 0 && cx.nrow > 0) {
     const double* src = P.V[t % cx.k];
     double* dst = stage ? cx.stage1 : cx.stage0;
     const unsigned seg_bytes = (unsigned)cx.ncell * 8u;
     const int64_t c0 = (int64_t)cx.b * P.cpc;
-    mbar_expect_tx(&sh.mbar[stage], 2u * seg_bytes);
-    tma_bulk_load(dst, src + c0, seg_bytes, &sh.mbar[stage]);
-    tma_bulk_load(dst + cx.ncell, src + P.NC + c0, seg_bytes, &sh.mbar[stage]);
+    mbar_expect_tx(&mbar[stage], 2u * seg_bytes);
+    tma_bulk_load(dst, src + c0, seg_bytes, &mbar[stage]);
+    tma_bulk_load(dst + cx.ncell, src + P.NC + c0, seg_bytes, &mbar[stage]);
   }
 }
 __device__ __forceinline__ void r3_issue_regs(const ResidentParams& P, const R3Ctx& cx, int t, double (&vr)[R3_VR]) {
-  const double* src = P.V[t % cx.k] + (int64_t)cx.b * P.cpc;
+  // thread-relative form (constant offsets, two per-thread limits) so that nothing per-q stays live across the step
+  const double* src = P.V[t % cx.k] + (int64_t)cx.b * P.cpc + 2 * (int)threadIdx.x;
+  const int lim = cx.nrow - 2 * (int)threadIdx.x, lims = cx.ncell - 2 * (int)threadIdx.x;
+  const int64_t hop = P.NC - cx.ncell;  // from the end of this CTA's first-species segment to the start of its second
 #pragma unroll
   for (int q = 0; q < R3_RP; ++q) {
-    const int lr = 2 * ((int)threadIdx.x + R3_THREADS * q);
-    const double* p = src + ((lr >= cx.ncell) ? (P.NC - cx.ncell) : (int64_t)0) + lr;
+    const int lr = 2 * R3_THREADS * q;
+    const double* p = src + ((lr >= lims) ? hop : (int64_t)0) + lr;
     if (q < R3_RPR) {
-      if (lr < cx.nrow) asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(vr[2 * (q < R3_RPR ? q : 0)]), "=d"(vr[2 * (q < R3_RPR ? q : 0) + 1]) : "l"(p));
-    } else if (lr < cx.nrow) {
+      if (lr < lim) asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(vr[2 * (q < R3_RPR ? q : 0)]), "=d"(vr[2 * (q < R3_RPR ? q : 0) + 1]) : "l"(p));
+    } else if (lr < lim) {
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(cx.annex + (q - R3_RPR) * R3_THREADS + threadIdx.x)), "l"(p) : "memory");
     }
   }
@@ -889,6 +894,52 @@ __device__ __forceinline__ void r3_issue_regs(const ResidentParams& P, const R3C
     if ((q) < R3_RPR) { o0 = vr[2 * ((q) < R3_RPR ? (q) : 0)]; o1 = vr[2 * ((q) < R3_RPR ? (q) : 0) + 1]; } \
     else { const double2 z_ = cx.annex[((q) - R3_RPR) * R3_THREADS + threadIdx.x]; o0 = z_.x; o1 = z_.y; }     \
   } while (0)
+
+// w = J(u) v_k (built-in Brusselator tangent) or the assembled sparse matrix times v_k (CSR view) for this CTA's rows;
+// thread `tid` holds the row pairs 2 * (tid + R3_THREADS * q), q = 0 .. R3_RP-1, of the CTA's row slice
+__device__ __forceinline__ void r3_apply_operator(const ResidentParams& P, const R3Ctx& cx, double (&w)[R3_ROWS]) {
+  const int tid = threadIdx.x;
+  const double* vk = P.V[P.k - 1];
+  const int N = P.N;
+  const int64_t N2 = (int64_t)N * N, NC = P.NC;
+  const int ncell = cx.ncell, nrow = cx.nrow;
+  const int64_t c0 = (int64_t)cx.b * P.cpc;
+#pragma unroll
+  for (int qq = 0; qq < R3_ROWS; ++qq) {
+    const int lr = 2 * (tid + R3_THREADS * (qq >> 1)) + (qq & 1);
+    w[qq] = 0.0;
+    if (lr < nrow && P.opkind == 1) {
+      const int s = lr >= ncell;
+      const int64_t r = (int64_t)s * NC + c0 + (lr - s * ncell);
+      double acc = 0.0;
+      for (int64_t e = P.rowptr[r], e1 = P.rowptr[r + 1]; e < e1; ++e) acc = fma(P.nzval[P.csr_map[e]], vk[P.csr_col[e]], acc);
+      w[qq] = acc;
+    } else if (lr < nrow) {
+      const int s = lr >= ncell;
+      const int64_t c = c0 + (lr - s * ncell);
+      int64_t cim, cip, cjm, cjp, ckm = 0, ckp = 0;
+      if (P.dim == 3) {
+        const int kk = (int)(c / N2);
+        const int r = (int)(c - (int64_t)kk * N2);
+        const int j = r / N, i = r - j * N;
+        cim = c + ((i == 0) ? (N - 1) : -1); cip = c + ((i + 1 == N) ? -(N - 1) : 1);
+        cjm = c + ((j == 0) ? (int64_t)(N - 1) * N : -N); cjp = c + ((j + 1 == N) ? -(int64_t)(N - 1) * N : N);
+        ckm = c + ((kk == 0) ? (int64_t)(N - 1) * N2 : -N2); ckp = c + ((kk + 1 == N) ? -(int64_t)(N - 1) * N2 : N2);
+      } else {
+        const int j = (int)(c / N), i = (int)(c - (int64_t)j * N);
+        cim = c + ((i == 0) ? (N - 1) : -1); cip = c + ((i + 1 == N) ? -(N - 1) : 1);
+        cjm = c + ((j == 0) ? (int64_t)(N - 1) * N : -N); cjp = c + ((j + 1 == N) ? -(int64_t)(N - 1) * N : N);
+      }
+      const double* x = vk + (int64_t)s * NC;
+      const double xc = x[c];
+      double lap = x[cim] + x[cip] + x[cjp] + x[cjm] - 4.0 * xc;
+      if (P.dim == 3) lap = lap + (x[ckp] + x[ckm] - 2.0 * xc);
+      const double uc = P.u[c], vc = P.u[c + NC], dc = vk[c], ec = vk[c + NC];
+      const double uv2 = 2.0 * uc * vc, uu = uc * uc;
+      w[qq] = s ? (P.a * lap + (P.A - uv2) * dc - uu * ec) : (P.a * lap + (uv2 - (P.A + 1.0)) * dc + uu * ec);
+    }
+  }
+}
 
 // One Gram-Schmidt step for the vector of step t whose stage role is ROLE = t % 3.
 template <int ROLE>
@@ -942,7 +993,7 @@ __device__ __forceinline__ void r3_step(const ResidentParams& P, R3Ctx& cx, R3Sh
   if (cx.b == 0 && tid == 0) { const int i = t % cx.k; P.h[i] = (t < cx.k) ? h : P.h[i] + h; }
   if (ROLE != 2) {
     __syncthreads();  // every thread is done with this shared-memory stage
-    if (t + 3 < cx.total && P.late_issue != 7) r3_issue_smem(P, cx, sh, t + 3, ROLE);
+    if (t + 3 < cx.total && P.late_issue != 7) r3_issue_smem(P, cx, sh.mbar, t + 3, ROLE);
   } else {
     if (t + 3 < cx.total && P.late_issue != 7) r3_issue_regs(P, cx, t + 3, vr);
   }
@@ -969,51 +1020,14 @@ __global__ void __launch_bounds__(R3_THREADS, 1) resident3_arnoldi_kernel(Reside
   }
   __syncthreads();
   // the first two basis vectors start travelling while the operator is applied
-  r3_issue_smem(P, cx, sh, 0, 0);
-  if (cx.total > 1) r3_issue_smem(P, cx, sh, 1, 1);
+  r3_issue_smem(P, cx, sh.mbar, 0, 0);
+  if (cx.total > 1) r3_issue_smem(P, cx, sh.mbar, 1, 1);
   // ---- 1. w = J(u) v_k (or the assembled sparse matrix times v_k) for this CTA's rows, into registers
-  const double* vk = P.V[P.k - 1];
   double w[R3_ROWS];
   double vr[R3_VR];
-  const int N = P.N;
-  const int64_t N2 = (int64_t)N * N, NC = P.NC;
+  r3_apply_operator(P, cx, w);
   const int ncell = cx.ncell, nrow = cx.nrow;
-  const int64_t c0 = (int64_t)b * cpc;
-#pragma unroll
-  for (int qq = 0; qq < R3_ROWS; ++qq) {
-    const int lr = 2 * (tid + R3_THREADS * (qq >> 1)) + (qq & 1);
-    w[qq] = 0.0;
-    if (lr < nrow && P.opkind == 1) {
-      const int s = lr >= ncell;
-      const int64_t r = (int64_t)s * NC + c0 + (lr - s * ncell);
-      double acc = 0.0;
-      for (int64_t e = P.rowptr[r], e1 = P.rowptr[r + 1]; e < e1; ++e) acc = fma(P.nzval[P.csr_map[e]], vk[P.csr_col[e]], acc);
-      w[qq] = acc;
-    } else if (lr < nrow) {
-      const int s = lr >= ncell;
-      const int64_t c = c0 + (lr - s * ncell);
-      int64_t cim, cip, cjm, cjp, ckm = 0, ckp = 0;
-      if (P.dim == 3) {
-        const int kk = (int)(c / N2);
-        const int r = (int)(c - (int64_t)kk * N2);
-        const int j = r / N, i = r - j * N;
-        cim = c + ((i == 0) ? (N - 1) : -1); cip = c + ((i + 1 == N) ? -(N - 1) : 1);
-        cjm = c + ((j == 0) ? (int64_t)(N - 1) * N : -N); cjp = c + ((j + 1 == N) ? -(int64_t)(N - 1) * N : N);
-        ckm = c + ((kk == 0) ? (int64_t)(N - 1) * N2 : -N2); ckp = c + ((kk + 1 == N) ? -(int64_t)(N - 1) * N2 : N2);
-      } else {
-        const int j = (int)(c / N), i = (int)(c - (int64_t)j * N);
-        cim = c + ((i == 0) ? (N - 1) : -1); cip = c + ((i + 1 == N) ? -(N - 1) : 1);
-        cjm = c + ((j == 0) ? (int64_t)(N - 1) * N : -N); cjp = c + ((j + 1 == N) ? -(int64_t)(N - 1) * N : N);
-      }
-      const double* x = vk + (int64_t)s * NC;
-      const double xc = x[c];
-      double lap = x[cim] + x[cip] + x[cjp] + x[cjm] - 4.0 * xc;
-      if (P.dim == 3) lap = lap + (x[ckp] + x[ckm] - 2.0 * xc);
-      const double uc = P.u[c], vc = P.u[c + NC], dc = vk[c], ec = vk[c + NC];
-      const double uv2 = 2.0 * uc * vc, uu = uc * uc;
-      w[qq] = s ? (P.a * lap + (P.A - uv2) * dc - uu * ec) : (P.a * lap + (uv2 - (P.A + 1.0)) * dc + uu * ec);
-    }
-  }
+  const int64_t NC = P.NC, c0 = (int64_t)b * cpc;
   // ---- 2. lag-1 modified Gram-Schmidt over three rotating stages
   const int total = cx.total;
   if (total > 2) r3_issue_regs(P, cx, 2, vr);
@@ -1070,6 +1084,219 @@ __global__ void __launch_bounds__(R3_THREADS, 1) resident3_arnoldi_kernel(Reside
   }
   if (b == 0 && tid == 0) resident_givens_tail(P, hbis, inv);
 }
+
+// =====================================================================================================================
+// Round-2 variant of the three-stage lag-1 kernel ("r3g"): the cross products <v_{t+1}, v_t> the lag-1 recurrence needs
+// are entries of the Gram matrix of the basis, i.e. they do not depend on w.  <v_{k}, v_{k-1}> falls out of the last update
+// sweep of the Arnoldi step that CREATES v_k (w_final is in registers, v_{k-1} is the stage being applied) and travels in
+// the free second slot of the norm exchange; it is stored once in gsub[k] and read back by every later step.  The dot
+// sweep therefore reads ONE staged vector instead of two (half the shared-memory traffic of the sweep that bounds the
+// step) and needs one block reduction instead of two.  Only the wrap-around of a second Gram-Schmidt pass (v_0 after
+// v_{k-1}) still takes its cross product in the sweep.
+// Barriers: one __syncthreads per basis vector (two when the stage being released lives in shared memory) instead of
+// two (three).  Every reduction / poll scratch is double-buffered by step parity, so no write can meet a read of the
+// previous step without a barrier in between (compute-sanitizer racecheck: profiles/).
+struct R3GShared {
+  uint64_t mbar[2];
+  double redA[2][8], redC[2][8];  // per-warp partials of the dot sweep, by step parity
+  double gA[2][8], gC[2][8];      // per-warp sums of the polled exchange entries, by step parity; gC[.][5] = stored cross product
+  double hprev[2];                // previous Gram-Schmidt coefficient, by step parity (kept out of the register file)
+};
+
+template <int ROLE>
+__device__ __forceinline__ void r3g_step(const ResidentParams& P, R3Ctx& cx, R3GShared& sh, int t, double (&w)[R3_ROWS], double (&vr)[R3_VR]) {
+  constexpr int NEXT = (ROLE + 1) % 3;
+  const int tid = threadIdx.x;
+  const int par = t & 1;
+  const int lim = cx.nrow - 2 * tid;                       // row pair q of this thread exists iff 2 * R3_THREADS * q < lim
+  const double* sc = (ROLE == 0 ? cx.stage0 : cx.stage1) + 2 * tid;   // current vector if it lives in shared memory
+  const double* sn = (NEXT == 0 ? cx.stage0 : cx.stage1) + 2 * tid;   // next vector if it lives in shared memory
+  const bool more = t + 1 < cx.total;
+  const int i = t % cx.k;
+  if (more) {
+    if (NEXT != 2 && cx.nrow > 0) mbar_wait(&sh.mbar[NEXT], (unsigned)(((t + 1) / 3) & 1));
+    if (NEXT == 2) asm volatile("cp.async.wait_group 0;" ::: "memory");
+    double da = 0.0, dc = 0.0;
+    if (i + 1 == cx.k) {  // wrap-around into the next Gram-Schmidt pass: <v_0, v_{k-1}> is not stored, take it in the sweep
+#pragma unroll
+      for (int q = 0; q < R3_RP; ++q) {
+        const int lr = 2 * R3_THREADS * q;  // offset from this thread's first row pair
+        if (lr < lim) {
+          double x0, x1, y0, y1;
+          if (NEXT == 2) { R3_VRGET(q, x0, x1); }
+          else { const double2 x = *reinterpret_cast<const double2*>(sn + lr); x0 = x.x; x1 = x.y; }
+          if (ROLE == 2) { R3_VRGET(q, y0, y1); }
+          else { const double2 y = *reinterpret_cast<const double2*>(sc + lr); y0 = y.x; y1 = y.y; }
+          da = fma(x0, w[2 * q], da); da = fma(x1, w[2 * q + 1], da);
+          dc = fma(x0, y0, dc); dc = fma(x1, y1, dc);
+        }
+      }
+      dc = warp_sum(dc);
+    } else {
+#pragma unroll
+      for (int q = 0; q < R3_RP; ++q) {
+        const int lr = 2 * R3_THREADS * q;  // offset from this thread's first row pair
+        if (lr < lim) {
+          double x0, x1;
+          if (NEXT == 2) { R3_VRGET(q, x0, x1); }
+          else { const double2 x = *reinterpret_cast<const double2*>(sn + lr); x0 = x.x; x1 = x.y; }
+          da = fma(x0, w[2 * q], da); da = fma(x1, w[2 * q + 1], da);
+        }
+      }
+    }
+    da = warp_sum(da);
+    if ((tid & 31) == 0) { sh.redA[par][tid >> 5] = da; sh.redC[par][tid >> 5] = dc; }
+  }
+  // Gram sub-diagonal entry <v_i, v_{i-1}>, stored when v_i was created: fetched by a spare polling thread (G <= 159)
+  if (tid == 159) sh.gC[par][5] = (i > 0) ? __ldg(P.gsub + i) : 0.0;
+  r3_poll(P.slots + (size_t)(t & 3) * R3_BUF_WORDS, cx.b, cx.G, P.epoch_base + (unsigned)t + 1u, P.err, sh.gA[par], sh.gC[par]);
+  __syncthreads();  // the only barrier of a register-role step
+  if (more && tid < 32) {  // warp 0: total of the eight warp partials in a fixed order, then publish for step t+1
+    const double* ra = sh.redA[par];
+    const double* rc = sh.redC[par];
+    const double ta = ((ra[0] + ra[1]) + (ra[2] + ra[3])) + ((ra[4] + ra[5]) + (ra[6] + ra[7]));
+    const double tc = ((rc[0] + rc[1]) + (rc[2] + rc[3])) + ((rc[4] + rc[5]) + (rc[6] + rc[7]));
+    r3_post(P.slots + (size_t)((t + 1) & 3) * R3_BUF_WORDS, cx.b, ta, tc, P.epoch_base + (unsigned)(t + 1) + 1u);
+  }
+  const double* ga = sh.gA[par];
+  const double* gc = sh.gC[par];
+  const double sa = ((ga[0] + ga[1]) + (ga[2] + ga[3])) + ga[4];
+  const double cross = (i > 0) ? gc[5] : (((gc[0] + gc[1]) + (gc[2] + gc[3])) + gc[4]);  // i == 0: wrap-around, taken in the sweep
+  const double h = sa - sh.hprev[par ^ 1] * cross;
+  if (tid == 0) sh.hprev[par] = h;
+  if (more) {
+#pragma unroll
+    for (int q = 0; q < R3_RP; ++q) {
+      const int lr = 2 * R3_THREADS * q;  // offset from this thread's first row pair
+      if (lr < lim) {
+        double y0, y1;
+        if (ROLE == 2) { R3_VRGET(q, y0, y1); }
+        else { const double2 y = *reinterpret_cast<const double2*>(sc + lr); y0 = y.x; y1 = y.y; }
+        w[2 * q] = fma(-h, y0, w[2 * q]);
+        w[2 * q + 1] = fma(-h, y1, w[2 * q + 1]);
+      }
+    }
+  } else {  // last update of the Arnoldi step: ||w||^2 and <w, v_{k-1}> (next step's Gram sub-diagonal entry) ride along
+    double nacc = 0.0, xacc = 0.0;
+#pragma unroll
+    for (int q = 0; q < R3_RP; ++q) {
+      const int lr = 2 * R3_THREADS * q;  // offset from this thread's first row pair
+      if (lr < lim) {
+        double y0, y1;
+        if (ROLE == 2) { R3_VRGET(q, y0, y1); }
+        else { const double2 y = *reinterpret_cast<const double2*>(sc + lr); y0 = y.x; y1 = y.y; }
+        const double w0 = fma(-h, y0, w[2 * q]), w1 = fma(-h, y1, w[2 * q + 1]);
+        w[2 * q] = w0; w[2 * q + 1] = w1;
+        nacc = fma(w0, w0, nacc); nacc = fma(w1, w1, nacc);
+        xacc = fma(w0, y0, xacc); xacc = fma(w1, y1, xacc);
+      }
+    }
+    nacc = warp_sum(nacc);
+    xacc = warp_sum(xacc);
+    if ((tid & 31) == 0) { sh.redA[par ^ 1][tid >> 5] = nacc; sh.redC[par ^ 1][tid >> 5] = xacc; }  // parity of "step total"
+  }
+  if (cx.b == 0 && tid == 0) P.h[i] = (t < cx.k) ? h : P.h[i] + h;
+  if (ROLE != 2) {
+    if (t + 3 < cx.total) {
+      __syncthreads();  // every thread is done with this shared-memory stage
+      r3_issue_smem(P, cx, sh.mbar, t + 3, ROLE);
+    }
+  } else if (t + 3 < cx.total) {
+    r3_issue_regs(P, cx, t + 3, vr);
+  }
+}
+
+__global__ void __launch_bounds__(R3_THREADS, 1) resident3g_arnoldi_kernel(ResidentParams P) {
+  if (P.st->status != 0) return;
+  extern __shared__ __align__(16) double rsm[];
+  __shared__ R3GShared sh;
+  R3Ctx cx;
+  const int cpc = P.cpc;
+  cx.stage0 = rsm;
+  cx.stage1 = rsm + 2 * cpc;
+  cx.annex = reinterpret_cast<double2*>(rsm + 4 * cpc);
+  const int tid = threadIdx.x, b = blockIdx.x, G = P.G;
+  cx.b = b; cx.G = G; cx.k = P.k; cx.total = P.passes * P.k;
+  cx.ncell = (int)max((int64_t)0, min((int64_t)cpc, P.NC - (int64_t)b * cpc));
+  cx.nrow = 2 * cx.ncell;
+  if (tid == 0) {
+    mbar_init(&sh.mbar[0], 1);
+    mbar_init(&sh.mbar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  // the first two basis vectors start travelling while the operator is applied
+  r3_issue_smem(P, cx, sh.mbar, 0, 0);
+  if (cx.total > 1) r3_issue_smem(P, cx, sh.mbar, 1, 1);
+  // ---- 1. w = J(u) v_k (or the assembled sparse matrix times v_k) for this CTA's rows, into registers
+  double w[R3_ROWS];
+  double vr[R3_VR];
+  r3_apply_operator(P, cx, w);
+  // ---- 2. lag-1 modified Gram-Schmidt over three rotating stages
+  const int total = cx.total;
+  const int nrow = cx.nrow;
+  const int lim = nrow - 2 * tid;
+  if (total > 2) r3_issue_regs(P, cx, 2, vr);
+  {
+    if (nrow > 0) mbar_wait(&sh.mbar[0], 0u);
+    double da = 0.0;
+#pragma unroll
+    for (int q = 0; q < R3_RP; ++q) {
+      const int lr = 2 * R3_THREADS * q;
+      if (lr < lim) {
+        const double2 x = *reinterpret_cast<const double2*>(cx.stage0 + 2 * tid + lr);
+        da = fma(x.x, w[2 * q], da); da = fma(x.y, w[2 * q + 1], da);
+      }
+    }
+    da = warp_sum(da);
+    if ((tid & 31) == 0) sh.redA[1][tid >> 5] = da;  // parity of "step -1"
+    if (tid == 0) sh.hprev[1] = 0.0;
+    __syncthreads();
+    if (tid < 32) {
+      const double* ra = sh.redA[1];
+      const double ta = ((ra[0] + ra[1]) + (ra[2] + ra[3])) + ((ra[4] + ra[5]) + (ra[6] + ra[7]));
+      r3_post(P.slots, b, ta, 0.0, P.epoch_base + 1u);
+    }
+  }
+  for (int t = 0; t < total; t += 3) {
+    r3g_step<0>(P, cx, sh, t, w, vr);
+    if (t + 1 < total) r3g_step<1>(P, cx, sh, t + 1, w, vr);
+    if (t + 2 < total) r3g_step<2>(P, cx, sh, t + 2, w, vr);
+  }
+  // ---- 3. ||w|| and <w, v_{k-1}> in one exchange (the last step left the warp partials in the scratch of parity
+  //         `total`), Givens (CTA 0), normalise, store v_{k+1}
+  const int par = total & 1;
+  __syncthreads();
+  if (tid < 32) {
+    const double* ra = sh.redA[par];
+    const double* rc = sh.redC[par];
+    const double ta = ((ra[0] + ra[1]) + (ra[2] + ra[3])) + ((ra[4] + ra[5]) + (ra[6] + ra[7]));
+    const double tc = ((rc[0] + rc[1]) + (rc[2] + rc[3])) + ((rc[4] + rc[5]) + (rc[6] + rc[7]));
+    r3_post(P.slots + (size_t)(total & 3) * R3_BUF_WORDS, b, ta, tc, P.epoch_base + (unsigned)total + 1u);
+  }
+  r3_poll(P.slots + (size_t)(total & 3) * R3_BUF_WORDS, b, G, P.epoch_base + (unsigned)total + 1u, P.err, sh.gA[par], sh.gC[par]);
+  __syncthreads();
+  const double* gaf = sh.gA[par];
+  const double* gcf = sh.gC[par];
+  const double hbis = sqrt(((gaf[0] + gaf[1]) + (gaf[2] + gaf[3])) + gaf[4]);
+  const double inv = hbis > 0.0 ? 1.0 / hbis : 0.0;
+  const int ncell = cx.ncell;
+  const int64_t NC = P.NC, c0 = (int64_t)b * cpc;
+#pragma unroll
+  for (int q = 0; q < R3_RP; ++q) {
+    const int lr = 2 * (tid + R3_THREADS * q);
+    if (lr < nrow) {
+      const int s = lr >= ncell;
+      double2 o;
+      o.x = w[2 * q] * inv; o.y = w[2 * q + 1] * inv;
+      *reinterpret_cast<double2*>(P.vnew + (int64_t)s * NC + c0 + (lr - s * ncell)) = o;
+    }
+  }
+  if (b == 0 && tid == 0) {
+    P.gsub[P.k] = (((gcf[0] + gcf[1]) + (gcf[2] + gcf[3])) + gcf[4]) * inv;  // <v_k, v_{k-1}> for every later Arnoldi step
+    resident_givens_tail(P, hbis, inv);
+  }
+}
 }  // namespace
 
 struct b200_gmres {
@@ -1083,6 +1310,7 @@ struct b200_gmres {
   double** d_Vptrs;
   int vptr_cap;
   double *w, *r0, *d_h, *d_hacc, *d_R, *d_cs, *d_sn, *d_z, *d_y, *d_partial, *d_norm_partial, *d_norm_partial2;
+  double* d_gsub;       // resident engine: Gram sub-diagonal <v_i, v_{i-1}> (see resident3g_arnoldi_kernel)
   double* d_hraw;
   int64_t hraw_cap;
   GmresState* d_state;
@@ -1098,8 +1326,8 @@ struct b200_gmres {
 namespace {
 int32_t gm_free_arrays(b200_gmres* gm) {
   cudaFree(gm->d_h); cudaFree(gm->d_hacc); cudaFree(gm->d_R); cudaFree(gm->d_cs); cudaFree(gm->d_sn);
-  cudaFree(gm->d_z); cudaFree(gm->d_y); cudaFree(gm->d_partial);
-  gm->d_h = gm->d_hacc = gm->d_R = gm->d_cs = gm->d_sn = gm->d_z = gm->d_y = gm->d_partial = nullptr;
+  cudaFree(gm->d_z); cudaFree(gm->d_y); cudaFree(gm->d_partial); cudaFree(gm->d_gsub);
+  gm->d_h = gm->d_hacc = gm->d_R = gm->d_cs = gm->d_sn = gm->d_z = gm->d_y = gm->d_partial = gm->d_gsub = nullptr;
   return B200_OK;
 }
 
@@ -1109,12 +1337,12 @@ int32_t gm_reserve(b200_gmres* gm, int need) {
   if (need <= gm->kcap) return B200_OK;
   int ncap = std::max(need, gm->kcap > 0 ? gm->kcap * 2 : 64);
   const int64_t rsz = (int64_t)ncap * (ncap + 1) / 2;
-  double *nh, *nha, *nR, *ncs, *nsn, *nz, *ny, *npart;
+  double *nh, *nha, *nR, *ncs, *nsn, *nz, *ny, *npart, *ngs;
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   if (cudaMalloc(&nh, sizeof(double) * (ncap + 2)) != cudaSuccess || cudaMalloc(&nha, sizeof(double) * (ncap + 2)) != cudaSuccess ||
       cudaMalloc(&nR, sizeof(double) * rsz) != cudaSuccess || cudaMalloc(&ncs, sizeof(double) * (ncap + 2)) != cudaSuccess ||
       cudaMalloc(&nsn, sizeof(double) * (ncap + 2)) != cudaSuccess || cudaMalloc(&nz, sizeof(double) * (ncap + 2)) != cudaSuccess ||
-      cudaMalloc(&ny, sizeof(double) * (ncap + 2)) != cudaSuccess ||
+      cudaMalloc(&ny, sizeof(double) * (ncap + 2)) != cudaSuccess || cudaMalloc(&ngs, sizeof(double) * (ncap + 2)) != cudaSuccess ||
       cudaMalloc(&npart, sizeof(double) * (int64_t)ncap * gm->G) != cudaSuccess) {
     cudaGetLastError();
     return ctx->fail(B200_ERR_NOMEM, "out of device memory growing the Krylov workspace", __FILE__, __LINE__);
@@ -1125,9 +1353,10 @@ int32_t gm_reserve(b200_gmres* gm, int need) {
     CUDA_TRY(ctx, cudaMemcpy(ncs, gm->d_cs, sizeof(double) * (oc + 2), cudaMemcpyDeviceToDevice));
     CUDA_TRY(ctx, cudaMemcpy(nsn, gm->d_sn, sizeof(double) * (oc + 2), cudaMemcpyDeviceToDevice));
     CUDA_TRY(ctx, cudaMemcpy(nz, gm->d_z, sizeof(double) * (oc + 2), cudaMemcpyDeviceToDevice));
+    CUDA_TRY(ctx, cudaMemcpy(ngs, gm->d_gsub, sizeof(double) * (oc + 2), cudaMemcpyDeviceToDevice));
     gm_free_arrays(gm);
   }
-  gm->d_h = nh; gm->d_hacc = nha; gm->d_R = nR; gm->d_cs = ncs; gm->d_sn = nsn; gm->d_z = nz; gm->d_y = ny; gm->d_partial = npart;
+  gm->d_h = nh; gm->d_hacc = nha; gm->d_R = nR; gm->d_cs = ncs; gm->d_sn = nsn; gm->d_z = nz; gm->d_y = ny; gm->d_partial = npart; gm->d_gsub = ngs;
   gm->kcap = ncap;
   return B200_OK;
 }
@@ -1153,6 +1382,8 @@ int32_t gm_ensure_vector(b200_gmres* gm, int idx) {
         return B200_ERR_NOMEM;  // caller turns this into B200_LS_OUT_OF_MEMORY
       }
     }
+    // defined contents: a kernel that early-exits on a finished status word never leaves an operand uninitialised
+    CUDA_TRY(ctx, cudaMemsetAsync(slab, 0, sizeof(double) * npad * cnt, ctx->stream));
     gm->slabs.push_back(slab);
     for (int q = 0; q < cnt; ++q) gm->V.push_back(slab + (int64_t)q * npad);
     table_dirty = true;
@@ -1236,6 +1467,7 @@ static int32_t linop_apply_unshifted(b200_linop* op, const double* x, double* y)
 
 extern "C" {
 int32_t b200_gemv(b200_ctx* ctx, int32_t trans, int64_t m, int64_t n, const double* A, int64_t ld, const double* x, double* y) {
+  B200_DEVICE_GUARD(ctx);
   if (!trans) {
     LAUNCH(ctx, dense_gemv_kernel, (int)((m + GM_THREADS - 1) / GM_THREADS), GM_THREADS, 0, 0, m, n, A, ld, x, y);
   } else {
@@ -1246,6 +1478,7 @@ int32_t b200_gemv(b200_ctx* ctx, int32_t trans, int64_t m, int64_t n, const doub
 }
 
 int32_t b200_linop_from_problem(b200_problem* prob, const double* u, int32_t jvp_mode, b200_linop** out) {
+  B200_DEVICE_GUARD(prob ? prob->ctx : nullptr);
   b200_linop* op = new b200_linop();
   memset(op, 0, sizeof(*op));
   op->ctx = prob->ctx; op->kind = LINOP_PROBLEM; op->n = prob->n; op->prob = prob; op->u = u; op->jvp_mode = jvp_mode;
@@ -1254,6 +1487,7 @@ int32_t b200_linop_from_problem(b200_problem* prob, const double* u, int32_t jvp
 }
 int32_t b200_linop_from_csc(b200_ctx* ctx, int64_t n, const int64_t* colptr, const int64_t* rowval, const double* nzval, int32_t base,
                             b200_linop** out) {
+  B200_DEVICE_GUARD(ctx);
   b200_linop* op = new b200_linop();
   memset(op, 0, sizeof(*op));
   op->ctx = ctx; op->kind = LINOP_CSC; op->n = n; op->colptr = colptr; op->rowval = rowval; op->nzval = nzval; op->index_base = base;
@@ -1261,6 +1495,7 @@ int32_t b200_linop_from_csc(b200_ctx* ctx, int64_t n, const int64_t* colptr, con
   return B200_OK;
 }
 int32_t b200_linop_from_dense(b200_ctx* ctx, int64_t n, const double* A, int64_t ld, b200_linop** out) {
+  B200_DEVICE_GUARD(ctx);
   b200_linop* op = new b200_linop();
   memset(op, 0, sizeof(*op));
   op->ctx = ctx; op->kind = LINOP_DENSE; op->n = n; op->A = A; op->ld = ld;
@@ -1268,13 +1503,17 @@ int32_t b200_linop_from_dense(b200_ctx* ctx, int64_t n, const double* A, int64_t
   return B200_OK;
 }
 int32_t b200_linop_from_callback(b200_ctx* ctx, int64_t n, b200_matvec_cb mv, void* user, b200_linop** out) {
+  B200_DEVICE_GUARD(ctx);
   b200_linop* op = new b200_linop();
   memset(op, 0, sizeof(*op));
   op->ctx = ctx; op->kind = LINOP_CALLBACK; op->n = n; op->mv = mv; op->user = user;
   *out = op;
   return B200_OK;
 }
-int32_t b200_linop_apply(b200_linop* op, const double* x, double* y) { return b200i_linop_apply(op, x, y); }
+int32_t b200_linop_apply(b200_linop* op, const double* x, double* y) {
+  B200_DEVICE_GUARD(op ? op->ctx : nullptr);
+  return b200i_linop_apply(op, x, y);
+}
 int32_t b200_linop_set_shift(b200_linop* op, double shift) { op->shift = shift; return B200_OK; }
 int32_t b200_linop_destroy(b200_linop* op) { delete op; return B200_OK; }
 
@@ -1292,11 +1531,12 @@ void b200_gmres_opts_default(b200_gmres_opts* o) {
 }
 
 int32_t b200_gmres_create(b200_ctx* ctx, int64_t n, const b200_gmres_opts* opts, b200_gmres** out) {
+  B200_DEVICE_GUARD(ctx);
   B200_REQUIRE(ctx, n > 0 && opts && out, "gmres_create: bad arguments");
   b200_gmres* gm = new b200_gmres();
   gm->ctx = ctx; gm->n = n; gm->opts = *opts;
   gm->kcap = 0; gm->d_Vptrs = nullptr; gm->vptr_cap = 0;
-  gm->d_h = gm->d_hacc = gm->d_R = gm->d_cs = gm->d_sn = gm->d_z = gm->d_y = gm->d_partial = nullptr;
+  gm->d_h = gm->d_hacc = gm->d_R = gm->d_cs = gm->d_sn = gm->d_z = gm->d_y = gm->d_partial = gm->d_gsub = nullptr;
   gm->d_hraw = nullptr; gm->hraw_cap = 0;
   gm->d_bar = nullptr; gm->d_slots = nullptr; gm->ll_epoch = 0; gm->dbg_on = 0; gm->Pl = gm->Pr = nullptr; gm->pt1 = gm->pt2 = nullptr;
   // streaming grid: 4 CTAs of 256 threads per SM, fewer for small n (at least 512 rows per CTA)
@@ -1313,6 +1553,8 @@ int32_t b200_gmres_create(b200_ctx* ctx, int64_t n, const b200_gmres_opts* opts,
   CUDA_TRY(ctx, cudaMalloc(&gm->d_slots, sizeof(unsigned long long) * 4 * LL_MAXG * LL_MAXG));
   CUDA_TRY(ctx, cudaMemsetAsync(gm->d_slots, 0, sizeof(unsigned long long) * 4 * LL_MAXG * LL_MAXG, ctx->stream));
   CUDA_TRY(ctx, cudaMemsetAsync(gm->d_bar, 0, 4 * sizeof(unsigned), ctx->stream));
+  CUDA_TRY(ctx, cudaFuncSetAttribute(update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * (GM_KCAP + 64))));
+  CUDA_TRY(ctx, cudaFuncSetAttribute(backsolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * (GM_KCAP + 64))));
   int mem = opts->restart > 0 ? opts->restart : (opts->memory > 0 ? opts->memory : 20);
   if (mem > n) mem = (int)n;
   int32_t s = gm_reserve(gm, std::max(mem + 1, 32));
@@ -1322,6 +1564,7 @@ int32_t b200_gmres_create(b200_ctx* ctx, int64_t n, const b200_gmres_opts* opts,
 }
 
 int32_t b200_gmres_destroy(b200_gmres* gm) {
+  B200_DEVICE_GUARD(gm ? gm->ctx : nullptr);
   if (!gm) return B200_OK;
   cudaStreamSynchronize(gm->ctx->stream);
   for (double* v : gm->slabs) cudaFree(v);
@@ -1344,6 +1587,7 @@ int32_t b200_gmres_set_tolerances(b200_gmres* gm, double atol, double rtol) {
   return B200_OK;
 }
 int32_t b200_gmres_set_precond(b200_gmres* gm, b200_linop* left_inv, b200_linop* right_inv) {
+  B200_DEVICE_GUARD(gm ? gm->ctx : nullptr);
   b200_ctx* ctx = gm->ctx;
   B200_REQUIRE(ctx, (!left_inv || left_inv->n == gm->n) && (!right_inv || right_inv->n == gm->n), "gmres_set_precond: operator size mismatch");
   gm->Pl = left_inv; gm->Pr = right_inv;
@@ -1354,6 +1598,7 @@ int32_t b200_gmres_set_precond(b200_gmres* gm, b200_linop* left_inv, b200_linop*
   return B200_OK;
 }
 int32_t b200_linop_block_jacobi(b200_problem* prob, const double* u, b200_linop** out) {
+  B200_DEVICE_GUARD(prob ? prob->ctx : nullptr);
   B200_REQUIRE(prob->ctx, prob->kind == B200_PROB_BRUSS2D || prob->kind == B200_PROB_BRUSS3D, "block-Jacobi preconditioner: built-in Brusselator problems only");
   b200_linop* op = new b200_linop();
   memset(op, 0, sizeof(*op));
@@ -1364,6 +1609,7 @@ int32_t b200_linop_block_jacobi(b200_problem* prob, const double* u, b200_linop*
 
 // test hook: keep the raw Hessenberg columns of the next solve (k+1 entries per column)
 int32_t b200_gmres_keep_hessenberg(b200_gmres* gm, int64_t capacity) {
+  B200_DEVICE_GUARD(gm ? gm->ctx : nullptr);
   b200_ctx* ctx = gm->ctx;
   if (gm->d_hraw) { cudaFree(gm->d_hraw); gm->d_hraw = nullptr; }
   gm->hraw_cap = capacity;
@@ -1372,6 +1618,7 @@ int32_t b200_gmres_keep_hessenberg(b200_gmres* gm, int64_t capacity) {
 }
 // test hook: phase timers of the resident kernel (cycles summed over steps, CTA 0): wait, dot, gather, update, steps
 int32_t b200_gmres_debug(b200_gmres* gm, int32_t enable, double* out_host, int32_t count) {
+  B200_DEVICE_GUARD(gm ? gm->ctx : nullptr);
   b200_ctx* ctx = gm->ctx;
   if (out_host && count > 0) B200_TRY(b200_memcpy_d2h(ctx, out_host, gm->d_norm_partial2, sizeof(double) * count));
   gm->dbg_on = enable;
@@ -1379,12 +1626,14 @@ int32_t b200_gmres_debug(b200_gmres* gm, int32_t enable, double* out_host, int32
   return B200_OK;
 }
 int32_t b200_gmres_get_hessenberg(b200_gmres* gm, double* out_host, int64_t count) {
+  B200_DEVICE_GUARD(gm ? gm->ctx : nullptr);
   b200_ctx* ctx = gm->ctx;
   if (!gm->d_hraw || count > gm->hraw_cap) return ctx->fail(B200_ERR_INVALID, "hessenberg capture not enabled / too small", __FILE__, __LINE__);
   return b200_memcpy_d2h(ctx, out_host, gm->d_hraw, sizeof(double) * count);
 }
 
 int32_t b200_gmres_solve(b200_gmres* gm, b200_linop* op, const double* b, double* x, b200_gmres_stats* stats) {
+  B200_DEVICE_GUARD(gm ? gm->ctx : nullptr);
   b200_ctx* ctx = gm->ctx;
   B200_REQUIRE(ctx, op && op->n == gm->n && b && x, "gmres_solve: bad arguments");
   B200_REQUIRE(ctx, (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(b) & 7) == 0,
@@ -1393,14 +1642,18 @@ int32_t b200_gmres_solve(b200_gmres* gm, b200_linop* op, const double* b, double
   const b200_gmres_opts& o = gm->opts;
   const int G = gm->G;
   const int orth = o.orth;
-  const int check_every = o.check_every > 0 ? o.check_every : 8;
+  // operators that run host code between kernels (callbacks; preconditioners synchronise per apply anyway) must never be
+  // handed the operand of an iteration that a finished solve skipped: poll the device status every iteration for them
+  const bool host_op = op->kind == LINOP_CALLBACK || (op->kind == LINOP_PROBLEM && op->prob->kind == B200_PROB_CALLBACK) ||
+                       (gm->Pl && gm->Pl->kind == LINOP_CALLBACK) || (gm->Pr && gm->Pr->kind == LINOP_CALLBACK);
+  const int check_every = host_op ? 1 : (o.check_every > 0 ? o.check_every : 8);
   // Gram-Schmidt block: -1 => as many vectors as fit in ~64 MB (half of the 126 MB L2), at most JT; 0 => unblocked
   int blk = o.block;
   if (blk < 0) blk = (int)std::min<int64_t>(JT, std::max<int64_t>(1, ((int64_t)64 << 20) / (8 * n)));
   if (blk > JT) blk = JT;
   if (orth == B200_ORTH_MGS) blk = 0;
   // resident engine: built-in Brusselator operator with the exact JVP, even cell count, one CTA per SM holds its rows
-  bool resident = false, resident3 = false;
+  bool resident = false, resident3 = false, r3g = false;
   int rs_G = 0, rs_cpc = 0, rs_passes = (orth == B200_ORTH_CGS2) ? 2 : 1;
   int64_t rs_NC = 0;
   size_t rs_smem = 0;
@@ -1422,11 +1675,13 @@ int32_t b200_gmres_solve(b200_gmres* gm, b200_linop* op, const double* b, double
     const bool wanted = (o.engine == B200_ENGINE_RESIDENT) || (o.engine == B200_ENGINE_AUTO && n >= 200000);
     if (fits && wanted) {
       resident = true;
-      static const int r3env = getenv("B200_RS3") ? atoi(getenv("B200_RS3")) : 1;  // B200_RS3=0: two-stage kernel (A/B runs)
+      static const int r3env = getenv("B200_RS3") ? atoi(getenv("B200_RS3")) : 2;  // A/B runs: 0 two-stage kernel, 1 round-1 three-stage kernel, 2 r3g
       resident3 = r3env != 0 && (2 * cpc <= (int64_t)R3_ROWS * R3_THREADS) && (rs_smem + R3_ANNEX_BYTES + 2048 <= ctx->smem_optin);
       if (resident3) rs_smem += R3_ANNEX_BYTES;
       CUDA_TRY(ctx, cudaFuncSetAttribute(resident_arnoldi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem));
       CUDA_TRY(ctx, cudaFuncSetAttribute(resident3_arnoldi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem));
+      CUDA_TRY(ctx, cudaFuncSetAttribute(resident3g_arnoldi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem));
+      r3g = resident3 && r3env >= 2;
     } else if (o.engine == B200_ENGINE_RESIDENT) {
       return ctx->fail(B200_ERR_UNSUPPORTED, "resident GMRES engine: problem does not fit (needs an even cell count and <= 7168 cells per SM)", __FILE__, __LINE__);
     }
@@ -1449,6 +1704,7 @@ int32_t b200_gmres_solve(b200_gmres* gm, b200_linop* op, const double* b, double
   init.atol = o.atol;
   init.rtol = o.rtol;
   *gm->h_state = init;
+  CUDA_TRY(ctx, cudaMemsetAsync(gm->d_bar, 0, 4 * sizeof(unsigned), ctx->stream));  // resident engine: exchange-timeout flag of a previous solve
   CUDA_TRY(ctx, cudaMemcpyAsync(gm->d_state, gm->h_state, sizeof(GmresState), cudaMemcpyHostToDevice, ctx->stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // h_state is reused as the read-back buffer below
 
@@ -1488,11 +1744,18 @@ int32_t b200_gmres_solve(b200_gmres* gm, b200_linop* op, const double* b, double
 
     int k = 0;
     int cycle_status = 0;
-    for (;;) {
+    if (host_op) {  // ||r0|| <= tol (or a non-finite start): do not call user code at all
+      B200_TRY(gm_fetch_state(gm));
+      cycle_status = gm->h_state->status;
+    }
+    while (cycle_status == 0) {
       ++k;
       B200_TRY(gm_reserve(gm, k + 1));
       rc = gm_ensure_vector(gm, k);
-      if (rc == B200_ERR_NOMEM || k + 40 > 6000) { oom = 1; --k; break; }  // 48 KB of coefficients in shared memory
+      // The basis cannot grow any further (device memory, or the GM_KCAP coefficients the update / back-substitution
+      // kernels stage in shared memory): Krylov.jl would keep going up to itmax = n; the closest thing that still
+      // converges is an implicit restart from the current iterate.  Only a basis too small to be useful is a failure.
+      if (rc == B200_ERR_NOMEM || k + 40 > GM_KCAP) { oom = 1; --k; break; }
       B200_TRY(rc);
       if (resident) {
         // one cooperative kernel: JVP -> (iterated) MGS with TMA-staged basis -> norm -> Givens -> v_{k+1}
@@ -1516,12 +1779,14 @@ int32_t b200_gmres_solve(b200_gmres* gm, b200_linop* op, const double* b, double
         { static const int li = getenv("B200_RS_LATE") ? atoi(getenv("B200_RS_LATE")) : 0; RP.late_issue = (li == 1) ? 1 : 0; }  // A/B knob of the two-stage kernel: prefetch after the exchange
         RP.slots = gm->d_slots; RP.epoch_base = gm->ll_epoch; RP.err = reinterpret_cast<int*>(gm->d_bar + 1);
         gm->ll_epoch += (unsigned)(rs_passes * k + 2);
-        RP.h = gm->d_h; RP.R = gm->d_R; RP.cs = gm->d_cs; RP.sn = gm->d_sn; RP.z = gm->d_z;
+        RP.h = gm->d_h; RP.gsub = gm->d_gsub; RP.R = gm->d_R; RP.cs = gm->d_cs; RP.sn = gm->d_sn; RP.z = gm->d_z;
         RP.hraw = (gm->d_hraw && (int64_t)k * (k + 3) / 2 <= gm->hraw_cap) ? gm->d_hraw : nullptr;
         RP.st = gm->d_state;
         void* args[] = {&RP};
         if (ctx->prof_on) ctx->prof_begin(B200_KID_RESIDENT, (rs_passes * (double)k + 3.0) * Bv);
-        if (resident3)
+        if (r3g)
+          CUDA_TRY(ctx, cudaLaunchCooperativeKernel((const void*)resident3g_arnoldi_kernel, dim3(rs_G), dim3(R3_THREADS), args, rs_smem, ctx->stream));
+        else if (resident3)
           CUDA_TRY(ctx, cudaLaunchCooperativeKernel((const void*)resident3_arnoldi_kernel, dim3(rs_G), dim3(R3_THREADS), args, rs_smem, ctx->stream));
         else
           CUDA_TRY(ctx, cudaLaunchCooperativeKernel((const void*)resident_arnoldi_kernel, dim3(rs_G), dim3(RS_THREADS), args, rs_smem, ctx->stream));
@@ -1592,8 +1857,10 @@ int32_t b200_gmres_solve(b200_gmres* gm, b200_linop* op, const double* b, double
     }
     if (oom) {
       B200_TRY(gm_fetch_state(gm));
-      if (gm->h_state->status != 0) { cycle_status = gm->h_state->status; k = gm->h_state->k; oom = 0; }
+      if (gm->h_state->status != 0) { cycle_status = gm->h_state->status; k = gm->h_state->k; }
+      else if (k >= 16) { cycle_status = -1; }  // implicit restart with the basis that fits
       else { cycle_status = B200_LS_OUT_OF_MEMORY; }
+      oom = 0;
     }
     nmatvec += k;
     iters_total += k;
@@ -1638,6 +1905,11 @@ int32_t b200_gmres_solve(b200_gmres* gm, b200_linop* op, const double* b, double
     break;
   }
   B200_TRY(gm_fetch_state(gm));
+  if (resident && final_status == B200_LS_NONFINITE) {  // tell an exchange time-out (bounded spin) from a numerical NaN / Inf
+    unsigned flag = 0;
+    CUDA_TRY(ctx, cudaMemcpy(&flag, gm->d_bar + 1, sizeof(unsigned), cudaMemcpyDeviceToHost));
+    if (flag) ctx->fail(B200_OK, "resident GMRES engine: a cross-CTA exchange timed out (bounded spin); the solve is reported as B200_LS_NONFINITE", __FILE__, __LINE__);
+  }
   st_local.status = final_status;
   st_local.iters = (int32_t)iters_total;
   st_local.nmatvec = nmatvec;

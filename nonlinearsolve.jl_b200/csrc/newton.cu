@@ -118,6 +118,7 @@ void b200_newton_opts_default(b200_newton_opts* o) {
 }
 
 int32_t b200_newton_destroy(b200_newton* nw) {
+  B200_DEVICE_GUARD(nw ? nw->ctx : nullptr);
   if (!nw) return B200_OK;
   b200_ctx* ctx = nw->ctx;
   cudaStreamSynchronize(ctx->stream);
@@ -132,6 +133,7 @@ int32_t b200_newton_destroy(b200_newton* nw) {
 }
 
 int32_t b200_newton_create(b200_problem* prob, const b200_newton_opts* opts, b200_newton** out) {
+  B200_DEVICE_GUARD(prob ? prob->ctx : nullptr);
   b200_ctx* ctx = prob->ctx;
   B200_REQUIRE(ctx, opts && out, "newton_create: bad arguments");
   B200_REQUIRE(ctx, opts->tr_scheme >= B200_TR_SIMPLE && opts->tr_scheme <= B200_TR_FAN, "newton_create: unknown radius update scheme");
@@ -200,6 +202,7 @@ int32_t b200_newton_create(b200_problem* prob, const b200_newton_opts* opts, b20
 
 // reinit!(cache, u0): everything __init computes from u0 (solve.jl:191-284; termination_conditions.jl:134-179)
 int32_t b200_newton_reinit(b200_newton* nw, const double* u0_dev) {
+  B200_DEVICE_GUARD(nw ? nw->ctx : nullptr);
   b200_ctx* ctx = nw->ctx;
   const int64_t n = nw->n;
   const b200_newton_opts& o = nw->o;
@@ -540,6 +543,7 @@ static int32_t newton_step_inner(b200_newton* nw) {
 }
 
 int32_t b200_newton_step(b200_newton* nw, int32_t* terminated_host) {
+  B200_DEVICE_GUARD(nw ? nw->ctx : nullptr);
   b200_ctx* ctx = nw->ctx;
   B200_REQUIRE(ctx, nw->initialised, "newton_step before newton_reinit");
   if (!(nw->force_stop || nw->nsteps >= nw->maxiters)) {  // not_terminated  abstract_types.jl:722-724
@@ -561,6 +565,7 @@ int32_t b200_newton_result_get(b200_newton* nw, b200_newton_result* r) {
 }
 
 int32_t b200_newton_solve(b200_newton* nw, b200_newton_result* result) {
+  B200_DEVICE_GUARD(nw ? nw->ctx : nullptr);
   b200_ctx* ctx = nw->ctx;
   B200_REQUIRE(ctx, nw->initialised, "newton_solve before newton_reinit");
   while (!nw->force_stop && nw->nsteps < nw->maxiters) {
@@ -598,6 +603,7 @@ int32_t b200_newton_trace(b200_newton* nw, b200_trace_rec* recs, int32_t cap, in
 }
 
 int32_t b200_newton_solve_host(b200_newton* nw, const double* u0_host, double* u_host, double* resid_host, b200_newton_result* result) {
+  B200_DEVICE_GUARD(nw ? nw->ctx : nullptr);
   b200_ctx* ctx = nw->ctx;
   const size_t bytes = sizeof(double) * nw->n;
   CUDA_TRY(ctx, cudaMemcpyAsync(nw->u, u0_host, bytes, cudaMemcpyHostToDevice, ctx->stream));

@@ -308,18 +308,22 @@ int32_t ensure_fd_scratch(b200_problem* p, int copies) {
 
 extern "C" {
 int32_t b200_problem_create_bruss2d(b200_ctx* ctx, int32_t N, double A, double B, double alpha, b200_problem** prob) {
+  B200_DEVICE_GUARD(ctx);
   return create_bruss(ctx, 2, N, A, B, alpha, prob);
 }
 int32_t b200_problem_create_bruss3d(b200_ctx* ctx, int32_t N, double A, double B, double alpha, b200_problem** prob) {
+  B200_DEVICE_GUARD(ctx);
   return create_bruss(ctx, 3, N, A, B, alpha, prob);
 }
 int32_t b200_problem_create_quadratic(b200_ctx* ctx, int64_t n, double p, b200_problem** prob) {
+  B200_DEVICE_GUARD(ctx);
   B200_REQUIRE(ctx, n > 0, "n must be positive");
   B200_TRY(create_common(ctx, prob, B200_PROB_QUADRATIC, 0, n));
   (*prob)->p = p;
   return B200_OK;
 }
 int32_t b200_problem_create_tridiag_quad(b200_ctx* ctx, int64_t n, const double* p_dev, b200_problem** prob) {
+  B200_DEVICE_GUARD(ctx);
   B200_REQUIRE(ctx, n > 0 && p_dev, "n must be positive and p_dev non-null");
   B200_TRY(create_common(ctx, prob, B200_PROB_TRIDIAG_QUAD, 0, n));
   double* copy = nullptr;
@@ -330,6 +334,7 @@ int32_t b200_problem_create_tridiag_quad(b200_ctx* ctx, int64_t n, const double*
 }
 int32_t b200_problem_create_callback(b200_ctx* ctx, int64_t n, b200_residual_cb f, b200_jvp_cb jvp, b200_jvp_cb vjp, void* user,
                                      b200_problem** prob) {
+  B200_DEVICE_GUARD(ctx);
   B200_REQUIRE(ctx, n > 0 && f, "callback problem needs n > 0 and a residual callback");
   B200_TRY(create_common(ctx, prob, B200_PROB_CALLBACK, 0, n));
   (*prob)->f_cb = f;
@@ -339,11 +344,13 @@ int32_t b200_problem_create_callback(b200_ctx* ctx, int64_t n, b200_residual_cb 
   return B200_OK;
 }
 int32_t b200_problem_set_jac(b200_problem* prob, b200_jac_cb jac_dense, b200_jac_cb jac_nzval) {
+  B200_DEVICE_GUARD(prob ? prob->ctx : nullptr);
   prob->jac_dense_cb = jac_dense;
   prob->jac_nzval_cb = jac_nzval;
   return B200_OK;
 }
 int32_t b200_problem_set_jac_prototype(b200_problem* prob, const int64_t* colptr, const int64_t* rowval, int32_t index_base) {
+  B200_DEVICE_GUARD(prob ? prob->ctx : nullptr);
   b200_ctx* ctx = prob->ctx;
   B200_REQUIRE(ctx, colptr && rowval && (index_base == 0 || index_base == 1), "set_jac_prototype: bad arguments");
   const int64_t n = prob->n, nnz = colptr[n] - index_base;
@@ -359,6 +366,7 @@ int32_t b200_problem_set_jac_prototype(b200_problem* prob, const int64_t* colptr
   return B200_OK;
 }
 int32_t b200_problem_destroy(b200_problem* p) {
+  B200_DEVICE_GUARD(p ? p->ctx : nullptr);
   if (!p) return B200_OK;
   cudaStreamSynchronize(p->ctx->stream);
   if (p->kind != B200_PROB_CALLBACK && p->pvec) cudaFree(const_cast<double*>(p->pvec));
@@ -371,6 +379,7 @@ int32_t b200_problem_n(b200_problem* p, int64_t* n) { *n = p->n; return B200_OK;
 int32_t b200_problem_set_AB(b200_problem* p, double A, double B) { p->A = A; p->B = B; return B200_OK; }
 
 int32_t b200_problem_u0(b200_problem* p, int32_t mode, double* u) {
+  B200_DEVICE_GUARD(p ? p->ctx : nullptr);
   b200_ctx* ctx = p->ctx;
   if (p->kind == B200_PROB_BRUSS2D || p->kind == B200_PROB_BRUSS3D) {
     const int dim = p->kind == B200_PROB_BRUSS2D ? 2 : 3;
@@ -381,9 +390,13 @@ int32_t b200_problem_u0(b200_problem* p, int32_t mode, double* u) {
   return b200_fill(ctx, p->n, 1.0, u);
 }
 
-int32_t b200_residual(b200_problem* p, const double* u, double* du) { return b200i_residual_norm(p, u, du, nullptr); }
+int32_t b200_residual(b200_problem* p, const double* u, double* du) {
+  B200_DEVICE_GUARD(p ? p->ctx : nullptr);
+  return b200i_residual_norm(p, u, du, nullptr);
+}
 
 int32_t b200_jvp(b200_problem* p, const double* u, const double* v, double* Jv) {
+  B200_DEVICE_GUARD(p ? p->ctx : nullptr);
   b200_ctx* ctx = p->ctx;
   switch (p->kind) {
     case B200_PROB_BRUSS2D:
@@ -403,6 +416,7 @@ int32_t b200_jvp(b200_problem* p, const double* u, const double* v, double* Jv) 
 }
 
 int32_t b200_vjp(b200_problem* p, const double* u, const double* w, double* JTw) {
+  B200_DEVICE_GUARD(p ? p->ctx : nullptr);
   b200_ctx* ctx = p->ctx;
   switch (p->kind) {
     case B200_PROB_BRUSS2D:
@@ -422,6 +436,7 @@ int32_t b200_vjp(b200_problem* p, const double* u, const double* w, double* JTw)
 }
 
 int32_t b200_residual_jvp(b200_problem* p, const double* u, const double* v, double* du, double* Jv) {
+  B200_DEVICE_GUARD(p ? p->ctx : nullptr);
   if (p->kind == B200_PROB_BRUSS2D || p->kind == B200_PROB_BRUSS3D) return launch_bruss<M_RESID | M_JVP>(p, u, v, du, Jv, nullptr, nullptr);
   B200_TRY(b200_residual(p, u, du));
   return b200_jvp(p, u, v, Jv);
@@ -429,6 +444,7 @@ int32_t b200_residual_jvp(b200_problem* p, const double* u, const double* v, dou
 
 // (f(u + eps v) - f(u)) / eps with FiniteDiff.jl's forward step; for the stencils both evaluations share one neighbourhood load.
 int32_t b200_jvp_fd(b200_problem* p, const double* u, const double* v, double* Jv) {
+  B200_DEVICE_GUARD(p ? p->ctx : nullptr);
   b200_ctx* ctx = p->ctx;
   double* d_dot = ctx->d_scalars + 8;
   double* d_eps = ctx->d_scalars + 9;

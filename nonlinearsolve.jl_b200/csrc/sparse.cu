@@ -98,6 +98,7 @@ void b200i_sparse_jac_csr(b200_sparse_jac* sj, const int64_t** rowptr, const int
 
 extern "C" {
 int32_t b200_pattern_nnz(b200_problem* p, int64_t* nnz) {
+  B200_DEVICE_GUARD(p ? p->ctx : nullptr);
   if (p->proto_colptr) { *nnz = p->proto_colptr[p->n]; return B200_OK; }  // user jac_prototype
   B200_REQUIRE(p->ctx, p->kind != B200_PROB_CALLBACK, "pattern: callback problems must bring their own jac_prototype");
   int64_t rows[16], total = 0;
@@ -106,6 +107,7 @@ int32_t b200_pattern_nnz(b200_problem* p, int64_t* nnz) {
   return B200_OK;
 }
 int32_t b200_pattern(b200_problem* p, int32_t base, int64_t* colptr, int64_t* rowval) {
+  B200_DEVICE_GUARD(p ? p->ctx : nullptr);
   if (p->proto_colptr) {
     for (int64_t c = 0; c <= p->n; ++c) colptr[c] = p->proto_colptr[c] + base;
     for (int64_t e = 0; e < p->proto_colptr[p->n]; ++e) rowval[e] = p->proto_rowval[e] + base;
@@ -168,6 +170,7 @@ int32_t b200_coloring_column(int64_t n, const int64_t* colptr, const int64_t* ro
 }
 
 int32_t b200_sparse_jac_destroy(b200_sparse_jac* sj) {
+  B200_DEVICE_GUARD(sj ? sj->ctx : nullptr);
   if (!sj) return B200_OK;
   cudaStreamSynchronize(sj->ctx->stream);
   cudaFree(sj->d_colptr); cudaFree(sj->d_rowval); cudaFree(sj->d_rowptr); cudaFree(sj->d_csr_col); cudaFree(sj->d_csr_map);
@@ -178,6 +181,7 @@ int32_t b200_sparse_jac_destroy(b200_sparse_jac* sj) {
 
 int32_t b200_sparse_jac_create(b200_problem* prob, const int64_t* colptr, const int64_t* rowval, int32_t base, const int64_t* colors,
                                int64_t ncolors, b200_sparse_jac** out) {
+  B200_DEVICE_GUARD(prob ? prob->ctx : nullptr);
   b200_ctx* ctx = prob->ctx;
   const int64_t n = prob->n;
   B200_REQUIRE(ctx, colptr && rowval && colors && ncolors > 0 && out, "sparse_jac_create: bad arguments");
@@ -217,6 +221,7 @@ int32_t b200_sparse_jac_create(b200_problem* prob, const int64_t* colptr, const 
 
 // DI.jacobian! with AutoSparse(AutoForwardDiff): one exact JVP per colour + decompression (jacobian.jl:244-247)
 int32_t b200_sparse_jac_fill(b200_sparse_jac* sj, const double* u, double* nzval) {
+  B200_DEVICE_GUARD(sj ? sj->ctx : nullptr);
   b200_ctx* ctx = sj->ctx;
   if (sj->prob->jac_nzval_cb) B200_TRY(b200i_sync_for_callback(ctx));
   if (sj->prob->jac_nzval_cb)  // jac!(J::SparseMatrixCSC, u, p) writes nzval directly
@@ -233,6 +238,7 @@ int32_t b200_sparse_jac_fill(b200_sparse_jac* sj, const double* u, double* nzval
 }
 
 int32_t b200_spmv(b200_sparse_jac* sj, const double* nzval, const double* x, double* y) {
+  B200_DEVICE_GUARD(sj ? sj->ctx : nullptr);
   b200_ctx* ctx = sj->ctx;
   LAUNCH(ctx, spmv_rows_kernel, (int)((sj->n + ST - 1) / ST), ST, 0, sj->n, (const int64_t*)sj->d_rowptr, (const int64_t*)sj->d_csr_col,
          (const int64_t*)sj->d_csr_map, nzval, x, y);
@@ -240,6 +246,7 @@ int32_t b200_spmv(b200_sparse_jac* sj, const double* nzval, const double* x, dou
   return B200_OK;
 }
 int32_t b200_spmv_t(b200_sparse_jac* sj, const double* nzval, const double* x, double* y) {
+  B200_DEVICE_GUARD(sj ? sj->ctx : nullptr);
   b200_ctx* ctx = sj->ctx;
   LAUNCH(ctx, spmv_cols_kernel, (int)((sj->n + ST - 1) / ST), ST, 0, sj->n, (const int64_t*)sj->d_colptr, (const int64_t*)sj->d_rowval, nzval,
          x, y);
@@ -247,6 +254,7 @@ int32_t b200_spmv_t(b200_sparse_jac* sj, const double* nzval, const double* x, d
   return B200_OK;
 }
 int32_t b200_sparse_jac_linop(b200_sparse_jac* sj, const double* nzval, b200_linop** out) {
+  B200_DEVICE_GUARD(sj ? sj->ctx : nullptr);
   b200_linop* op = new b200_linop();
   memset(op, 0, sizeof(*op));
   op->ctx = sj->ctx; op->kind = LINOP_SPARSE_JAC; op->n = sj->n; op->sj = sj; op->nzval = nzval;
