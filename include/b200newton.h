@@ -80,18 +80,29 @@ enum {
 enum { B200_PROB_BRUSS2D = 1, B200_PROB_BRUSS3D = 2, B200_PROB_QUADRATIC = 3, B200_PROB_TRIDIAG_QUAD = 4, B200_PROB_CALLBACK = 5 };
 enum { B200_ORTH_MGS = 0, B200_ORTH_CGS = 1, B200_ORTH_CGS2 = 2 };
 enum { B200_ENGINE_AUTO = 0, B200_ENGINE_MULTIKERNEL = 1, B200_ENGINE_RESIDENT = 2 };
-enum { B200_LINSOLVE_GMRES = 0, B200_LINSOLVE_DENSE_LU = 1, B200_LINSOLVE_SPARSE_GMRES = 2 };
+/* SPARSE_LU: what NewtonRaphson() does on a sparse jac_prototype (linsolve = nothing -> LinearSolve's sparse direct default,
+   KLU/UMFPACK; sparsity_tests__item1.jl:54-93, operator_jacobian.jl:22): coloured sparse Jacobian + a direct factorisation
+   (reverse Cuthill-McKee ordering + banded LU with partial pivoting on the device, b200_sparse_lu_*) */
+enum { B200_LINSOLVE_GMRES = 0, B200_LINSOLVE_DENSE_LU = 1, B200_LINSOLVE_SPARSE_GMRES = 2, B200_LINSOLVE_SPARSE_LU = 3 };
 enum { B200_JVP_EXACT = 0, B200_JVP_FINITE_DIFF = 1 };
 enum { B200_GLOBALIZATION_NONE = 0, B200_GLOBALIZATION_TRUST_REGION = 1, B200_GLOBALIZATION_LINESEARCH = 2 };
 /* descent: NewtonDescent (descent/newton.jl) or DampedNewtonDescent + SwitchedEvolutionRelaxation = PseudoTransient
    (descent/damped_newton.jl:234-340, NonlinearSolveFirstOrder/src/pseudo_transient.jl:37-170): (J + I/alpha) du = -f */
-/* RadiusUpdateSchemes.{Simple, NLsolve, NocedalWright, Hei, Yuan, Fan} (Bastin is not offered: its delta-u cache is never
-   filled in the reference, trust_region.jl:484-503) */
-enum { B200_TR_SIMPLE = 0, B200_TR_NLSOLVE = 1, B200_TR_NOCEDAL_WRIGHT = 2, B200_TR_HEI = 3, B200_TR_YUAN = 4, B200_TR_FAN = 5 };
+/* RadiusUpdateSchemes.{Simple, NLsolve, NocedalWright, Hei, Yuan, Fan, Bastin}.  Bastin (trust_region.jl:484-503) reads a
+   `δu_cache` that the reference allocates with `similar(u)` and never writes; the library uses the step just taken, which is
+   what the retrospective scheme of the cited paper evaluates. */
+enum { B200_TR_SIMPLE = 0, B200_TR_NLSOLVE = 1, B200_TR_NOCEDAL_WRIGHT = 2, B200_TR_HEI = 3, B200_TR_YUAN = 4, B200_TR_FAN = 5, B200_TR_BASTIN = 6 };
 enum { B200_DESCENT_NEWTON = 0, B200_DESCENT_PSEUDO_TRANSIENT = 1 };
-enum { B200_PRECOND_NONE = 0, B200_PRECOND_BLOCK_JACOBI_LEFT = 1, B200_PRECOND_BLOCK_JACOBI_RIGHT = 2 };
+/* built-in preconditioners (LinearSolve `precs(A, p)`, large_systems.md:244-316): inverse of the 2x2 species blocks, or one
+   geometric-multigrid V-cycle of the Brusselator Jacobian (the tutorial's AlgebraicMultigrid ruge_stuben / smoothed_aggregation) */
+enum { B200_PRECOND_NONE = 0, B200_PRECOND_BLOCK_JACOBI_LEFT = 1, B200_PRECOND_BLOCK_JACOBI_RIGHT = 2,
+       B200_PRECOND_MULTIGRID_LEFT = 3, B200_PRECOND_MULTIGRID_RIGHT = 4 };
 enum { B200_FORCING_NONE = 0, B200_FORCING_EW2 = 1 };
-enum { B200_TERM_ABS_NORM_SAFE_BEST = 0, B200_TERM_ABS_NORM = 1, B200_TERM_ABS_NORM_SAFE = 2 };
+/* termination modes (public.jl:300-407, termination_conditions.jl:243-372); `du` = f(u).  The three AbsNorm modes keep
+   their round-1 values; Norm / Rel / RelNorm / Abs / RelNormSafe / RelNormSafeBest follow */
+enum { B200_TERM_ABS_NORM_SAFE_BEST = 0, B200_TERM_ABS_NORM = 1, B200_TERM_ABS_NORM_SAFE = 2, B200_TERM_NORM = 3, B200_TERM_REL = 4,
+       B200_TERM_REL_NORM = 5, B200_TERM_ABS = 6, B200_TERM_REL_NORM_SAFE = 7, B200_TERM_REL_NORM_SAFE_BEST = 8 };
+enum { B200_NORM_INF = 0, B200_NORM_L2 = 1 }; /* internalnorm: maximum(abs, .) (NonlinearProblem default) or norm(., 2) */
 enum { B200_U0_REFERENCE = 0, B200_U0_PERTURBED_Z = 1 };
 enum { B200_ORDER_NATURAL = 0, B200_ORDER_LARGEST_FIRST = 1 };
 
@@ -168,6 +179,9 @@ typedef struct b200_newton_opts {
   int32_t descent; /* B200_DESCENT_* */
   int32_t tr_scheme; /* B200_TR_*: RadiusUpdateSchemes (trust_region.jl:431-509); thresholds/factors of 0 take the scheme's defaults (:330-384) */
   double pt_alpha_initial; /* PseudoTransient(alpha_initial = 1e-3); 0 => 1e-3 */
+  double maxtime;          /* seconds of accumulated step time after which the solve stops with MaxTime (NonlinearSolveBase/src/solve.jl:847-855); <= 0 => none */
+  int32_t term_norm;       /* B200_NORM_*: the termination mode's internalnorm */
+  int32_t term_max_stalled_steps; /* Safe modes: window of the step-norm stall test; 0 => 32 (the solver default's value), < 0 => test disabled */
 } b200_newton_opts;
 
 typedef struct b200_newton_result {
@@ -284,6 +298,11 @@ int32_t b200_gmres_set_precond(b200_gmres* gm, b200_linop* left_inv, b200_linop*
 /* Built-in block-Jacobi preconditioner of the Brusselator Jacobian at u: inverse of the 2x2 species blocks on the diagonal
  * (large_systems.md:244-316 uses an incomplete LU / multigrid of the same matrix through `precs`). */
 int32_t b200_linop_block_jacobi(b200_problem* prob, const double* u, b200_linop** out);
+/* Built-in preconditioner by kind (B200_PRECOND_*, the LEFT / RIGHT values of a family name the same operator): block-Jacobi
+ * or one multigrid V-cycle of the Brusselator Jacobian at u — coarsening by the prime factors of N down to one cell,
+ * damped block-Jacobi smoothing (2 pre + 2 post sweeps), trilinear / full-weighting transfers for factor 2 and aggregation
+ * for odd factors, rediscretised coarse operators, exact 2x2 solve on the last level.  The operator applies M^-1. */
+int32_t b200_linop_precond(b200_problem* prob, const double* u, int32_t kind, b200_linop** out);
 int32_t b200_gmres_solve(b200_gmres* gm, b200_linop* op, const double* b, double* x_inout, b200_gmres_stats* stats_host);
 
 /* ---------------------------------------------------------------- dense fallback (a5) */
@@ -305,6 +324,18 @@ int32_t b200_sparse_jac_fill(b200_sparse_jac* sj, const double* u, double* nzval
 int32_t b200_sparse_jac_linop(b200_sparse_jac* sj, const double* nzval_dev, b200_linop** op);
 int32_t b200_spmv(b200_sparse_jac* sj, const double* nzval_dev, const double* x, double* y);   /* y = J x  */
 int32_t b200_spmv_t(b200_sparse_jac* sj, const double* nzval_dev, const double* x, double* y); /* y = J' x */
+
+/* ---------------------------------------------------------------- sparse direct solve (a6; small 2D / 3D grids)
+ * Reverse Cuthill-McKee ordering of the pattern (host, once), then LAPACK-gbtrf-style banded LU with partial pivoting and
+ * the two banded triangular solves on the device.  Memory n * (2 kl + ku + 1) doubles: B200_ERR_NOMEM when the band does not
+ * fit (3D N = 100: use GMRES on the assembled matrix, as the reference's own GPU test does). */
+typedef struct b200_sparse_lu b200_sparse_lu;
+int32_t b200_sparse_lu_create(b200_ctx* ctx, int64_t n, const int64_t* colptr_host, const int64_t* rowval_host, int32_t index_base,
+                              b200_sparse_lu** lu);
+int32_t b200_sparse_lu_destroy(b200_sparse_lu* lu);
+int32_t b200_sparse_lu_bandwidth(b200_sparse_lu* lu, int64_t* kl_host, int64_t* ku_host);
+int32_t b200_sparse_lu_factor(b200_sparse_lu* lu, const double* nzval_dev, int32_t* info_host);   /* info > 0: zero pivot at that column (1-based) */
+int32_t b200_sparse_lu_solve(b200_sparse_lu* lu, const double* b_dev, double* x_dev);            /* x = A^-1 b (x may alias b) */
 
 /* ---------------------------------------------------------------- Newton driver (a4, a7, a8, a9) */
 void b200_newton_opts_default(b200_newton_opts* opts);
@@ -337,6 +368,35 @@ int32_t b200_ens_destroy(b200_ensemble* ens);
 int32_t b200_ens_solve(b200_ensemble* ens, const double* u0_dev, const double* A_dev, const double* B_dev, double* u_out_dev,
                        double* resid_inf_dev, int32_t* retcodes_dev, int32_t* nsteps_dev, int32_t* njvp_dev,
                        b200_ens_result* result_host);
+
+/* ---------------------------------------------------------------- collective step of the ensemble path
+ * The ensemble shards by contiguous trajectory blocks, rank r owning [r K/R, (r+1) K/R): no collective on the data path.
+ * After the solve: ONE all-gather of the solutions (EnsembleSolution.u in trajectory order on every rank) and one
+ * all-reduce of the status counters, NCCL over NVLink / NVSwitch, enqueued on the context's stream (ordered after the solve
+ * kernel, no host synchronisation in between).  Replaces what SciMLBase's `__solve(::EnsembleProblem, ...)` does when it
+ * collects the per-trajectory solutions (test/PolyAlgorithms/core_tests__item6.jl:14-20); a host without torch.distributed
+ * (the Julia glue, tests/abi_c) runs BASELINE config 5 on 8 GPUs through these calls.  NCCL is bound at run time
+ * (dlopen of libnccl.so.2; B200_ERR_UNSUPPORTED when it cannot be loaded). */
+typedef struct b200_comm b200_comm;
+#define B200_NCCL_UNIQUE_ID_BYTES 128
+int32_t b200_nccl_version(int32_t* version_host);
+/* one process per GPU: rank 0 creates the id, the host language ships the 128 bytes to the other ranks (MPI / sockets /
+   a file), every rank calls b200_nccl_init with the same id */
+int32_t b200_nccl_unique_id(void* id128_host);
+int32_t b200_nccl_init(b200_ctx* ctx, int32_t nranks, int32_t rank, const void* unique_id128_host, b200_comm** comm);
+/* single process driving ndev devices (ncclCommInitAll): comms[i] belongs to ctxs[i]; wrap the per-device collective calls
+   of one step in b200_nccl_group_start / _end */
+int32_t b200_nccl_init_all(b200_ctx* const* ctxs, int32_t ndev, b200_comm** comms);
+int32_t b200_nccl_group_start(void);
+int32_t b200_nccl_group_end(void);
+int32_t b200_nccl_destroy(b200_comm* comm);
+/* u_all[r * count_local + i] = u_local[i] of rank r (count_local doubles per rank, equal on all ranks) */
+int32_t b200_ens_allgather(b200_comm* comm, const double* u_local_dev, int64_t count_local, double* u_all_dev);
+/* sums of nprob / nsuccess / total_nsteps / total_njvp, maxima of max_nsteps / worst_resid_inf over the ranks;
+   _begin enqueues (usable inside a group), _finish synchronises the stream and fills the struct */
+int32_t b200_ens_allreduce_stats_begin(b200_comm* comm, const b200_ens_result* local_host);
+int32_t b200_ens_allreduce_stats_finish(b200_comm* comm, b200_ens_result* global_host);
+int32_t b200_ens_allreduce_stats(b200_comm* comm, const b200_ens_result* local_host, b200_ens_result* global_host);
 
 #ifdef __cplusplus
 }

@@ -21,14 +21,15 @@ LS_SOLVED, LS_MAXITERS, LS_BREAKDOWN, LS_NONFINITE, LS_OUT_OF_MEMORY = 1, 2, 3, 
 PROB_BRUSS2D, PROB_BRUSS3D, PROB_QUADRATIC, PROB_TRIDIAG_QUAD, PROB_CALLBACK = 1, 2, 3, 4, 5
 ORTH_MGS, ORTH_CGS, ORTH_CGS2 = 0, 1, 2
 ENGINE_AUTO, ENGINE_MULTIKERNEL, ENGINE_RESIDENT = 0, 1, 2
-LINSOLVE_GMRES, LINSOLVE_DENSE_LU, LINSOLVE_SPARSE_GMRES = 0, 1, 2
+LINSOLVE_GMRES, LINSOLVE_DENSE_LU, LINSOLVE_SPARSE_GMRES, LINSOLVE_SPARSE_LU = 0, 1, 2, 3
 JVP_EXACT, JVP_FINITE_DIFF = 0, 1
 GLOB_NONE, GLOB_TRUST_REGION, GLOB_LINESEARCH = 0, 1, 2
-PRECOND_NONE, PRECOND_BLOCK_JACOBI_LEFT, PRECOND_BLOCK_JACOBI_RIGHT = 0, 1, 2
+PRECOND_NONE, PRECOND_BLOCK_JACOBI_LEFT, PRECOND_BLOCK_JACOBI_RIGHT, PRECOND_MULTIGRID_LEFT, PRECOND_MULTIGRID_RIGHT = 0, 1, 2, 3, 4
 DESCENT_NEWTON, DESCENT_PSEUDO_TRANSIENT = 0, 1
-TR_SIMPLE, TR_NLSOLVE, TR_NOCEDAL_WRIGHT, TR_HEI, TR_YUAN, TR_FAN = range(6)
+TR_SIMPLE, TR_NLSOLVE, TR_NOCEDAL_WRIGHT, TR_HEI, TR_YUAN, TR_FAN, TR_BASTIN = range(7)
 FORCING_NONE, FORCING_EW2 = 0, 1
-TERM_ABS_NORM_SAFE_BEST, TERM_ABS_NORM, TERM_ABS_NORM_SAFE = 0, 1, 2
+TERM_ABS_NORM_SAFE_BEST, TERM_ABS_NORM, TERM_ABS_NORM_SAFE, TERM_NORM, TERM_REL, TERM_REL_NORM, TERM_ABS, TERM_REL_NORM_SAFE, TERM_REL_NORM_SAFE_BEST = range(9)
+NORM_INF, NORM_L2 = 0, 1
 U0_REFERENCE, U0_PERTURBED_Z = 0, 1
 ORDER_NATURAL, ORDER_LARGEST_FIRST = 0, 1
 KID_NAMES = ["jvp", "multidot", "update", "mgs", "normalize", "residual", "givens", "resident", "lu_panel", "lu_gemm", "lu_other", "sparse"]
@@ -55,7 +56,7 @@ class NewtonOpts(C.Structure):
                 ("tr_shrink_factor", C.c_double), ("tr_expand_factor", C.c_double), ("tr_max_trust_radius", C.c_double),
                 ("tr_initial_trust_radius", C.c_double), ("ls_c1", C.c_double), ("ls_rho_hi", C.c_double), ("ls_rho_lo", C.c_double),
                 ("ls_maxiters", C.c_int32), ("precond", C.c_int32), ("descent", C.c_int32), ("tr_scheme", C.c_int32),
-                ("pt_alpha_initial", C.c_double)]
+                ("pt_alpha_initial", C.c_double), ("maxtime", C.c_double), ("term_norm", C.c_int32), ("term_max_stalled_steps", C.c_int32)]
 
 
 class NewtonResult(C.Structure):
@@ -148,6 +149,12 @@ SIGNATURES = {
     "b200_gmres_set_precond": (I32, [P, P, P]),
     "b200_linop_set_shift": (I32, [P, F64]),
     "b200_linop_block_jacobi": (I32, [P, P, PP]),
+    "b200_linop_precond": (I32, [P, P, I32, PP]),
+    "b200_sparse_lu_create": (I32, [P, I64, P, P, I32, PP]),
+    "b200_sparse_lu_destroy": (I32, [P]),
+    "b200_sparse_lu_bandwidth": (I32, [P, PI64, PI64]),
+    "b200_sparse_lu_factor": (I32, [P, P, PI32]),
+    "b200_sparse_lu_solve": (I32, [P, P, P]),
     "b200_gmres_solve": (I32, [P, P, P, P, C.POINTER(GmresStats)]),
     "b200_dense_jac_fill": (I32, [P, P, P, I64]),
     "b200_getrf": (I32, [P, I64, P, I64, P, PI32]),
@@ -176,6 +183,17 @@ SIGNATURES = {
     "b200_ens_create": (I32, [P, I32, I32, F64, C.POINTER(NewtonOpts), PP]),
     "b200_ens_destroy": (I32, [P]),
     "b200_ens_solve": (I32, [P, P, P, P, P, P, P, P, P, C.POINTER(EnsResult)]),
+    "b200_nccl_version": (I32, [PI32]),
+    "b200_nccl_unique_id": (I32, [P]),
+    "b200_nccl_init": (I32, [P, I32, I32, P, PP]),
+    "b200_nccl_init_all": (I32, [PP, I32, PP]),
+    "b200_nccl_group_start": (I32, []),
+    "b200_nccl_group_end": (I32, []),
+    "b200_nccl_destroy": (I32, [P]),
+    "b200_ens_allgather": (I32, [P, P, I64, P]),
+    "b200_ens_allreduce_stats_begin": (I32, [P, C.POINTER(EnsResult)]),
+    "b200_ens_allreduce_stats_finish": (I32, [P, C.POINTER(EnsResult)]),
+    "b200_ens_allreduce_stats": (I32, [P, C.POINTER(EnsResult), C.POINTER(EnsResult)]),
 }
 # test hooks exported by the library but not part of the public header
 EXTRA_SIGNATURES = {

@@ -391,8 +391,64 @@ class BlockJacobi:
         return op
 
 
+class Multigrid:
+    """Built-in preconditioner for `KrylovJL_GMRES(precs = ...)`: one geometric-multigrid V-cycle of the Brusselator Jacobian
+    (coarsening by the prime factors of N down to one cell, damped block-Jacobi smoothing), rebuilt from the current iterate
+    at every Newton step — the role `AlgebraicMultigrid.aspreconditioner(ruge_stuben(W))` plays in
+    docs/src/tutorials/large_systems.md:290-316."""
+
+    def __init__(self, side="right"):
+        assert side in ("left", "right")
+        self.side = side
+
+    @property
+    def code(self):
+        return abi.PRECOND_MULTIGRID_LEFT if self.side == "left" else abi.PRECOND_MULTIGRID_RIGHT
+
+    def linop(self, dprob, u):
+        op = C.c_void_p()
+        check(dprob.ctx.handle, lib().b200_linop_precond(dprob.handle, u.ptr, self.code, C.byref(op)))
+        return op
+
+
 class LUFactorization:
     needs_concrete_A = True
+
+
+class KLUFactorization:
+    """LinearSolve.KLUFactorization(): sparse direct factorisation of the concrete sparse Jacobian (operator_jacobian.jl:22).
+    Device route: reverse Cuthill-McKee + banded LU with partial pivoting (b200_sparse_lu_*)."""
+    needs_concrete_A = True
+
+
+UMFPACKFactorization = KLUFactorization
+
+
+class SparseBandLU:
+    """Direct handle on the device sparse direct solver for a CSC pattern (colptr, rowval host arrays, 1-based by default)."""
+
+    def __init__(self, ctx, n, colptr, rowval, index_base=1):
+        self.ctx, self.n = ctx, n
+        colptr = np.ascontiguousarray(colptr, dtype=np.int64)
+        rowval = np.ascontiguousarray(rowval, dtype=np.int64)
+        self._h = C.c_void_p()
+        check(ctx.handle, lib().b200_sparse_lu_create(ctx.handle, n, colptr.ctypes.data_as(C.c_void_p), rowval.ctypes.data_as(C.c_void_p), index_base, C.byref(self._h)))
+        self._fin = ctx._adopt(weakref.finalize(self, lib().b200_sparse_lu_destroy, self._h))
+
+    def bandwidth(self):
+        kl, ku = C.c_int64(0), C.c_int64(0)
+        check(self.ctx.handle, lib().b200_sparse_lu_bandwidth(self._h, C.byref(kl), C.byref(ku)))
+        return kl.value, ku.value
+
+    def factor(self, nzval):
+        info = C.c_int32(0)
+        check(self.ctx.handle, lib().b200_sparse_lu_factor(self._h, nzval.ptr, C.byref(info)))
+        return info.value
+
+    def solve(self, b, x=None):
+        x = x or self.ctx.zeros(self.n)
+        check(self.ctx.handle, lib().b200_sparse_lu_solve(self._h, b.ptr, x.ptr))
+        return x
 
 
 class AutoForwardDiff:
@@ -411,16 +467,53 @@ class EisenstatWalkerForcing2:
         self.safeguard, self.safeguard_threshold = safeguard, safeguard_threshold
 
 
-class AbsNormSafeBestTerminationMode:
+class _TerminationMode:
+    """Termination modes of NonlinearSolveBase (public.jl:300-407).  `norm`: the mode's internalnorm — "inf" (maximum(abs, .),
+    the NonlinearProblem default) or "l2" (norm(., 2)); Safe modes take `max_stalled_steps` (None: no step-norm stall test,
+    as when the reference's constructor is called without it; the solver's own default mode uses 32)."""
     code = abi.TERM_ABS_NORM_SAFE_BEST
+    safe = False
+
+    def __init__(self, norm="inf", max_stalled_steps=32):
+        assert norm in ("inf", "l2")
+        self.norm = abi.NORM_INF if norm == "inf" else abi.NORM_L2
+        self.max_stalled_steps = -1 if (max_stalled_steps is None or not self.safe) else int(max_stalled_steps)
 
 
-class AbsNormSafeTerminationMode:
-    code = abi.TERM_ABS_NORM_SAFE
+class AbsNormSafeBestTerminationMode(_TerminationMode):
+    code, safe = abi.TERM_ABS_NORM_SAFE_BEST, True
 
 
-class AbsNormTerminationMode:
+class AbsNormSafeTerminationMode(_TerminationMode):
+    code, safe = abi.TERM_ABS_NORM_SAFE, True
+
+
+class AbsNormTerminationMode(_TerminationMode):
     code = abi.TERM_ABS_NORM
+
+
+class NormTerminationMode(_TerminationMode):
+    code = abi.TERM_NORM
+
+
+class RelTerminationMode(_TerminationMode):
+    code = abi.TERM_REL
+
+
+class RelNormTerminationMode(_TerminationMode):
+    code = abi.TERM_REL_NORM
+
+
+class AbsTerminationMode(_TerminationMode):
+    code = abi.TERM_ABS
+
+
+class RelNormSafeTerminationMode(_TerminationMode):
+    code, safe = abi.TERM_REL_NORM_SAFE, True
+
+
+class RelNormSafeBestTerminationMode(_TerminationMode):
+    code, safe = abi.TERM_REL_NORM_SAFE_BEST, True
 
 
 class BackTracking:
@@ -457,8 +550,8 @@ class PseudoTransient(_FirstOrder):
 
 
 class RadiusUpdateSchemes:
-    """RadiusUpdateSchemes.{Simple, NLsolve, NocedalWright, Hei, Yuan, Fan}  (trust_region.jl:431-509)."""
-    Simple, NLsolve, NocedalWright, Hei, Yuan, Fan = (abi.TR_SIMPLE, abi.TR_NLSOLVE, abi.TR_NOCEDAL_WRIGHT, abi.TR_HEI, abi.TR_YUAN, abi.TR_FAN)
+    """RadiusUpdateSchemes.{Simple, NLsolve, NocedalWright, Hei, Yuan, Fan, Bastin}  (trust_region.jl:431-520)."""
+    Simple, NLsolve, NocedalWright, Hei, Yuan, Fan, Bastin = (abi.TR_SIMPLE, abi.TR_NLSOLVE, abi.TR_NOCEDAL_WRIGHT, abi.TR_HEI, abi.TR_YUAN, abi.TR_FAN, abi.TR_BASTIN)
 
 
 class TrustRegion(_FirstOrder):
@@ -480,7 +573,7 @@ class TrustRegion(_FirstOrder):
         self.max_shrink_times = max_shrink_times
 
 
-def _build_opts(prob, alg, abstol, reltol, maxiters, termination_condition, store_trace):
+def _build_opts(prob, alg, abstol, reltol, maxiters, termination_condition, store_trace, maxtime=None):
     o = abi.NewtonOpts()
     lib().b200_newton_opts_default(C.byref(o))
     o.abstol = float(abstol) if abstol is not None else 0.0
@@ -490,17 +583,24 @@ def _build_opts(prob, alg, abstol, reltol, maxiters, termination_condition, stor
     o.globalization = alg.globalization
     o.descent = getattr(alg, "descent", abi.DESCENT_NEWTON)
     o.pt_alpha_initial = getattr(alg, "alpha_initial", 0.0)
+    o.maxtime = float(maxtime) if maxtime is not None else 0.0
     if termination_condition is not None:
+        if isinstance(termination_condition, type):
+            termination_condition = termination_condition()
         o.termination = termination_condition.code
+        o.term_norm = termination_condition.norm
+        o.term_max_stalled_steps = termination_condition.max_stalled_steps
     ls = alg.linsolve
     sparse = prob.f.sparsity is not None or prob.f.jac_prototype is not None
-    if ls is None or isinstance(ls, LUFactorization):
-        # linsolve === nothing -> LinearSolve default: dense LU for a dense J.  A sparse J would go to KLU/UMFPACK in the
-        # reference (CPU only); here it is solved by GMRES on the assembled J, as the reference's own GPU test does
+    if ls is None or isinstance(ls, (LUFactorization, KLUFactorization)):
+        # linsolve === nothing -> LinearSolve default: dense LU for a dense J, a sparse direct factorisation (KLU / UMFPACK)
+        # for a sparse J (sparsity_tests__item1.jl:54-93).  Device route for the latter: RCM + banded LU (b200_sparse_lu_*);
+        # at sizes whose band does not fit (3D N = 100) newton_create fails with B200_ERR_NOMEM and the message says to use
+        # `linsolve = KrylovJL_GMRES()` on the assembled matrix, which is what the reference's own GPU test does
         # (test/gpu/cuda_tests__item1.jl:32).
-        o.linsolve = abi.LINSOLVE_SPARSE_GMRES if sparse else abi.LINSOLVE_DENSE_LU
-        if sparse:
-            KrylovJL_GMRES().fill(o.gmres)
+        if isinstance(ls, KLUFactorization) and not sparse:
+            raise TypeError("KLUFactorization needs a sparse Jacobian (sparsity / jac_prototype)")
+        o.linsolve = abi.LINSOLVE_SPARSE_LU if sparse else abi.LINSOLVE_DENSE_LU
     elif isinstance(ls, KrylovJL_GMRES):
         ls.fill(o.gmres)
         if getattr(ls, "precs", None) is not None:
@@ -805,11 +905,11 @@ class GmresSolver:
 class NonlinearSolveCache:
     """What `init(prob, alg; kwargs...)` returns: persistent device workspace, iterator interface."""
 
-    def __init__(self, prob, alg, abstol=None, reltol=None, maxiters=1000, termination_condition=None, store_trace=True, ctx=None):
+    def __init__(self, prob, alg, abstol=None, reltol=None, maxiters=1000, termination_condition=None, store_trace=True, ctx=None, maxtime=None):
         self.prob, self.alg = prob, alg
         self.ctx = ctx or prob.ctx or default_context()
         self.dprob = _DeviceProblem(self.ctx, prob)
-        self.opts = _build_opts(prob, alg, abstol, reltol, maxiters, termination_condition, store_trace)
+        self.opts = _build_opts(prob, alg, abstol, reltol, maxiters, termination_condition, store_trace, maxtime)
         self._h = C.c_void_p()
         check(self.ctx.handle, lib().b200_newton_create(self.dprob.handle, C.byref(self.opts), C.byref(self._h)))
         self._fin = self.ctx._adopt(weakref.finalize(self, lib().b200_newton_destroy, self._h))
@@ -954,6 +1054,48 @@ class EnsembleCache:
         check(self.ctx.handle, lib().b200_ens_solve(self._h, u0_dev.ptr, A_dev.ptr, B_dev.ptr, self.u_out.ptr, self.resid.ptr, self.rc.ptr,
                                                     self.ns.ptr, self.nj.ptr, C.byref(res)))
         return res
+
+
+class Communicator:
+    """The collective step of the ensemble path through the library's own C-ABI entry points (b200_nccl_init /
+    b200_ens_allgather / b200_ens_allreduce_stats): NCCL over NVLink, enqueued on the context's stream.  One process per GPU:
+    rank 0 calls `Communicator.unique_id()` and ships the 128 bytes to the other ranks (any host-side channel)."""
+
+    @staticmethod
+    def unique_id():
+        buf = (C.c_ubyte * 128)()
+        st = lib().b200_nccl_unique_id(buf)
+        if st != 0:
+            raise abi.B200Error(st, "b200_nccl_unique_id failed (libnccl.so.2 not loadable?)")
+        return bytes(buf)
+
+    @staticmethod
+    def nccl_version():
+        v = C.c_int32(0)
+        return v.value if lib().b200_nccl_version(C.byref(v)) == 0 else None
+
+    def __init__(self, ctx, nranks, rank, unique_id):
+        self.ctx, self.nranks, self.rank = ctx, nranks, rank
+        self._h = C.c_void_p()
+        buf = (C.c_ubyte * 128).from_buffer_copy(unique_id)
+        check(ctx.handle, lib().b200_nccl_init(ctx.handle, nranks, rank, buf, C.byref(self._h)))
+        self._fin = ctx._adopt(weakref.finalize(self, lib().b200_nccl_destroy, self._h))
+
+    def allgather(self, u_local, u_all):
+        check(self.ctx.handle, lib().b200_ens_allgather(self._h, u_local.ptr, u_local.n, u_all.ptr))
+
+    def allreduce_stats(self, local):
+        out = abi.EnsResult()
+        check(self.ctx.handle, lib().b200_ens_allreduce_stats(self._h, C.byref(local), C.byref(out)))
+        return out
+
+    def allreduce_stats_begin(self, local):
+        check(self.ctx.handle, lib().b200_ens_allreduce_stats_begin(self._h, C.byref(local)))
+
+    def allreduce_stats_finish(self):
+        out = abi.EnsResult()
+        check(self.ctx.handle, lib().b200_ens_allreduce_stats_finish(self._h, C.byref(out)))
+        return out
 
 
 def _solve_ensemble(ens, alg, ensalg, trajectories, ctx=None, **kw):

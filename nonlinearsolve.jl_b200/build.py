@@ -69,7 +69,7 @@ def build(force=False, verbose=False):
         for _, out in results:
             sys.stdout.write(out)
     host_cc = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-    cmd = [_nvcc(), *ARCH, "-shared", "-ccbin", host_cc, "-cudart", "shared", "-Xlinker", "-rpath,/usr/local/cuda/lib64", "-o", LIB, *objs]
+    cmd = [_nvcc(), *ARCH, "-shared", "-ccbin", host_cc, "-cudart", "shared", "-Xlinker", "-rpath,/usr/local/cuda/lib64", "-o", LIB, *objs, "-ldl"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s" % r.stdout)

@@ -56,7 +56,8 @@ struct b200_ctx {
   } while (0)
 
 #define B200_RED_MAX_BLOCKS 2048
-enum { RED_DOT = 0, RED_SUMSQ = 1, RED_MAXABS = 2, RED_DIFFSQ = 3, RED_MIN = 4, RED_MAX = 5, RED_NEQ = 6 };
+enum { RED_DOT = 0, RED_SUMSQ = 1, RED_MAXABS = 2, RED_DIFFSQ = 3, RED_MIN = 4, RED_MAX = 5, RED_NEQ = 6,
+       RED_SUMSQ2 = 7 /* sum (x+y)^2 */, RED_MAXABS2 = 8 /* max |x+y| */, RED_RELVIOL = 9 /* #{ |x| > a |x+y| } */ };
 
 #define CUDA_TRY(ctx, expr)                                                             \
   do {                                                                                  \
@@ -153,6 +154,7 @@ struct b200_problem {
 };
 
 struct b200_sparse_jac;
+struct b200_mg;
 
 struct b200_linop {
   b200_ctx* ctx;
@@ -170,8 +172,10 @@ struct b200_linop {
   void* user;
   b200_sparse_jac* sj;
   double shift;  // operator is A + shift I
+  b200_mg* mg;   // LINOP_MULTIGRID: the hierarchy (owned when owns_mg)
+  int32_t owns_mg;
 };
-enum { LINOP_PROBLEM = 0, LINOP_CSC = 1, LINOP_DENSE = 2, LINOP_CALLBACK = 3, LINOP_SPARSE_JAC = 4, LINOP_BLOCK_JACOBI = 5 };
+enum { LINOP_PROBLEM = 0, LINOP_CSC = 1, LINOP_DENSE = 2, LINOP_CALLBACK = 3, LINOP_SPARSE_JAC = 4, LINOP_BLOCK_JACOBI = 5, LINOP_MULTIGRID = 6 };
 
 // internal (non-ABI) helpers implemented across the .cu files
 // Host callbacks run user device code on streams the library knows nothing about (its own stream is non-blocking): drain
@@ -183,9 +187,15 @@ static inline int32_t b200i_sync_for_callback(b200_ctx* ctx) {
   return B200_OK;
 }
 int32_t b200i_linop_apply(b200_linop* op, const double* x, double* y);
+// geometric multigrid preconditioner of the built-in Brusselator Jacobian (mg.cu)
+int32_t b200i_mg_create(b200_problem* prob, b200_mg** out);
+int32_t b200i_mg_destroy(b200_mg* mg);
+int32_t b200i_mg_setup(b200_mg* mg, const double* u);   // rebuild the coarse operators for the linearisation point u
+int32_t b200i_mg_apply(b200_mg* mg, const double* x, double* y);
+int32_t b200i_mg_levels(b200_mg* mg, int32_t* nlev, int32_t* sizes, int32_t cap);
 int32_t b200i_diag_shift(b200_ctx* ctx, int64_t n, double* A, int64_t ld, double shift);  // A[i,i] += shift
 void b200i_sparse_jac_csr(b200_sparse_jac* sj, const int64_t** rowptr, const int64_t** csr_col, const int64_t** csr_map);
 int32_t b200i_residual_norm(b200_problem* prob, const double* u, double* du, double* d_norminf /*device, pre-zeroed*/);
 int32_t b200i_axpy_norm(b200_ctx* ctx, int64_t n, double a, const double* x, double* y, double* d_sumsq /*device, pre-zeroed*/);
-int32_t b200i_reduce_sum_dev(b200_ctx* ctx, int64_t n, const double* x, const double* y, int mode, double* d_out);
+int32_t b200i_reduce_sum_dev(b200_ctx* ctx, int64_t n, const double* x, const double* y, int mode, double* d_out, double a = 0.0);
 int32_t b200i_fetch_scalars(b200_ctx* ctx, int count);  // d_scalars[0..count) -> h_scalars, synchronises

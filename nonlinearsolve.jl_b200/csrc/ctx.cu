@@ -241,7 +241,7 @@ __device__ __forceinline__ double red_identity() {
 }
 template <int MODE>
 __device__ __forceinline__ double red_combine(double a, double b) {
-  if (MODE == RED_MAXABS || MODE == RED_MAX) return fmax(a, b);
+  if (MODE == RED_MAXABS || MODE == RED_MAX || MODE == RED_MAXABS2) return fmax(a, b);
   if (MODE == RED_MIN) return fmin(a, b);
   return a + b;
 }
@@ -263,7 +263,7 @@ __device__ __forceinline__ double red_block(double v, double* red) {
 
 template <int MODE>
 __global__ void __launch_bounds__(EW_THREADS) reduce_stage1(int64_t n, const double* __restrict__ x, const double* __restrict__ y,
-                                                             double* __restrict__ partials) {
+                                                             double* __restrict__ partials, double a) {
   __shared__ double red[32];
   double acc = red_identity<MODE>();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -274,6 +274,9 @@ __global__ void __launch_bounds__(EW_THREADS) reduce_stage1(int64_t n, const dou
     else if (MODE == RED_MAXABS) v = abs_nf(x[i]);
     else if (MODE == RED_DIFFSQ) { double d = x[i] - y[i]; v = d * d; }
     else if (MODE == RED_NEQ) v = (x[i] != y[i]) ? 1.0 : 0.0;
+    else if (MODE == RED_SUMSQ2) { double d = x[i] + y[i]; v = d * d; }
+    else if (MODE == RED_MAXABS2) v = abs_nf(x[i] + y[i]);
+    else if (MODE == RED_RELVIOL) v = (fabs(x[i]) <= a * fabs(x[i] + y[i])) ? 0.0 : 1.0;  // NaN counts as a violation
     else v = x[i];
     acc = red_combine<MODE>(acc, v);
   }
@@ -290,18 +293,21 @@ __global__ void __launch_bounds__(EW_THREADS) reduce_stage2(int nb, const double
 }
 
 template <int MODE>
-int32_t reduce_dev(b200_ctx* ctx, int64_t n, const double* x, const double* y, double* d_out, double* partials) {
+int32_t reduce_dev(b200_ctx* ctx, int64_t n, const double* x, const double* y, double* d_out, double* partials, double a = 0.0) {
   int64_t nb64 = (n + (int64_t)EW_THREADS * 8 - 1) / ((int64_t)EW_THREADS * 8);
   int nb = (int)(nb64 < 1 ? 1 : (nb64 > B200_RED_MAX_BLOCKS ? B200_RED_MAX_BLOCKS : nb64));
-  LAUNCH(ctx, (reduce_stage1<MODE>), nb, EW_THREADS, 0, n, x, y, partials);
+  LAUNCH(ctx, (reduce_stage1<MODE>), nb, EW_THREADS, 0, n, x, y, partials, a);
   LAUNCH(ctx, (reduce_stage2<MODE>), 1, EW_THREADS, 0, nb, partials, d_out);
   CHECK_LAUNCH(ctx);
   return B200_OK;
 }
 }  // namespace
 
-int32_t b200i_reduce_sum_dev(b200_ctx* ctx, int64_t n, const double* x, const double* y, int mode, double* d_out) {
+int32_t b200i_reduce_sum_dev(b200_ctx* ctx, int64_t n, const double* x, const double* y, int mode, double* d_out, double a) {
   switch (mode) {
+    case RED_SUMSQ2: return reduce_dev<RED_SUMSQ2>(ctx, n, x, y, d_out, ctx->d_partials);
+    case RED_MAXABS2: return reduce_dev<RED_MAXABS2>(ctx, n, x, y, d_out, ctx->d_partials);
+    case RED_RELVIOL: return reduce_dev<RED_RELVIOL>(ctx, n, x, y, d_out, ctx->d_partials, a);
     case RED_DOT: return reduce_dev<RED_DOT>(ctx, n, x, y, d_out, ctx->d_partials);
     case RED_SUMSQ: return reduce_dev<RED_SUMSQ>(ctx, n, x, y, d_out, ctx->d_partials);
     case RED_MAXABS: return reduce_dev<RED_MAXABS>(ctx, n, x, y, d_out, ctx->d_partials);

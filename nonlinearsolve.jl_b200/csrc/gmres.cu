@@ -1096,6 +1096,48 @@ __global__ void __launch_bounds__(R3_THREADS, 1) resident3_arnoldi_kernel(Reside
 // Barriers: one __syncthreads per basis vector (two when the stage being released lives in shared memory) instead of
 // two (three).  Every reduction / poll scratch is double-buffered by step parity, so no write can meet a read of the
 // previous step without a barrier in between (compute-sanitizer racecheck: profiles/).
+// Early poll of exchange t: the words were published one step ago, so the load is issued BEFORE the dot sweep of the
+// step and its L2 round trip is hidden underneath it; r3g_poll_finish checks the epochs afterwards and only spins if a CTA is late.
+__device__ __forceinline__ void r3g_poll_issue(const unsigned long long* buf, int b, int G, unsigned long long& a0, unsigned long long& a1) {
+  const int tid = threadIdx.x;
+  a0 = 0ull; a1 = 0ull;
+  if (tid < G) {
+    const unsigned long long* src = buf + ((size_t)(b & (R3_REPL - 1)) * LL_MAXG + tid) * 4;
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a0), "=l"(a1) : "l"(src) : "memory");
+  }
+}
+__device__ __forceinline__ void r3g_poll_finish(const unsigned long long* buf, int b, int G, unsigned epoch, int* err, bool need_c, unsigned long long a0,
+                                                unsigned long long a1, double* gA, double* gC) {
+  const int tid = threadIdx.x;
+  if (tid < 160) {
+    double xa = 0.0, xc = 0.0;
+    if (tid < G) {
+      const unsigned long long* src = buf + ((size_t)(b & (R3_REPL - 1)) * LL_MAXG + tid) * 4;
+      unsigned spins = 0;
+      while (((unsigned)(a0 >> 32) != epoch) || ((unsigned)(a1 >> 32) != epoch)) {
+        asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a0), "=l"(a1) : "l"(src) : "memory");
+        if (++spins > (1u << 22)) { *err = 1; break; }
+      }
+      xa = __longlong_as_double((long long)((a0 & 0xffffffffull) | (a1 << 32)));
+      if (need_c) {  // wrap-around step only: the cross product travels in the second pair (same store burst as the first)
+        unsigned long long c0, c1;
+        spins = 0;
+        do {
+          asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(c0), "=l"(c1) : "l"(src + 2) : "memory");
+          if (++spins > (1u << 22)) { *err = 1; break; }
+        } while (((unsigned)(c0 >> 32) != epoch) || ((unsigned)(c1 >> 32) != epoch));
+        xc = __longlong_as_double((long long)((c0 & 0xffffffffull) | (c1 << 32)));
+      }
+    }
+    xa = warp_sum(xa);
+    if ((tid & 31) == 0) gA[tid >> 5] = xa;
+    if (need_c) {
+      xc = warp_sum(xc);
+      if ((tid & 31) == 0) gC[tid >> 5] = xc;
+    }
+  }
+}
+
 struct R3GShared {
   uint64_t mbar[2];
   double redA[2][8], redC[2][8];  // per-warp partials of the dot sweep, by step parity
@@ -1113,6 +1155,9 @@ __device__ __forceinline__ void r3g_step(const ResidentParams& P, R3Ctx& cx, R3G
   const double* sn = (NEXT == 0 ? cx.stage0 : cx.stage1) + 2 * tid;   // next vector if it lives in shared memory
   const bool more = t + 1 < cx.total;
   const int i = t % cx.k;
+  const unsigned long long* pollbuf = P.slots + (size_t)(t & 3) * R3_BUF_WORDS;
+  unsigned long long ea0, ea1;
+  r3g_poll_issue(pollbuf, cx.b, cx.G, ea0, ea1);
   if (more) {
     if (NEXT != 2 && cx.nrow > 0) mbar_wait(&sh.mbar[NEXT], (unsigned)(((t + 1) / 3) & 1));
     if (NEXT == 2) asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -1133,6 +1178,7 @@ __device__ __forceinline__ void r3g_step(const ResidentParams& P, R3Ctx& cx, R3G
       }
       dc = warp_sum(dc);
     } else {
+      double db = 0.0;  // two independent chains: 27 dependent DFMAs each instead of 54 (2 warps per scheduler cannot hide more)
 #pragma unroll
       for (int q = 0; q < R3_RP; ++q) {
         const int lr = 2 * R3_THREADS * q;  // offset from this thread's first row pair
@@ -1140,16 +1186,17 @@ __device__ __forceinline__ void r3g_step(const ResidentParams& P, R3Ctx& cx, R3G
           double x0, x1;
           if (NEXT == 2) { R3_VRGET(q, x0, x1); }
           else { const double2 x = *reinterpret_cast<const double2*>(sn + lr); x0 = x.x; x1 = x.y; }
-          da = fma(x0, w[2 * q], da); da = fma(x1, w[2 * q + 1], da);
+          da = fma(x0, w[2 * q], da); db = fma(x1, w[2 * q + 1], db);
         }
       }
+      da += db;
     }
     da = warp_sum(da);
     if ((tid & 31) == 0) { sh.redA[par][tid >> 5] = da; sh.redC[par][tid >> 5] = dc; }
   }
   // Gram sub-diagonal entry <v_i, v_{i-1}>, stored when v_i was created: fetched by a spare polling thread (G <= 159)
   if (tid == 159) sh.gC[par][5] = (i > 0) ? __ldg(P.gsub + i) : 0.0;
-  r3_poll(P.slots + (size_t)(t & 3) * R3_BUF_WORDS, cx.b, cx.G, P.epoch_base + (unsigned)t + 1u, P.err, sh.gA[par], sh.gC[par]);
+  r3g_poll_finish(pollbuf, cx.b, cx.G, P.epoch_base + (unsigned)t + 1u, P.err, i == 0 && t > 0, ea0, ea1, sh.gA[par], sh.gC[par]);
   __syncthreads();  // the only barrier of a register-role step
   if (more && tid < 32) {  // warp 0: total of the eight warp partials in a fixed order, then publish for step t+1
     const double* ra = sh.redA[par];
@@ -1161,7 +1208,8 @@ __device__ __forceinline__ void r3g_step(const ResidentParams& P, R3Ctx& cx, R3G
   const double* ga = sh.gA[par];
   const double* gc = sh.gC[par];
   const double sa = ((ga[0] + ga[1]) + (ga[2] + ga[3])) + ga[4];
-  const double cross = (i > 0) ? gc[5] : (((gc[0] + gc[1]) + (gc[2] + gc[3])) + gc[4]);  // i == 0: wrap-around, taken in the sweep
+  // i == 0: first vector of a pass (t == 0: nothing precedes it; t > 0: wrap-around, cross product taken in the sweep of step t-1)
+  const double cross = (i > 0) ? gc[5] : (t > 0 ? (((gc[0] + gc[1]) + (gc[2] + gc[3])) + gc[4]) : 0.0);
   const double h = sa - sh.hprev[par ^ 1] * cross;
   if (tid == 0) sh.hprev[par] = h;
   if (more) {
@@ -1454,6 +1502,8 @@ static int32_t linop_apply_unshifted(b200_linop* op, const double* x, double* y)
       return op->mv(op->user, x, y) == 0 ? B200_OK : ctx->fail(B200_ERR_CALLBACK, "matvec callback failed", __FILE__, __LINE__);
     case LINOP_SPARSE_JAC:
       return b200_spmv(op->sj, op->nzval, x, y);
+    case LINOP_MULTIGRID:
+      return b200i_mg_apply(op->mg, x, y);
     case LINOP_BLOCK_JACOBI: {
       const int64_t NC = op->n / 2;
       const double lapdiag = -(op->prob->kind == B200_PROB_BRUSS3D ? 6.0 : 4.0) * op->prob->a;
@@ -1515,7 +1565,13 @@ int32_t b200_linop_apply(b200_linop* op, const double* x, double* y) {
   return b200i_linop_apply(op, x, y);
 }
 int32_t b200_linop_set_shift(b200_linop* op, double shift) { op->shift = shift; return B200_OK; }
-int32_t b200_linop_destroy(b200_linop* op) { delete op; return B200_OK; }
+int32_t b200_linop_destroy(b200_linop* op) {
+  if (!op) return B200_OK;
+  B200_DEVICE_GUARD(op->ctx);
+  if (op->mg && op->owns_mg) b200i_mg_destroy(op->mg);
+  delete op;
+  return B200_OK;
+}
 
 void b200_gmres_opts_default(b200_gmres_opts* o) {
   memset(o, 0, sizeof(*o));
@@ -1603,6 +1659,23 @@ int32_t b200_linop_block_jacobi(b200_problem* prob, const double* u, b200_linop*
   b200_linop* op = new b200_linop();
   memset(op, 0, sizeof(*op));
   op->ctx = prob->ctx; op->kind = LINOP_BLOCK_JACOBI; op->n = prob->n; op->prob = prob; op->u = u;
+  *out = op;
+  return B200_OK;
+}
+
+int32_t b200_linop_precond(b200_problem* prob, const double* u, int32_t kind, b200_linop** out) {
+  B200_DEVICE_GUARD(prob ? prob->ctx : nullptr);
+  b200_ctx* ctx = prob->ctx;
+  B200_REQUIRE(ctx, u && out, "linop_precond: bad arguments");
+  if (kind == B200_PRECOND_BLOCK_JACOBI_LEFT || kind == B200_PRECOND_BLOCK_JACOBI_RIGHT) return b200_linop_block_jacobi(prob, u, out);
+  B200_REQUIRE(ctx, kind == B200_PRECOND_MULTIGRID_LEFT || kind == B200_PRECOND_MULTIGRID_RIGHT, "linop_precond: unknown preconditioner kind");
+  b200_mg* mg = nullptr;
+  B200_TRY(b200i_mg_create(prob, &mg));
+  int32_t st = b200i_mg_setup(mg, u);
+  if (st != B200_OK) { b200i_mg_destroy(mg); return st; }
+  b200_linop* op = new b200_linop();
+  memset(op, 0, sizeof(*op));
+  op->ctx = ctx; op->kind = LINOP_MULTIGRID; op->n = prob->n; op->prob = prob; op->u = u; op->mg = mg; op->owns_mg = 1;
   *out = op;
   return B200_OK;
 }

@@ -12,17 +12,24 @@
 #include "common.cuh"
 #include <math.h>
 #include <algorithm>
+#include <chrono>
 
 extern "C" int32_t b200_gmres_keep_hessenberg(b200_gmres* gm, int64_t capacity);
 
 namespace {
 struct TermCache {  // NonlinearTerminationModeCache (termination_conditions.jl:60-98)
   int mode;
-  double abstol, best, initial;
+  int norm_kind;        // B200_NORM_*
+  int max_stalled;      // window of the step-norm stall test (0: disabled)
+  double abstol, reltol, best, initial, u0_norm;
   int nsteps;
   int retcode;
   double obj_trace[100];
-  double step_trace[32];
+  double step_trace[128];
+};
+// what the modes read of (du = f(u), u): filled on demand by term_quantities()
+struct TermQuant {
+  double f_inf, f_norm, sum_norm, rel_viol;  // ||f||_inf ; internalnorm(f) ; internalnorm(f + u) ; #{ |f_i| > reltol |u_i + f_i| }
 };
 }  // namespace
 
@@ -38,12 +45,14 @@ struct b200_newton {
   b200_gmres* gm;
   b200_linop op;
   b200_linop prec;  // built-in preconditioner (opts.precond), re-pointed at the current iterate every step
+  b200_mg* mg;      // multigrid hierarchy when opts.precond is MULTIGRID_*
   // dense
   double* Jdense;
   int64_t* ipiv;
   // sparse
   b200_sparse_jac* sj;
   double* nzval;
+  b200_sparse_lu* slu;  // LINSOLVE_SPARSE_LU: band factorisation of the assembled Jacobian
   // state
   TermCache tc;
   b200_newton_result res;
@@ -55,6 +64,7 @@ struct b200_newton {
   double tp1, tp2, tp3, tp4;      // radius-update scheme parameters (get_parameters, trust_region.jl:372-379)
   double alpha_inv, pt_res_norm;  // PseudoTransient: 1/alpha and the residual 2-norm of the previous step (SER)
   double fnorm_inf;  // ||f(u)||_inf of the current iterate
+  double total_time; // accumulated wall time of the steps (maxtime)
   double bytes;
 };
 
@@ -63,29 +73,69 @@ namespace {
 int32_t h_nrm2(b200_newton* nw, const double* x, double* out) { return b200_nrm2(nw->ctx, nw->n, x, out); }
 int32_t h_dot(b200_newton* nw, const double* x, const double* y, double* out) { return b200_dot(nw->ctx, nw->n, x, y, out); }
 
-// termination_conditions.jl:243-336 for the AbsNorm* modes; `objective` = ||fu||_inf, `du_norm` = ||u - uprev||_2
-int term_check(b200_newton* nw, double objective, double du_norm, bool* new_best) {
+bool term_is_safe(int mode) {
+  return mode == B200_TERM_ABS_NORM_SAFE_BEST || mode == B200_TERM_ABS_NORM_SAFE || mode == B200_TERM_REL_NORM_SAFE || mode == B200_TERM_REL_NORM_SAFE_BEST;
+}
+bool term_is_best(int mode) { return mode == B200_TERM_ABS_NORM_SAFE_BEST || mode == B200_TERM_REL_NORM_SAFE_BEST; }
+bool term_is_rel(int mode) { return mode == B200_TERM_REL_NORM_SAFE || mode == B200_TERM_REL_NORM_SAFE_BEST; }
+
+// the reductions over (fu, u) a mode needs beyond ||fu||_inf (which the residual kernel's epilogue already produced)
+int32_t term_quantities(b200_newton* nw, const double* fu, const double* u, double f_inf, TermQuant* q) {
+  b200_ctx* ctx = nw->ctx;
+  const int64_t n = nw->n;
+  const int mode = nw->tc.mode;
+  const bool l2 = nw->tc.norm_kind == B200_NORM_L2;
+  q->f_inf = f_inf; q->f_norm = f_inf; q->sum_norm = 0.0; q->rel_viol = 0.0;
+  const bool need_sum = mode == B200_TERM_NORM || mode == B200_TERM_REL_NORM || term_is_rel(mode);
+  const bool need_viol = mode == B200_TERM_REL;
+  const bool need_f2 = l2 && mode != B200_TERM_ABS && mode != B200_TERM_REL;
+  if (!need_sum && !need_viol && !need_f2) return B200_OK;
+  if (need_f2) B200_TRY(b200i_reduce_sum_dev(ctx, n, fu, nullptr, RED_SUMSQ, ctx->d_scalars + 8));
+  if (need_sum) B200_TRY(b200i_reduce_sum_dev(ctx, n, fu, u, l2 ? RED_SUMSQ2 : RED_MAXABS2, ctx->d_scalars + 9));
+  if (need_viol) B200_TRY(b200i_reduce_sum_dev(ctx, n, fu, u, RED_RELVIOL, ctx->d_scalars + 10, nw->tc.reltol));
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scalars + 8, ctx->d_scalars + 8, sizeof(double) * 3, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (need_f2) q->f_norm = sqrt(ctx->h_scalars[8]);
+  if (need_sum) q->sum_norm = l2 ? sqrt(ctx->h_scalars[9]) : ctx->h_scalars[9];
+  if (need_viol) q->rel_viol = ctx->h_scalars[10];
+  return B200_OK;
+}
+
+// check_convergence (termination_conditions.jl:339-372) for the plain modes and the Safe-mode state machine (:243-336);
+// `du_norm` = ||u - uprev||_2
+int term_check(b200_newton* nw, const TermQuant& q, double du_norm, bool* new_best) {
   TermCache& tc = nw->tc;
   *new_best = false;
-  if (tc.mode == B200_TERM_ABS_NORM) {
-    if (objective <= tc.abstol) { tc.retcode = B200_RC_SUCCESS; return 1; }
-    return 0;
+  switch (tc.mode) {
+    case B200_TERM_ABS_NORM: if (q.f_norm <= tc.abstol) { tc.retcode = B200_RC_SUCCESS; return 1; } return 0;
+    case B200_TERM_ABS: if (q.f_inf <= tc.abstol) { tc.retcode = B200_RC_SUCCESS; return 1; } return 0;          // all(|du| <= abstol)
+    case B200_TERM_NORM: if (q.f_norm <= tc.abstol || q.f_norm <= tc.reltol * q.sum_norm) { tc.retcode = B200_RC_SUCCESS; return 1; } return 0;
+    case B200_TERM_REL_NORM: if (q.f_norm <= tc.reltol * q.sum_norm) { tc.retcode = B200_RC_SUCCESS; return 1; } return 0;
+    case B200_TERM_REL: if (q.rel_viol == 0.0) { tc.retcode = B200_RC_SUCCESS; return 1; } return 0;          // all(|du| <= reltol |u + du|)
+    default: break;
   }
+  const bool rel = term_is_rel(tc.mode);
+  double objective, criteria;
+  if (!rel) { objective = q.f_norm; criteria = tc.abstol; }
+  else { objective = q.f_norm / (q.sum_norm + (nextafter(tc.reltol, INFINITY) - tc.reltol)); criteria = tc.reltol; }  // + eps(reltol)
   if (!std::isfinite(objective)) { tc.retcode = B200_RC_UNSTABLE; return 1; }
-  if (tc.mode == B200_TERM_ABS_NORM_SAFE_BEST && objective < tc.best) { tc.best = objective; *new_best = true; }
-  if (objective <= tc.abstol) { tc.retcode = B200_RC_SUCCESS; return 1; }
+  if (term_is_best(tc.mode) && objective < tc.best) { tc.best = objective; *new_best = true; }
+  if (objective <= criteria) { tc.retcode = B200_RC_SUCCESS; return 1; }
   tc.nsteps += 1;
   tc.obj_trace[(tc.nsteps - 1) % 100] = objective;
-  if (objective <= 3.0 * tc.abstol && tc.nsteps > 100) {
+  if (objective <= 3.0 * criteria && tc.nsteps > 100) {  // patience_objective_multiplier = 3, patience_steps = 100, min_max_factor = 1.3
     double mn = INFINITY, mx = -INFINITY;
     for (int i = 0; i < 100; ++i) { mn = std::min(mn, tc.obj_trace[i]); mx = std::max(mx, tc.obj_trace[i]); }
     if (mn < 1.3 * mx) { tc.retcode = B200_RC_STALLED; return 1; }
   }
-  tc.step_trace[(tc.nsteps - 1) % 32] = du_norm;
-  if (tc.nsteps > 32) {
-    double mx = 0.0;
-    for (int i = 0; i < 32; ++i) mx = std::max(mx, tc.step_trace[i]);
-    if (mx <= tc.abstol) { tc.retcode = B200_RC_STALLED; return 1; }
+  if (tc.max_stalled > 0) {
+    tc.step_trace[(tc.nsteps - 1) % tc.max_stalled] = du_norm;
+    if (tc.nsteps > tc.max_stalled) {
+      double mx = 0.0;
+      for (int i = 0; i < tc.max_stalled; ++i) mx = std::max(mx, tc.step_trace[i]);
+      const bool stalled = rel ? (mx <= tc.reltol * (mx + tc.u0_norm)) : (mx <= tc.abstol);
+      if (stalled) { tc.retcode = B200_RC_STALLED; return 1; }
+    }
   }
   tc.retcode = B200_RC_FAILURE;
   return 0;
@@ -127,7 +177,9 @@ int32_t b200_newton_destroy(b200_newton* nw) {
   for (double* v : vecs) if (v) cudaFree(v);
   if (nw->ipiv) cudaFree(nw->ipiv);
   if (nw->gm) b200_gmres_destroy(nw->gm);
+  if (nw->mg) b200i_mg_destroy(nw->mg);
   if (nw->sj) b200_sparse_jac_destroy(nw->sj);
+  if (nw->slu) b200_sparse_lu_destroy(nw->slu);
   delete nw;
   return B200_OK;
 }
@@ -136,13 +188,17 @@ int32_t b200_newton_create(b200_problem* prob, const b200_newton_opts* opts, b20
   B200_DEVICE_GUARD(prob ? prob->ctx : nullptr);
   b200_ctx* ctx = prob->ctx;
   B200_REQUIRE(ctx, opts && out, "newton_create: bad arguments");
-  B200_REQUIRE(ctx, opts->tr_scheme >= B200_TR_SIMPLE && opts->tr_scheme <= B200_TR_FAN, "newton_create: unknown radius update scheme");
+  B200_REQUIRE(ctx, opts->tr_scheme >= B200_TR_SIMPLE && opts->tr_scheme <= B200_TR_BASTIN, "newton_create: unknown radius update scheme");
+  B200_REQUIRE(ctx, opts->termination >= B200_TERM_ABS_NORM_SAFE_BEST && opts->termination <= B200_TERM_REL_NORM_SAFE_BEST, "newton_create: unknown termination mode");
+  B200_REQUIRE(ctx, opts->term_norm == B200_NORM_INF || opts->term_norm == B200_NORM_L2, "newton_create: unknown termination norm");
+  B200_REQUIRE(ctx, opts->term_max_stalled_steps <= 128, "newton_create: term_max_stalled_steps must be <= 128");
   B200_REQUIRE(ctx, opts->descent == B200_DESCENT_NEWTON || (opts->descent == B200_DESCENT_PSEUDO_TRANSIENT && opts->globalization != B200_GLOBALIZATION_TRUST_REGION),
                "newton_create: descent must be Newton or PseudoTransient (the latter without a trust region)");
   B200_REQUIRE(ctx, opts->precond == B200_PRECOND_NONE ||
                         ((opts->linsolve == B200_LINSOLVE_GMRES || opts->linsolve == B200_LINSOLVE_SPARSE_GMRES) &&
                          (prob->kind == B200_PROB_BRUSS2D || prob->kind == B200_PROB_BRUSS3D)),
-               "newton_create: the built-in block-Jacobi preconditioner needs a Krylov linsolve and a built-in Brusselator problem");
+               "newton_create: the built-in preconditioners need a Krylov linsolve and a built-in Brusselator problem");
+  B200_REQUIRE(ctx, opts->precond >= B200_PRECOND_NONE && opts->precond <= B200_PRECOND_MULTIGRID_RIGHT, "newton_create: unknown preconditioner");
   b200_newton* nw = new b200_newton();
   nw->ctx = ctx; nw->prob = prob; nw->o = *opts; nw->n = prob->n;
   nw->abstol = opts->abstol > 0 ? opts->abstol : 3.0e-13;  // common_defaults.jl:44-48
@@ -150,13 +206,13 @@ int32_t b200_newton_create(b200_problem* prob, const b200_newton_opts* opts, b20
   nw->maxiters = opts->maxiters > 0 ? opts->maxiters : 1000;
   nw->u = nw->fu = nw->u_cache = nw->du = nw->xlin = nw->best_u = nullptr;
   nw->u_trial = nw->fu_trial = nw->Jdu = nw->JTfu = nw->du_c = nw->c1 = nw->c2 = nullptr;
-  nw->gm = nullptr; nw->Jdense = nullptr; nw->ipiv = nullptr; nw->sj = nullptr; nw->nzval = nullptr;
+  nw->slu = nullptr; nw->mg = nullptr; nw->gm = nullptr; nw->Jdense = nullptr; nw->ipiv = nullptr; nw->sj = nullptr; nw->nzval = nullptr;
   nw->initialised = 0;
   const int64_t n = nw->n;
   int32_t s = B200_OK;
   auto A = [&](double** p) { if (s == B200_OK) s = alloc_vec(ctx, n, p); };
   A(&nw->u); A(&nw->fu); A(&nw->u_cache); A(&nw->du); A(&nw->xlin);
-  if (opts->termination == B200_TERM_ABS_NORM_SAFE_BEST) A(&nw->best_u);
+  if (term_is_best(opts->termination)) A(&nw->best_u);
   if (opts->globalization == B200_GLOBALIZATION_TRUST_REGION) {
     A(&nw->u_trial); A(&nw->fu_trial); A(&nw->Jdu); A(&nw->JTfu); A(&nw->du_c); A(&nw->c1); A(&nw->c2);
   }
@@ -164,6 +220,10 @@ int32_t b200_newton_create(b200_problem* prob, const b200_newton_opts* opts, b20
   if (s != B200_OK) { b200_newton_destroy(nw); return s; }
   memset(&nw->op, 0, sizeof(nw->op));
   nw->op.ctx = ctx; nw->op.n = n;
+  if (opts->precond == B200_PRECOND_MULTIGRID_LEFT || opts->precond == B200_PRECOND_MULTIGRID_RIGHT) {
+    s = b200i_mg_create(prob, &nw->mg);
+    if (s != B200_OK) { b200_newton_destroy(nw); return s; }
+  }
   if (opts->linsolve == B200_LINSOLVE_GMRES || opts->linsolve == B200_LINSOLVE_SPARSE_GMRES) {
     b200_gmres_opts g = opts->gmres;
     if (g.atol <= 0) g.atol = nw->abstol;  // linsolve_kwargs = (; abstol, reltol)   solve.jl:203
@@ -180,7 +240,7 @@ int32_t b200_newton_create(b200_problem* prob, const b200_newton_opts* opts, b20
       b200_newton_destroy(nw);
       return ctx->fail(B200_ERR_NOMEM, "dense Jacobian does not fit in device memory", __FILE__, __LINE__);
     }
-  } else if (opts->linsolve == B200_LINSOLVE_SPARSE_GMRES) {
+  } else if (opts->linsolve == B200_LINSOLVE_SPARSE_GMRES || opts->linsolve == B200_LINSOLVE_SPARSE_LU) {
     // jac_prototype + colouring once at init (jacobian.jl:286-353; colouring ext :13-28)
     int64_t nnz = 0;
     s = b200_pattern_nnz(prob, &nnz);
@@ -190,6 +250,8 @@ int32_t b200_newton_create(b200_problem* prob, const b200_newton_opts* opts, b20
     if (s == B200_OK) s = b200_coloring_column(n, colptr.data(), rowval.data(), 1, B200_ORDER_LARGEST_FIRST, colors.data(), &ncolors);
     if (s == B200_OK) s = b200_sparse_jac_create(prob, colptr.data(), rowval.data(), 1, colors.data(), ncolors, &nw->sj);
     if (s == B200_OK && cudaMalloc(&nw->nzval, sizeof(double) * nnz) != cudaSuccess) { cudaGetLastError(); s = B200_ERR_NOMEM; }
+    // sparse direct route (linsolve = nothing on a sparse prototype): symbolic phase once, like LinearSolve's cache
+    if (s == B200_OK && opts->linsolve == B200_LINSOLVE_SPARSE_LU) s = b200_sparse_lu_create(ctx, n, colptr.data(), rowval.data(), 1, &nw->slu);
     if (s != B200_OK) { b200_newton_destroy(nw); return s; }
     nw->op.kind = LINOP_SPARSE_JAC; nw->op.sj = nw->sj; nw->op.nzval = nw->nzval;
   } else {
@@ -216,9 +278,22 @@ int32_t b200_newton_reinit(b200_newton* nw, const double* u0_dev) {
   nw->fnorm_inf = ctx->h_scalars[0];
   memset(&nw->tc, 0, sizeof(nw->tc));
   nw->tc.mode = o.termination;
+  nw->tc.norm_kind = o.term_norm;
+  nw->tc.max_stalled = !term_is_safe(o.termination) ? 0 : (o.term_max_stalled_steps < 0 ? 0 : (o.term_max_stalled_steps == 0 ? 32 : o.term_max_stalled_steps));
   nw->tc.abstol = nw->abstol;
-  nw->tc.initial = nw->fnorm_inf;
-  nw->tc.best = (o.termination == B200_TERM_ABS_NORM) ? INFINITY : nw->fnorm_inf;
+  nw->tc.reltol = nw->reltol;
+  nw->total_time = 0.0;
+  {  // SciMLBase.reinit!(::NonlinearTerminationModeCache, du, u)   termination_conditions.jl:180-215
+    TermQuant q;
+    B200_TRY(term_quantities(nw, nw->fu, nw->u, nw->fnorm_inf, &q));
+    if (!term_is_safe(o.termination)) nw->tc.best = INFINITY;
+    else if (!term_is_rel(o.termination)) nw->tc.best = q.f_norm;
+    else {
+      nw->tc.best = q.f_norm / (q.sum_norm + 2.220446049250313e-16);   // eps(TT)
+      if (nw->tc.max_stalled > 0) B200_TRY(h_nrm2(nw, nw->u, &nw->tc.u0_norm));
+    }
+    nw->tc.initial = nw->tc.best;
+  }
   memset(&nw->res, 0, sizeof(nw->res));
   nw->trace.clear();
   nw->retcode = B200_RC_DEFAULT; nw->force_stop = 0; nw->make_new_jacobian = 1; nw->nsteps = 0; nw->have_factor = 0;
@@ -235,11 +310,12 @@ int32_t b200_newton_reinit(b200_newton* nw, const double* u0_dev) {
     else if (sch == B200_TR_HEI) { nw->tp1 = 5.0; nw->tp2 = 0.1; nw->tp3 = 0.15; nw->tp4 = 0.15; }
     else if (sch == B200_TR_YUAN) { nw->tp1 = 2.0; nw->tp2 = 1.0 / 6; nw->tp3 = 6.0; }
     else if (sch == B200_TR_FAN) { nw->tp1 = 0.1; nw->tp2 = 0.25; nw->tp3 = 12.0; nw->tp4 = 1.0e18; }
+    else if (sch == B200_TR_BASTIN) { nw->tp1 = 2.5; nw->tp2 = 0.25; }
     if (o.tr_max_trust_radius > 0) nw->max_tr = o.tr_max_trust_radius;  // max_trust_radius  :330-337
-    else nw->max_tr = (sch == B200_TR_SIMPLE || sch == B200_TR_NOCEDAL_WRIGHT) ? std::max(fu_norm, umax - umin) : INFINITY;
+    else nw->max_tr = (sch == B200_TR_SIMPLE || sch == B200_TR_NOCEDAL_WRIGHT) ? std::max(fu_norm, umax - umin) : INFINITY;  // Hei, Yuan, Fan, NLsolve, Bastin: unbounded
     if (o.tr_initial_trust_radius > 0) nw->trust_region = o.tr_initial_trust_radius;  // initial_trust_radius  :339-346
     else if (sch == B200_TR_NLSOLVE) nw->trust_region = u0_norm > 0 ? u0_norm : 1.0;
-    else if (sch == B200_TR_HEI) nw->trust_region = 1.0;
+    else if (sch == B200_TR_HEI || sch == B200_TR_BASTIN) nw->trust_region = 1.0;
     else if (sch == B200_TR_FAN) nw->trust_region = pow(fu_norm, 0.99) / 10.0;
     else nw->trust_region = nw->max_tr / 11.0;
     if (sch == B200_TR_YUAN) {  // itr = p1 ||J' fu||  :232-234
@@ -269,12 +345,12 @@ static int32_t newton_step_inner(b200_newton* nw) {
   const b200_newton_opts& o = nw->o;
   const double Bv = 8.0 * (double)n;
   const bool tr_on = o.globalization == B200_GLOBALIZATION_TRUST_REGION;
-  const bool krylov = o.linsolve != B200_LINSOLVE_DENSE_LU;
+  const bool krylov = o.linsolve == B200_LINSOLVE_GMRES || o.linsolve == B200_LINSOLVE_SPARSE_GMRES;
   const int sch = o.tr_scheme;  // per-scheme defaults  trust_region.jl:348-381
-  const double step_thr = o.tr_step_threshold > 0 ? o.tr_step_threshold : (sch == B200_TR_HEI ? 0.0 : sch == B200_TR_YUAN ? 1.0 / 1000 : 1.0 / 10000);
-  const double shrink_thr = o.tr_shrink_threshold > 0 ? o.tr_shrink_threshold : (sch == B200_TR_HEI ? 0.0 : sch == B200_TR_NLSOLVE ? 1.0 / 20 : 0.25);
-  const double expand_thr = o.tr_expand_threshold > 0 ? o.tr_expand_threshold : (sch == B200_TR_NLSOLVE ? 0.9 : sch == B200_TR_HEI ? 0.0 : 0.75);
-  const double shrink_fac = o.tr_shrink_factor > 0 ? o.tr_shrink_factor : (sch == B200_TR_NLSOLVE ? 0.5 : sch == B200_TR_HEI ? 0.0 : 0.25);
+  const double step_thr = o.tr_step_threshold > 0 ? o.tr_step_threshold : (sch == B200_TR_HEI ? 0.0 : sch == B200_TR_YUAN ? 1.0 / 1000 : sch == B200_TR_BASTIN ? 1.0 / 20 : 1.0 / 10000);
+  const double shrink_thr = o.tr_shrink_threshold > 0 ? o.tr_shrink_threshold : (sch == B200_TR_HEI ? 0.0 : (sch == B200_TR_NLSOLVE || sch == B200_TR_BASTIN) ? 1.0 / 20 : 0.25);
+  const double expand_thr = o.tr_expand_threshold > 0 ? o.tr_expand_threshold : ((sch == B200_TR_NLSOLVE || sch == B200_TR_BASTIN) ? 0.9 : sch == B200_TR_HEI ? 0.0 : 0.75);
+  const double shrink_fac = o.tr_shrink_factor > 0 ? o.tr_shrink_factor : (sch == B200_TR_NLSOLVE ? 0.5 : sch == B200_TR_HEI ? 0.0 : sch == B200_TR_BASTIN ? 1.0 / 20 : 0.25);
   const double expand_fac = o.tr_expand_factor > 0 ? o.tr_expand_factor : 2.0;
   const int max_shrink = o.max_shrink_times > 0 ? o.max_shrink_times : 32;
 
@@ -286,9 +362,10 @@ static int32_t newton_step_inner(b200_newton* nw) {
         nw->res.njacs += 1;
         B200_TRY(b200_dense_jac_fill(nw->prob, nw->u, nw->Jdense, n));  // written straight into the LU workspace (K10: no copyto!)
         nw->have_factor = 0;
-      } else if (o.linsolve == B200_LINSOLVE_SPARSE_GMRES) {
+      } else if (o.linsolve == B200_LINSOLVE_SPARSE_GMRES || o.linsolve == B200_LINSOLVE_SPARSE_LU) {
         nw->res.njacs += 1;
         B200_TRY(b200_sparse_jac_fill(nw->sj, nw->u, nw->nzval));
+        nw->have_factor = 0;
       }
     } else {
       new_jacobian = 0;
@@ -324,7 +401,17 @@ static int32_t newton_step_inner(b200_newton* nw) {
     b200_gmres_stats gs;
     memset(&gs, 0, sizeof(gs));
     nw->res.nsolve += 1;
-    if (!krylov) {
+    if (o.linsolve == B200_LINSOLVE_SPARSE_LU) {
+      if (!nw->have_factor) {
+        nw->res.nfactors += 1;
+        int32_t info = 0;
+        if (o.descent == B200_DESCENT_PSEUDO_TRANSIENT) return ctx->fail(B200_ERR_UNSUPPORTED, "PseudoTransient with the sparse direct solver is not offered (use dense LU or GMRES)", __FILE__, __LINE__);
+        B200_TRY(b200_sparse_lu_factor(nw->slu, nw->nzval, &info));
+        nw->have_factor = 1;
+        if (info != 0) lin_success = 0;
+      }
+      if (lin_success) B200_TRY(b200_sparse_lu_solve(nw->slu, nw->fu, nw->xlin));
+    } else if (!krylov) {
       if (!nw->have_factor) {  // update_A! for a factorisation on a fresh A (…LinearSolveExt.jl:81-86)
         nw->res.nfactors += 1;
         int32_t info = 0;
@@ -339,9 +426,15 @@ static int32_t newton_step_inner(b200_newton* nw) {
       if (o.gmres.warm_start) CUDA_TRY(ctx, cudaMemcpyAsync(nw->xlin, nw->du, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
       if (o.precond != B200_PRECOND_NONE) {  // precs(A, p): rebuilt from the current iterate, like update_A! does for Pl / Pr
         memset(&nw->prec, 0, sizeof(nw->prec));
-        nw->prec.ctx = ctx; nw->prec.kind = LINOP_BLOCK_JACOBI; nw->prec.n = n; nw->prec.prob = nw->prob; nw->prec.u = nw->u;
-        B200_TRY(b200_gmres_set_precond(nw->gm, o.precond == B200_PRECOND_BLOCK_JACOBI_LEFT ? &nw->prec : nullptr,
-                                        o.precond == B200_PRECOND_BLOCK_JACOBI_RIGHT ? &nw->prec : nullptr));
+        nw->prec.ctx = ctx; nw->prec.n = n; nw->prec.prob = nw->prob; nw->prec.u = nw->u;
+        if (nw->mg) {
+          nw->prec.kind = LINOP_MULTIGRID; nw->prec.mg = nw->mg;
+          if (new_jacobian) B200_TRY(b200i_mg_setup(nw->mg, nw->u));  // coarse operators follow the linearisation point
+        } else {
+          nw->prec.kind = LINOP_BLOCK_JACOBI;
+        }
+        const bool left = o.precond == B200_PRECOND_BLOCK_JACOBI_LEFT || o.precond == B200_PRECOND_MULTIGRID_LEFT;
+        B200_TRY(b200_gmres_set_precond(nw->gm, left ? &nw->prec : nullptr, left ? nullptr : &nw->prec));
       }
       B200_TRY(b200_gmres_solve(nw->gm, &nw->op, nw->fu, nw->xlin, &gs));
       nw->res.njvp += gs.nmatvec;
@@ -510,6 +603,18 @@ static int32_t newton_step_inner(b200_newton* nw) {
         if (rho < shrink_thr) { nw->tp1 *= nw->tp2; nw->shrink_counter += 1; }
         else { nw->shrink_counter = 0; if (rho > expand_thr) nw->tp1 = std::min(nw->tp1 * nw->tp3, nw->tp4); }
         tr = nw->tp1 * pow(nt, 0.99);
+      } else if (sch == B200_TR_BASTIN) {  // :500-520, retrospective ratio at the trial point with the step just taken
+        if (rho > step_thr) {
+          double d1, d2;
+          B200_TRY(b200_jvp(nw->prob, nw->u_trial, nw->du, nw->Jdu));
+          B200_TRY(b200_vjp(nw->prob, nw->u_trial, nw->fu_trial, nw->JTfu));
+          B200_TRY(h_dot(nw, nw->JTfu, nw->JTfu, &d1));
+          B200_TRY(b200_vjp(nw->prob, nw->u_trial, nw->Jdu, nw->JTfu));
+          B200_TRY(h_dot(nw, nw->JTfu, nw->JTfu, &d2));
+          const double rho_retro = num / (d1 + d2 / 2.0);
+          if (rho_retro >= expand_thr) tr = nw->tp1 * dun;
+          nw->shrink_counter = 0;
+        } else { tr *= nw->tp2; nw->shrink_counter += 1; }
       }
       nw->trust_region = std::min(nw->trust_region, nw->max_tr);
       if (accepted) {
@@ -527,7 +632,9 @@ static int32_t newton_step_inner(b200_newton* nw) {
     }
     nw->fnorm_inf = objective;
     bool new_best = false;
-    if (term_check(nw, objective, du_norm, &new_best)) { nw->retcode = nw->tc.retcode; nw->force_stop = 1; }  // check_and_update!
+    TermQuant tq;
+    B200_TRY(term_quantities(nw, nw->fu, nw->u, objective, &tq));
+    if (term_check(nw, tq, du_norm, &new_best)) { nw->retcode = nw->tc.retcode; nw->force_stop = 1; }  // check_and_update!
     if (new_best && nw->best_u) CUDA_TRY(ctx, cudaMemcpyAsync(nw->best_u, nw->u, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
     if (o.store_trace) {
       b200_trace_rec t;
@@ -542,14 +649,28 @@ static int32_t newton_step_inner(b200_newton* nw) {
   return B200_OK;
 }
 
+// CommonSolve.step! (NonlinearSolveBase/src/solve.jl:835-858): one step, the counters, and the wall-clock limit
+static int32_t newton_timed_step(b200_newton* nw) {
+  const bool limited = nw->o.maxtime > 0.0;
+  std::chrono::steady_clock::time_point t0;
+  if (limited) t0 = std::chrono::steady_clock::now();
+  B200_TRY(newton_step_inner(nw));
+  nw->res.nsteps += 1;
+  nw->nsteps += 1;
+  if (limited) {
+    CUDA_TRY(nw->ctx, cudaStreamSynchronize(nw->ctx->stream));
+    nw->total_time += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (!nw->force_stop && nw->retcode == B200_RC_DEFAULT && nw->total_time >= nw->o.maxtime) { nw->retcode = B200_RC_MAXTIME; nw->force_stop = 1; }
+  }
+  return B200_OK;
+}
+
 int32_t b200_newton_step(b200_newton* nw, int32_t* terminated_host) {
   B200_DEVICE_GUARD(nw ? nw->ctx : nullptr);
   b200_ctx* ctx = nw->ctx;
   B200_REQUIRE(ctx, nw->initialised, "newton_step before newton_reinit");
   if (!(nw->force_stop || nw->nsteps >= nw->maxiters)) {  // not_terminated  abstract_types.jl:722-724
-    B200_TRY(newton_step_inner(nw));
-    nw->res.nsteps += 1;  // CommonSolve.step!  NonlinearSolveBase/src/solve.jl:835-858
-    nw->nsteps += 1;
+    B200_TRY(newton_timed_step(nw));
   }
   if (terminated_host) *terminated_host = (nw->force_stop || nw->nsteps >= nw->maxiters) ? 1 : 0;
   return B200_OK;
@@ -568,11 +689,7 @@ int32_t b200_newton_solve(b200_newton* nw, b200_newton_result* result) {
   B200_DEVICE_GUARD(nw ? nw->ctx : nullptr);
   b200_ctx* ctx = nw->ctx;
   B200_REQUIRE(ctx, nw->initialised, "newton_solve before newton_reinit");
-  while (!nw->force_stop && nw->nsteps < nw->maxiters) {
-    B200_TRY(newton_step_inner(nw));
-    nw->res.nsteps += 1;
-    nw->nsteps += 1;
-  }
+  while (!nw->force_stop && nw->nsteps < nw->maxiters) B200_TRY(newton_timed_step(nw));
   if (nw->retcode == B200_RC_DEFAULT) nw->retcode = (nw->nsteps >= nw->maxiters) ? B200_RC_MAXITERS : B200_RC_SUCCESS;  // solve.jl:372-376
   // update_from_termination_cache! for Best modes: roll back to the best iterate (termination_conditions.jl:440-453)
   if (nw->best_u) {

@@ -1,0 +1,68 @@
+"""Generates tests/golden/control_sequences.json from oracle/newton_numpy.py (the independent NumPy restatement of the
+reference's scalar control logic).  Deterministic; tests/test_control_sequences.py regenerates it and compares with the
+committed file, then holds BOTH oracle/oracle.c and the CUDA driver to these sequences.
+
+    python tests/golden/make_control_golden.py
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import newton_numpy as nn  # noqa: E402
+
+SCHEMES = ["Simple", "NLsolve", "NocedalWright", "Hei", "Yuan", "Fan", "Bastin"]
+MODES = ["AbsNormSafeBest", "AbsNorm", "AbsNormSafe", "Norm", "Rel", "RelNorm", "Abs", "RelNormSafe", "RelNormSafeBest"]
+
+
+def cases():
+    out = []
+    # the reference start, and starts far enough out (10x, 30x) that steps get rejected and the line search backtracks
+    for N, scale in ((6, 1.0), (6, 10.0), (6, 30.0)):
+        base = dict(problem="bruss2d", N=N, u0_scale=scale, abstol=1e-8, reltol=1e-8)
+        out.append(dict(base, name="newton_N%d_x%g" % (N, scale)))
+        for s in SCHEMES:
+            if (scale <= 10.0 or s == "Simple") and not (s == "Bastin" and scale > 1.0):  # Bastin from 10x takes 269 steps
+                out.append(dict(base, name="tr_%s_N%d_x%g" % (s, N, scale), globalization="trust_region", tr_scheme=s))
+        out.append(dict(base, name="linesearch_N%d_x%g" % (N, scale), globalization="linesearch"))
+        if scale <= 10.0:
+            out.append(dict(base, name="pseudotransient_N%d_x%g" % (N, scale), descent="pseudo_transient", alpha_initial=1.0, maxiters=200))
+    out.append(dict(problem="quadratic", n=10, name="pseudotransient_quadratic_alpha10", descent="pseudo_transient", alpha_initial=10.0, abstol=1e-9, reltol=1e-9))
+    for m in MODES:
+        for norm in ("inf", "l2"):
+            out.append(dict(problem="bruss2d", N=6, u0_scale=1.0, name="term_%s_%s" % (m, norm), termination=m, term_norm=norm, abstol=1e-7, reltol=1e-9))
+    out.append(dict(problem="bruss2d", N=6, u0_scale=1.0, name="maxiters_2", maxiters=2, abstol=1e-12, reltol=1e-12))
+    return out
+
+
+def run(case):
+    if case["problem"] == "bruss2d":
+        prob = nn.Brusselator2D(case["N"])
+        u0 = prob.u0() * case["u0_scale"]
+    else:
+        prob = nn.Quadratic(case["n"])
+        u0 = np.ones(case["n"])
+    term = nn.Termination(mode=case.get("termination", "AbsNormSafeBest"), norm=case.get("term_norm", "inf"), abstol=case["abstol"], reltol=case["reltol"])
+    r = nn.solve(prob, u0, globalization=case.get("globalization", "none"), tr_scheme=case.get("tr_scheme", "Simple"), descent=case.get("descent", "newton"),
+                 alpha_initial=case.get("alpha_initial", 1e-3), termination=term, maxiters=case.get("maxiters", 1000))
+    u = r.pop("u")
+    r["u_norm2"] = float(np.linalg.norm(u))
+    r["u_first"] = [float(x) for x in u[:4]]
+    return r
+
+
+def generate():
+    return [dict(case=c, expect=run(c)) for c in cases()]
+
+
+if __name__ == "__main__":
+    data = generate()
+    path = os.path.join(ROOT, "tests", "golden", "control_sequences.json")
+    with open(path, "w") as f:
+        json.dump(data, f, indent=1)
+    for d in data:
+        e = d["expect"]
+        print("%-40s rc=%d nsteps=%d nf=%d njacs=%d acc=%s" % (d["case"]["name"], e["retcode"], e["nsteps"], e["nf"], e["njacs"], "".join(map(str, e["accepted"]))[:40]))

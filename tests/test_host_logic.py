@@ -30,10 +30,11 @@ def test_defaults_match_the_reference(nls):
     assert o.gmres.atol == 0.0 and o.gmres.rtol == 0.0                                                          # inherit abstol / reltol (solve.jl:203)
     assert o.max_shrink_times == 32 and (o.ew_eta0, o.ew_eta_max, o.ew_gamma, o.ew_alpha) == (0.5, 0.9, 0.9, 2.0)  # eisenstat_walker.jl:18-30
     assert o.jvp_mode == abi.JVP_EXACT
-    # linsolve = nothing: dense LU for a dense J, GMRES on the assembled J for a sparse one
+    # linsolve = nothing: dense LU for a dense J, the sparse direct factorisation for a sparse one (LinearSolve's defaults)
     assert _opts(nls, nls.NewtonRaphson()).linsolve == abi.LINSOLVE_DENSE_LU
     fs = nls.NonlinearFunction(nls.Brusselator2D(8), sparsity=nls.TracerSparsityDetector())
-    assert _opts(nls, nls.NewtonRaphson(), f=fs).linsolve == abi.LINSOLVE_SPARSE_GMRES
+    assert _opts(nls, nls.NewtonRaphson(), f=fs).linsolve == abi.LINSOLVE_SPARSE_LU
+    assert _opts(nls, nls.NewtonRaphson(linsolve=nls.KLUFactorization()), f=fs).linsolve == abi.LINSOLVE_SPARSE_LU
     assert _opts(nls, nls.NewtonRaphson(linsolve=nls.KrylovJL_GMRES()), f=fs).linsolve == abi.LINSOLVE_SPARSE_GMRES
     assert _opts(nls, nls.NewtonRaphson(linsolve=nls.KrylovJL_GMRES(), concrete_jac=True)).linsolve == abi.LINSOLVE_SPARSE_GMRES
 
@@ -48,6 +49,11 @@ def test_algorithm_options_reach_the_struct(nls):
     o = _opts(nls, nls.PseudoTransient(alpha_initial=0.25, linsolve=nls.KrylovJL_GMRES(precs=nls.BlockJacobi("right"), orth="mgs", gmres_restart=30)))
     assert (o.descent, o.pt_alpha_initial, o.precond) == (abi.DESCENT_PSEUDO_TRANSIENT, 0.25, abi.PRECOND_BLOCK_JACOBI_RIGHT)
     assert (o.gmres.orth, o.gmres.restart) == (abi.ORTH_MGS, 30)
+    o = _opts(nls, nls.NewtonRaphson(linsolve=nls.KrylovJL_GMRES(precs=nls.Multigrid("right"))), maxtime=2.5,
+              termination_condition=nls.RelNormSafeBestTerminationMode(norm="l2", max_stalled_steps=None))
+    assert (o.precond, o.maxtime, o.termination, o.term_norm, o.term_max_stalled_steps) == (abi.PRECOND_MULTIGRID_RIGHT, 2.5, abi.TERM_REL_NORM_SAFE_BEST, abi.NORM_L2, -1)
+    o = _opts(nls, nls.TrustRegion(radius_update_scheme=nls.RadiusUpdateSchemes.Bastin))
+    assert o.tr_scheme == abi.TR_BASTIN == 6
     o = _opts(nls, nls.NewtonRaphson(linsolve=nls.KrylovJL_GMRES(), forcing=nls.EisenstatWalkerForcing2(), jvp_autodiff=nls.AutoFiniteDiff()),
               termination_condition=nls.AbsNormTerminationMode())
     assert o.forcing == abi.FORCING_EW2 and o.jvp_mode == abi.JVP_FINITE_DIFF and o.termination == nls.AbsNormTerminationMode().code
