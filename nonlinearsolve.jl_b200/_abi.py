@@ -199,7 +199,6 @@ SIGNATURES = {
 EXTRA_SIGNATURES = {
     "b200_gmres_keep_hessenberg": (I32, [P, I64]),
     "b200_gmres_get_hessenberg": (I32, [P, P, I64]),
-    "b200_gmres_debug": (I32, [P, I32, P, I32]),
 }
 
 _lib = None

@@ -356,7 +356,7 @@ class KrylovJL_GMRES:
                  engine="auto", block=0, precs=None):
         # precs: LinearSolve's `precs = (A, p) -> (Pl, Pr)`; here a BlockJacobi(side) descriptor of the built-in preconditioner
         self.precs = precs
-        self.block = block  # Gram-Schmidt in L2-sized blocks of this many basis vectors (0: whole basis, -1: automatic)
+        self.block = 0      # reserved (the L2-blocked Gram-Schmidt of round 1 was slower than the streaming kernels and is gone)
         self.gmres_restart, self.memory, self.itmax, self.orth = gmres_restart, memory, itmax, orth
         self.warm_start, self.atol, self.rtol, self.check_every, self.engine = warm_start, atol, rtol, check_every, engine
 

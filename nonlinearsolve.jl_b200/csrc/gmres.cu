@@ -68,8 +68,6 @@ __device__ __forceinline__ void block_rows(int64_t n, int64_t& r0, int64_t& r1) 
 }
 
 // ---- h[c] partials: partial[c * G + blockIdx.x] = sum over this CTA's rows of V[c][r] * w[r]
-//      KEEP = true: the columns are loaded with the default policy so that they stay in L2 for the blocked update sweep.
-template <bool KEEP>
 __global__ void __launch_bounds__(GM_THREADS) multidot_kernel(const GmresState* __restrict__ st, const double* const* __restrict__ V,
                                                                int k, const double* __restrict__ w, int64_t n,
                                                                double* __restrict__ partial) {
@@ -92,12 +90,7 @@ __global__ void __launch_bounds__(GM_THREADS) multidot_kernel(const GmresState* 
         double2 v2[JT];
 #pragma unroll
         for (int c = 0; c < JT; ++c) {
-          if (KEEP) {
-            if (c0 + c < k) v2[c] = *reinterpret_cast<const double2*>(vp[c] + r);
-            else v2[c] = make_double2(0.0, 0.0);
-          } else {
-            v2[c] = __ldcs(reinterpret_cast<const double2*>(vp[c] + r));  // streamed once: evict-first
-          }
+          v2[c] = __ldcs(reinterpret_cast<const double2*>(vp[c] + r));  // streamed once: evict-first
         }
 #pragma unroll
         for (int c = 0; c < JT; ++c) acc[c] = fma(v2[c].x, w2.x, fma(v2[c].y, w2.y, acc[c]));
@@ -182,66 +175,6 @@ __global__ void __launch_bounds__(GM_THREADS) update_kernel(const GmresState* __
       double w1 = w_in[r];
       for (int c = 0; c < k; ++c) w1 = fma(hc[c], V[c][r], w1);
       w_out[r] = w1;
-      nacc = fma(w1, w1, nacc);
-    }
-  }
-  if (norm_partial) {
-    nacc = block_sum(nacc, red);
-    if (threadIdx.x == 0) norm_partial[blockIdx.x] = nacc;
-  }
-}
-
-// ---- blocked Gram-Schmidt update: coefficients of the kb (<= JT) columns of this block are reduced in-kernel from the
-//      multi-dot partials (every CTA sums the same G partials in the same order: deterministic, no extra launch), then
-//      w -= sum_c coef[c] V[c].  CTA 0 publishes the coefficients: h[c] = coef (first pass) or h[c] += coef (second pass).
-//      The block's vectors were just streamed by the multi-dot sweep and are re-read here from L2, so the basis crosses
-//      HBM once per Gram-Schmidt pass instead of twice.
-__global__ void __launch_bounds__(GM_THREADS) update_block_kernel(const GmresState* __restrict__ st, const double* const* __restrict__ V,
-                                                                   int kb, const double* __restrict__ partial, int accumulate,
-                                                                   double* __restrict__ h, double* w, int64_t n,
-                                                                   double* __restrict__ norm_partial) {
-  if (st->status != 0) return;
-  __shared__ double hc[JT];
-  __shared__ double red[32];
-  const int G = gridDim.x;
-  {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (wid < kb) {
-      double s = 0.0;
-      for (int b = lane; b < G; b += 32) s += partial[(int64_t)wid * G + b];
-      s = warp_sum(s);
-      if (lane == 0) {
-        hc[wid] = s;
-        if (blockIdx.x == 0) h[wid] = accumulate ? h[wid] + s : s;
-      }
-    }
-  }
-  __syncthreads();
-  int64_t r0, r1;
-  block_rows(n, r0, r1);
-  double nacc = 0.0;
-  const double* vp[JT];
-#pragma unroll
-  for (int c = 0; c < JT; ++c) vp[c] = V[c < kb ? c : 0];
-  for (int64_t r = r0 + 2 * threadIdx.x; r < r1; r += 2 * GM_THREADS) {
-    if (r + 1 < r1) {
-      double2 w2 = *reinterpret_cast<const double2*>(w + r);
-      double2 v2[JT];
-#pragma unroll
-      for (int c = 0; c < JT; ++c)
-        if (c < kb) v2[c] = __ldcs(reinterpret_cast<const double2*>(vp[c] + r));  // last use of the block: evict first
-#pragma unroll
-      for (int c = 0; c < JT; ++c)
-        if (c < kb) {
-          w2.x = fma(-hc[c], v2[c].x, w2.x);
-          w2.y = fma(-hc[c], v2[c].y, w2.y);
-        }
-      *reinterpret_cast<double2*>(w + r) = w2;
-      nacc = fma(w2.x, w2.x, fma(w2.y, w2.y, nacc));
-    } else {
-      double w1 = w[r];
-      for (int c = 0; c < kb; ++c) w1 = fma(-hc[c], vp[c][r], w1);
-      w[r] = w1;
       nacc = fma(w1, w1, nacc);
     }
   }
@@ -459,20 +392,17 @@ __global__ void __launch_bounds__(GM_THREADS) dense_gemv_kernel(int trans, int64
 }
 // =====================================================================================================================
 // Resident Arnoldi step (engine B200_ENGINE_RESIDENT): ONE cooperative kernel per Arnoldi iteration for the built-in
-// Brusselator operators.  One CTA per SM; CTA b owns the cells [b*cpc, (b+1)*cpc) of both species for the whole step:
-//   1. w = J(u) v_k is evaluated straight into registers (RR rows per thread) — it never touches HBM;
-//   2. the Krylov basis is streamed through shared memory ONCE per Gram-Schmidt pass by TMA bulk copies
-//      (cp.async.bulk + mbarrier, two stages: v_{i+1} lands while v_i is being used); per basis vector: dot partial ->
-//      grid barrier -> every CTA sums the same per-CTA partials in the same order (deterministic) -> w -= h_i v_i
-//      from the copy still in shared memory.  This is modified Gram-Schmidt (Krylov.jl's scheme), applied twice when
-//      reorthogonalisation is requested: `passes * k * Bv` of HBM traffic instead of the 2x of the multi-kernel engine;
+// Brusselator operators (or an assembled sparse Jacobian through its CSR view).  One CTA per SM; CTA b owns the cells
+// [b*cpc, (b+1)*cpc) of both species for the whole step:
+//   1. w = J(u) v_k is evaluated straight into registers — it never touches HBM;
+//   2. the Krylov basis is streamed ONCE per Gram-Schmidt pass (TMA bulk copies into two shared-memory stages + a third
+//      stage in registers); per basis vector: dot partial -> cross-CTA exchange -> w -= h_i v_i from the copy still on
+//      chip.  That is modified Gram-Schmidt (Krylov.jl's scheme), applied twice when reorthogonalisation is requested:
+//      `passes * k * Bv` of HBM traffic instead of the 2x of the multi-kernel engine;
 //   3. ||w||, Givens recurrence (CTA 0), normalisation and the store of v_{k+1} close the step.
 // Cross-CTA exchanges poll with bounded spins so a fault can never hang the GPU (cooperative launch guarantees co-residency).
-constexpr int RS_THREADS = 512;
-constexpr int RS_RR = 28;  // max rows per thread -> at most 28 * 512 = 14336 rows (7168 cells) per CTA
-
 struct ResidentParams {
-  int dim, N, k, passes, G, late_issue;
+  int dim, N, k, passes, G;
   int opkind;       // 0: built-in Brusselator J(u) v, 1: assembled sparse matrix through its CSR view
   const int64_t *rowptr, *csr_col, *csr_map;
   const double* nzval;
@@ -482,9 +412,8 @@ struct ResidentParams {
   const double* u;
   const double* const* V;
   double* vnew;     // V[k]
-  unsigned long long* slots;  // [2][G][2] ping-pong {data32 | epoch << 32} words (NCCL-LL style flag-in-word publication)
+  unsigned long long* slots;  // four rotating exchange tables of {data32 | epoch << 32} words (NCCL-LL style flag-in-word publication)
   unsigned epoch_base;        // unique, monotonically increasing across launches
-  double* dbg;                // optional phase timers (cycles) of CTA 0: wait, dot, gather, update, steps
   int* err;
   double* h;        // Hessenberg column workspace (k + 1)
   double* gsub;     // r3g kernel: gsub[i] = <v_i, v_{i-1}>, written by the step that creates v_i
@@ -492,62 +421,10 @@ struct ResidentParams {
   GmresState* st;
 };
 
-// Cross-CTA all-to-all of one double per CTA with the synchronisation folded into the data (the idea of NCCL's LL
-// protocol): each 64-bit word carries 32 data bits and a 32-bit epoch, and 64-bit stores are single transactions, so a
-// reader that sees the expected epoch in both words has the value — no fence, no atomic, no separate barrier, one L2 round
-// trip.  Two slot buffers alternate by step parity: a CTA can only overwrite a buffer two steps later, i.e. after every
-// other CTA has passed the step in between and therefore finished reading the older value.
-// Every slot sits in its own 256-byte block so that the all-to-all polls spread over the L2 slices instead of hammering one.
+// Cross-CTA exchange with the synchronisation folded into the data (the idea of NCCL's LL protocol): each 64-bit word
+// carries 32 data bits and a 32-bit epoch, and 64-bit stores are single transactions, so a reader that sees the expected
+// epoch in every word of an entry has the value — no fence, no atomic, no separate barrier, one L2 round trip.
 constexpr int LL_MAXG = 160;
-// PUSH model (NCCL-LL all-gather style): CTA b posts its word pair into slot b of EVERY destination CTA's private receive
-// buffer (posted, uncoalesced stores that nobody waits on); each CTA then polls only its own dense buffer with coalesced
-// 128-bit loads (G * 16 bytes = 19 cache lines, no reader contention).  Called by all lanes of warp 0.
-__device__ __forceinline__ void ll_publish(unsigned long long* slots, int b, int G, double v, unsigned epoch) {
-  const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
-  const unsigned long long w0 = (bits & 0xffffffffull) | ((unsigned long long)epoch << 32);
-  const unsigned long long w1 = (bits >> 32) | ((unsigned long long)epoch << 32);
-  const int lane = threadIdx.x & 31;
-#pragma unroll
-  for (int q = 0; q < 5; ++q) {
-    const int dest = lane + 32 * q;
-    if (dest < G) asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(slots + 2 * ((size_t)dest * LL_MAXG + b)), "l"(w0), "l"(w1) : "memory");
-  }
-}
-constexpr int LL_PER_LANE = 5;  // up to 160 CTAs
-#ifndef P_LL_SLEEP
-#define P_LL_SLEEP 0
-#endif
-__device__ __forceinline__ double ll_gather_sum(const unsigned long long* slots, int G, unsigned epoch, int* err, unsigned* rounds = nullptr) {
-  const int lane = threadIdx.x & 31;
-  const unsigned long long* mine = slots + 2 * (size_t)blockIdx.x * LL_MAXG;  // this CTA's receive buffer
-  unsigned long long w0[LL_PER_LANE], w1[LL_PER_LANE];
-  unsigned spins = 0;
-  bool ok;
-  if (P_LL_SLEEP > 0) __nanosleep(P_LL_SLEEP);  // the answer cannot be there earlier than one L2 round trip: do not add load
-  do {
-    ok = true;
-#pragma unroll
-    for (int q = 0; q < LL_PER_LANE; ++q) {
-      const int s = lane + 32 * q;
-      if (s < G) asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0[q]), "=l"(w1[q]) : "l"(mine + 2 * s) : "memory");
-    }
-#pragma unroll
-    for (int q = 0; q < LL_PER_LANE; ++q) {
-      const int s = lane + 32 * q;
-      if (s < G) ok = ok && ((unsigned)(w0[q] >> 32) == epoch) && ((unsigned)(w1[q] >> 32) == epoch);
-    }
-    if (++spins > (1u << 22)) { *err = 1; break; }  // bounded: a fault can never hang the GPU
-  } while (!__all_sync(0xffffffffu, ok));
-  if (rounds) *rounds += spins;
-  double s = 0.0;
-#pragma unroll
-  for (int q = 0; q < LL_PER_LANE; ++q) {
-    const int sl = lane + 32 * q;
-    if (sl < G) s += __longlong_as_double((long long)((w0[q] & 0xffffffffull) | (w1[q] << 32)));
-  }
-  return warp_sum(s);
-}
-
 __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
 }
@@ -603,160 +480,10 @@ __device__ __forceinline__ void resident_givens_tail(const ResidentParams& P, do
     st->status = status;
   }
 
-__global__ void __launch_bounds__(RS_THREADS, 1) resident_arnoldi_kernel(ResidentParams P) {
-  if (P.st->status != 0) return;  // uniform across the grid: nobody reaches a barrier
-  extern __shared__ __align__(16) double rsm[];
-  const int cpc = P.cpc;
-  const int rows_cap = 2 * cpc;              // rows of one stage
-  double* stage0 = rsm;
-  double* stage1 = rsm + rows_cap;
-  __shared__ uint64_t mbar[2];
-  __shared__ double red[32];
-  __shared__ double hshare;
-  const int tid = threadIdx.x, b = blockIdx.x, G = P.G;
-  const int64_t c0 = (int64_t)b * cpc;
-  const int ncell = (int)max((int64_t)0, min((int64_t)cpc, P.NC - c0));  // even (NC and cpc are even)
-  const int nrow = 2 * ncell;
-  const unsigned seg_bytes = (unsigned)ncell * 8u;
-  if (tid == 0) {
-    mbar_init(&mbar[0], 1);
-    mbar_init(&mbar[1], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  // ---- 1. w = J(u) v_k for this CTA's rows, into registers
-  const double* vk = P.V[P.k - 1];
-  double w[RS_RR];
-  const int N = P.N;
-  const int64_t N2 = (int64_t)N * N, NC = P.NC;
-#pragma unroll
-  for (int q = 0; q < RS_RR; ++q) {
-    const int lr = tid + RS_THREADS * q;
-    w[q] = 0.0;
-    if (lr < nrow && P.opkind == 1) {
-      const int s = lr >= ncell;
-      const int64_t r = (int64_t)s * NC + c0 + (lr - s * ncell);
-      double acc = 0.0;
-      for (int64_t e = P.rowptr[r], e1 = P.rowptr[r + 1]; e < e1; ++e) acc = fma(P.nzval[P.csr_map[e]], vk[P.csr_col[e]], acc);
-      w[q] = acc;
-    } else if (lr < nrow) {
-      const int s = lr >= ncell;
-      const int64_t c = c0 + (lr - s * ncell);
-      int64_t cim, cip, cjm, cjp, ckm = 0, ckp = 0;
-      if (P.dim == 3) {
-        const int kk = (int)(c / N2);
-        const int r = (int)(c - (int64_t)kk * N2);
-        const int j = r / N, i = r - j * N;
-        cim = c + ((i == 0) ? (N - 1) : -1); cip = c + ((i + 1 == N) ? -(N - 1) : 1);
-        cjm = c + ((j == 0) ? (int64_t)(N - 1) * N : -N); cjp = c + ((j + 1 == N) ? -(int64_t)(N - 1) * N : N);
-        ckm = c + ((kk == 0) ? (int64_t)(N - 1) * N2 : -N2); ckp = c + ((kk + 1 == N) ? -(int64_t)(N - 1) * N2 : N2);
-      } else {
-        const int j = (int)(c / N), i = (int)(c - (int64_t)j * N);
-        cim = c + ((i == 0) ? (N - 1) : -1); cip = c + ((i + 1 == N) ? -(N - 1) : 1);
-        cjm = c + ((j == 0) ? (int64_t)(N - 1) * N : -N); cjp = c + ((j + 1 == N) ? -(int64_t)(N - 1) * N : N);
-      }
-      const double* x = vk + (int64_t)s * NC;
-      const double xc = x[c];
-      double lap = x[cim] + x[cip] + x[cjp] + x[cjm] - 4.0 * xc;
-      if (P.dim == 3) lap = lap + (x[ckp] + x[ckm] - 2.0 * xc);
-      const double uc = P.u[c], vc = P.u[c + NC], dc = vk[c], ec = vk[c + NC];
-      const double uv2 = 2.0 * uc * vc, uu = uc * uc;
-      w[q] = s ? (P.a * lap + (P.A - uv2) * dc - uu * ec) : (P.a * lap + (uv2 - (P.A + 1.0)) * dc + uu * ec);
-    }
-  }
-  // ---- 2. (iterated) modified Gram-Schmidt with the basis streamed through shared memory by TMA bulk copies
-  const int k = P.k, total = P.passes * k;
-  auto issue = [&](int t) {  // load basis vector (t % k) into stage (t & 1)
-    if (tid == 0 && nrow > 0) {
-      const double* src = P.V[t % k];
-      double* dst = (t & 1) ? stage1 : stage0;
-      mbar_expect_tx(&mbar[t & 1], 2u * seg_bytes);
-      tma_bulk_load(dst, src + c0, seg_bytes, &mbar[t & 1]);
-      tma_bulk_load(dst + ncell, src + NC + c0, seg_bytes, &mbar[t & 1]);
-    }
-  };
-  long long acc_wait = 0, acc_dot = 0, acc_gather = 0, acc_update = 0;
-  unsigned poll_rounds = 0;
-  issue(0);
-  for (int t = 0; t < total; ++t) {
-    const int i = t % k;
-    __syncthreads();                     // every thread is done reading stage (t+1)&1 (used by step t-1)
-    if (!P.late_issue && t + 1 < total) issue(t + 1);     // prefetch the next basis vector underneath this step
-    const double* vs = (t & 1) ? stage1 : stage0;
-    long long tc0 = clock64();
-    if (nrow > 0) mbar_wait(&mbar[t & 1], (unsigned)((t >> 1) & 1));
-    long long tc1 = clock64();
-    double d = 0.0;
-#pragma unroll
-    for (int q = 0; q < RS_RR; ++q) {
-      const int lr = tid + RS_THREADS * q;
-      if (lr < nrow) d = fma(vs[lr], w[q], d);
-    }
-    d = block_sum(d, red);
-    long long tc2 = clock64();
-    // publish this CTA's partial and gather everybody's in ONE round trip (no atomics, no separate barrier): the
-    // reduction over CTAs is done identically by every CTA, in a fixed order -> deterministic and identical everywhere
-    unsigned long long* slots = P.slots + (size_t)(t & 1) * 2 * LL_MAXG * LL_MAXG;
-    const unsigned epoch = P.epoch_base + (unsigned)t + 1u;
-    if (tid < 32) {
-      if (tid == 0) red[0] = d;  // block_sum leaves the total in thread 0 only
-      __syncwarp();
-      ll_publish(slots, b, G, red[0], epoch);
-      const double s = ll_gather_sum(slots, G, epoch, P.err, &poll_rounds);
-      if (tid == 0) hshare = s;
-    }
-    __syncthreads();
-    if (P.late_issue && t + 1 < total) issue(t + 1);
-    long long tc3 = clock64();
-    const double h = hshare;
-#pragma unroll
-    for (int q = 0; q < RS_RR; ++q) {
-      const int lr = tid + RS_THREADS * q;
-      if (lr < nrow) w[q] = fma(-h, vs[lr], w[q]);
-    }
-    if (b == 0 && tid == 0) P.h[i] = (t < k) ? h : P.h[i] + h;
-    if (P.dbg && tid == 0) {
-      long long tc4 = clock64();
-      acc_wait += tc1 - tc0; acc_dot += tc2 - tc1; acc_gather += tc3 - tc2; acc_update += tc4 - tc3;
-    }
-  }
-  if (P.dbg && tid == 0) {  // per-CTA phase totals (cycles), written once: [b*4 + phase]; steps in dbg[4*G]
-    P.dbg[4 * b + 0] += (double)acc_wait; P.dbg[4 * b + 1] += (double)acc_dot; P.dbg[4 * b + 2] += (double)acc_gather; P.dbg[4 * b + 3] += (double)acc_update;
-    if (b == 0) { P.dbg[4 * G] += (double)total; P.dbg[4 * G + 1] += (double)poll_rounds; }
-  }
-  // ---- 3. ||w||, Givens (CTA 0), normalise, store v_{k+1}
-  double nacc = 0.0;
-#pragma unroll
-  for (int q = 0; q < RS_RR; ++q) nacc = fma(w[q], w[q], nacc);
-  nacc = block_sum(nacc, red);
-  {
-    unsigned long long* slots = P.slots + (size_t)(total & 1) * 2 * LL_MAXG * LL_MAXG;
-    const unsigned epoch = P.epoch_base + (unsigned)total + 1u;
-    if (tid < 32) {
-      if (tid == 0) red[0] = nacc;
-      __syncwarp();
-      ll_publish(slots, b, G, red[0], epoch);
-      const double s = ll_gather_sum(slots, G, epoch, P.err);
-      if (tid == 0) hshare = s;
-    }
-  }
-  __syncthreads();
-  const double hbis = sqrt(hshare);
-  const double inv = hbis > 0.0 ? 1.0 / hbis : 0.0;
-#pragma unroll
-  for (int q = 0; q < RS_RR; ++q) {
-    const int lr = tid + RS_THREADS * q;
-    if (lr < nrow) {
-      const int s = lr >= ncell;
-      P.vnew[(int64_t)s * NC + c0 + (lr - s * ncell)] = w[q] * inv;
-    }
-  }
-  if (b == 0 && tid == 0) resident_givens_tail(P, hbis, inv);
-}
 // =====================================================================================================================
-// Three-stage, lag-1 variant of the resident Arnoldi step (engine RESIDENT, chosen when the rows of one SM fit 54 per
-// thread at 256 threads): the two shared-memory stages are joined by a THIRD stage held in registers (54 more doubles per
-// thread, filled by 128-bit global loads that stay in flight for a whole step), so three basis vectors are on chip and the
+// Three-stage, lag-1 organisation of the resident Arnoldi step (rows of one SM fit 54 per thread at 256 threads): the two
+// shared-memory stages are joined by a THIRD stage held in registers (48 more doubles per thread, filled by 128-bit global
+// loads that stay in flight for a whole step, + a small cp.async annex), so three basis vectors are on chip and the
 // exchange of vector t overlaps the dot products of vector t+1:
 //     h_{t+1} = <v_{t+1}, w_t> - h_t <v_{t+1}, v_t>          (w_t: w before the update with v_t)
 // which are the modified Gram-Schmidt coefficients exactly (the cross product restores the missing update); the pair
@@ -807,53 +534,6 @@ __device__ __forceinline__ void r3_poll(const unsigned long long* buf, int b, in
   }
 }
 
-struct R3Shared {
-  uint64_t mbar[2];
-  double redA[8], redC[8], gA[8], gC[8];
-  long long acc[4], tl;  // debug phase timers (thread 0)
-#ifdef B200_R3_HAZARD_FREE
-  // racecheck-clean variant (profiles/README.md, "compute-sanitizer"): the prologue reduces through its own scratch and
-  // the poll scratch alternates with the step parity, so no write can meet a read of the previous step without a barrier
-  // in between.  Not the default until it has been timed: the 255-register allocation of this kernel moves with any edit.
-  double redPA[8], redPC[8], gA2[8], gC2[8];
-#endif
-};
-#ifdef B200_R3_HAZARD_FREE
-#define R3_GA(t) (((t) & 1) ? sh.gA2 : sh.gA)
-#define R3_GC(t) (((t) & 1) ? sh.gC2 : sh.gC)
-#else
-#define R3_GA(t) (sh.gA)
-#define R3_GC(t) (sh.gC)
-#endif
-
-// block reduction of (da, dc) over 8 warps; result valid in every lane of warp 0.  One __syncthreads.
-__device__ __forceinline__ void r3_reduce2(double& da, double& dc, R3Shared& sh, bool prologue = false) {
-  const int tid = threadIdx.x;
-#ifdef B200_R3_HAZARD_FREE
-  double* const ra = prologue ? sh.redPA : sh.redA;
-  double* const rc = prologue ? sh.redPC : sh.redC;
-#else
-  double* const ra = sh.redA;
-  double* const rc = sh.redC;
-  (void)prologue;
-#endif
-  da = warp_sum(da);
-  dc = warp_sum(dc);
-  if ((tid & 31) == 0) { ra[tid >> 5] = da; rc[tid >> 5] = dc; }
-  __syncthreads();
-  if (tid < 32) {
-    da = (tid < R3_THREADS / 32) ? ra[tid] : 0.0;
-    dc = (tid < R3_THREADS / 32) ? rc[tid] : 0.0;
-    da = warp_sum(da);
-    dc = warp_sum(dc);
-  }
-}
-
-#ifdef B200_R3_TIMERS
-#define R3_TICK(ph) do { if (P.dbg && threadIdx.x == 0) { const long long c_ = clock64(); sh.acc[ph] += c_ - sh.tl; sh.tl = c_; } } while (0)
-#else
-#define R3_TICK(ph) do { } while (0)
-#endif
 struct R3Ctx {
   double *stage0, *stage1;
   double2* annex;
@@ -941,161 +621,6 @@ __device__ __forceinline__ void r3_apply_operator(const ResidentParams& P, const
   }
 }
 
-// One Gram-Schmidt step for the vector of step t whose stage role is ROLE = t % 3.
-template <int ROLE>
-__device__ __forceinline__ void r3_step(const ResidentParams& P, R3Ctx& cx, R3Shared& sh, int t, double (&w)[R3_ROWS], double (&vr)[R3_VR], double& hprev) {
-  constexpr int NEXT = (ROLE + 1) % 3;
-  const int tid = threadIdx.x;
-  const double* sc = ROLE == 0 ? cx.stage0 : cx.stage1;   // current vector if it lives in shared memory
-  const double* sn = NEXT == 0 ? cx.stage0 : cx.stage1;   // next vector if it lives in shared memory
-  if (t + 1 < cx.total) {
-    if (NEXT != 2 && cx.nrow > 0 && (P.late_issue != 7 || t < 2)) mbar_wait(&sh.mbar[NEXT], (unsigned)(((t + 1) / 3) & 1));
-    if (NEXT == 2) asm volatile("cp.async.wait_group 0;" ::: "memory");
-    R3_TICK(0);
-    double da = 0.0, dc = 0.0;
-#pragma unroll
-    for (int q = 0; q < R3_RP; ++q) {
-      const int lr = 2 * (tid + R3_THREADS * q);
-      if (lr < cx.nrow) {
-        double x0, x1, y0, y1;
-        if (NEXT == 2) { R3_VRGET(q, x0, x1); }
-        else { const double2 x = *reinterpret_cast<const double2*>(sn + lr); x0 = x.x; x1 = x.y; }
-        if (ROLE == 2) { R3_VRGET(q, y0, y1); }
-        else { const double2 y = *reinterpret_cast<const double2*>(sc + lr); y0 = y.x; y1 = y.y; }
-        da = fma(x0, w[2 * q], da); da = fma(x1, w[2 * q + 1], da);
-        dc = fma(x0, y0, dc); dc = fma(x1, y1, dc);
-      }
-    }
-    r3_reduce2(da, dc, sh);
-    if (tid < 32) r3_post(P.slots + (size_t)((t + 1) & 3) * R3_BUF_WORDS, cx.b, da, dc, P.epoch_base + (unsigned)(t + 1) + 1u);
-    R3_TICK(1);
-  }
-  double* const ga = R3_GA(t);
-  double* const gc = R3_GC(t);
-  r3_poll(P.slots + (size_t)(t & 3) * R3_BUF_WORDS, cx.b, cx.G, P.epoch_base + (unsigned)t + 1u, P.err, ga, gc);
-  __syncthreads();
-  R3_TICK(2);
-  const double sa = ((ga[0] + ga[1]) + (ga[2] + ga[3])) + ga[4];
-  const double scs = ((gc[0] + gc[1]) + (gc[2] + gc[3])) + gc[4];
-  const double h = sa - hprev * scs;
-  hprev = h;
-#pragma unroll
-  for (int q = 0; q < R3_RP; ++q) {
-    const int lr = 2 * (tid + R3_THREADS * q);
-    if (lr < cx.nrow) {
-      double y0, y1;
-      if (ROLE == 2) { R3_VRGET(q, y0, y1); }
-      else { const double2 y = *reinterpret_cast<const double2*>(sc + lr); y0 = y.x; y1 = y.y; }
-      w[2 * q] = fma(-h, y0, w[2 * q]);
-      w[2 * q + 1] = fma(-h, y1, w[2 * q + 1]);
-    }
-  }
-  if (cx.b == 0 && tid == 0) { const int i = t % cx.k; P.h[i] = (t < cx.k) ? h : P.h[i] + h; }
-  if (ROLE != 2) {
-    __syncthreads();  // every thread is done with this shared-memory stage
-    if (t + 3 < cx.total && P.late_issue != 7) r3_issue_smem(P, cx, sh.mbar, t + 3, ROLE);
-  } else {
-    if (t + 3 < cx.total && P.late_issue != 7) r3_issue_regs(P, cx, t + 3, vr);
-  }
-  R3_TICK(3);
-}
-
-__global__ void __launch_bounds__(R3_THREADS, 1) resident3_arnoldi_kernel(ResidentParams P) {
-  if (P.st->status != 0) return;
-  extern __shared__ __align__(16) double rsm[];
-  __shared__ R3Shared sh;
-  R3Ctx cx;
-  const int cpc = P.cpc;
-  cx.stage0 = rsm;
-  cx.stage1 = rsm + 2 * cpc;
-  cx.annex = reinterpret_cast<double2*>(rsm + 4 * cpc);
-  const int tid = threadIdx.x, b = blockIdx.x, G = P.G;
-  cx.b = b; cx.G = G; cx.k = P.k; cx.total = P.passes * P.k;
-  cx.ncell = (int)max((int64_t)0, min((int64_t)cpc, P.NC - (int64_t)b * cpc));
-  cx.nrow = 2 * cx.ncell;
-  if (tid == 0) {
-    mbar_init(&sh.mbar[0], 1);
-    mbar_init(&sh.mbar[1], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  // the first two basis vectors start travelling while the operator is applied
-  r3_issue_smem(P, cx, sh.mbar, 0, 0);
-  if (cx.total > 1) r3_issue_smem(P, cx, sh.mbar, 1, 1);
-  // ---- 1. w = J(u) v_k (or the assembled sparse matrix times v_k) for this CTA's rows, into registers
-  double w[R3_ROWS];
-  double vr[R3_VR];
-  r3_apply_operator(P, cx, w);
-  const int ncell = cx.ncell, nrow = cx.nrow;
-  const int64_t NC = P.NC, c0 = (int64_t)b * cpc;
-  // ---- 2. lag-1 modified Gram-Schmidt over three rotating stages
-  const int total = cx.total;
-  if (total > 2) r3_issue_regs(P, cx, 2, vr);
-  {
-    if (nrow > 0) mbar_wait(&sh.mbar[0], 0u);
-    double da = 0.0, dc = 0.0;
-#pragma unroll
-    for (int q = 0; q < R3_RP; ++q) {
-      const int lr = 2 * (tid + R3_THREADS * q);
-      if (lr < nrow) {
-        const double2 x = *reinterpret_cast<const double2*>(cx.stage0 + lr);
-        da = fma(x.x, w[2 * q], da); da = fma(x.y, w[2 * q + 1], da);
-      }
-    }
-    r3_reduce2(da, dc, sh, true);
-    if (tid < 32) r3_post(P.slots, b, da, 0.0, P.epoch_base + 1u);
-  }
-  double hprev = 0.0;
-#ifdef B200_R3_TIMERS
-  if (P.dbg && tid == 0) { sh.acc[0] = sh.acc[1] = sh.acc[2] = sh.acc[3] = 0; sh.tl = clock64(); }
-#endif
-  for (int t = 0; t < total; t += 3) {
-    r3_step<0>(P, cx, sh, t, w, vr, hprev);
-    if (t + 1 < total) r3_step<1>(P, cx, sh, t + 1, w, vr, hprev);
-    if (t + 2 < total) r3_step<2>(P, cx, sh, t + 2, w, vr, hprev);
-  }
-#ifdef B200_R3_TIMERS
-  if (P.dbg && tid == 0) {
-    for (int i = 0; i < 4; ++i) P.dbg[4 * b + i] += (double)sh.acc[i];
-    if (b == 0) P.dbg[4 * G] += (double)total;
-  }
-#endif
-  // ---- 3. ||w||, Givens (CTA 0), normalise, store v_{k+1}
-  double nacc = 0.0, zero = 0.0;
-#pragma unroll
-  for (int qq = 0; qq < R3_ROWS; ++qq) nacc = fma(w[qq], w[qq], nacc);
-  __syncthreads();
-  r3_reduce2(nacc, zero, sh);
-  if (tid < 32) r3_post(P.slots + (size_t)(total & 3) * R3_BUF_WORDS, b, nacc, 0.0, P.epoch_base + (unsigned)total + 1u);
-  double* const gaf = R3_GA(total);
-  r3_poll(P.slots + (size_t)(total & 3) * R3_BUF_WORDS, b, G, P.epoch_base + (unsigned)total + 1u, P.err, gaf, R3_GC(total));
-  __syncthreads();
-  const double hbis = sqrt(((gaf[0] + gaf[1]) + (gaf[2] + gaf[3])) + gaf[4]);
-  const double inv = hbis > 0.0 ? 1.0 / hbis : 0.0;
-#pragma unroll
-  for (int q = 0; q < R3_RP; ++q) {
-    const int lr = 2 * (tid + R3_THREADS * q);
-    if (lr < nrow) {
-      const int s = lr >= ncell;
-      double2 o;
-      o.x = w[2 * q] * inv; o.y = w[2 * q + 1] * inv;
-      *reinterpret_cast<double2*>(P.vnew + (int64_t)s * NC + c0 + (lr - s * ncell)) = o;
-    }
-  }
-  if (b == 0 && tid == 0) resident_givens_tail(P, hbis, inv);
-}
-
-// =====================================================================================================================
-// Round-2 variant of the three-stage lag-1 kernel ("r3g"): the cross products <v_{t+1}, v_t> the lag-1 recurrence needs
-// are entries of the Gram matrix of the basis, i.e. they do not depend on w.  <v_{k}, v_{k-1}> falls out of the last update
-// sweep of the Arnoldi step that CREATES v_k (w_final is in registers, v_{k-1} is the stage being applied) and travels in
-// the free second slot of the norm exchange; it is stored once in gsub[k] and read back by every later step.  The dot
-// sweep therefore reads ONE staged vector instead of two (half the shared-memory traffic of the sweep that bounds the
-// step) and needs one block reduction instead of two.  Only the wrap-around of a second Gram-Schmidt pass (v_0 after
-// v_{k-1}) still takes its cross product in the sweep.
-// Barriers: one __syncthreads per basis vector (two when the stage being released lives in shared memory) instead of
-// two (three).  Every reduction / poll scratch is double-buffered by step parity, so no write can meet a read of the
-// previous step without a barrier in between (compute-sanitizer racecheck: profiles/).
 // Early poll of exchange t: the words were published one step ago, so the load is issued BEFORE the dot sweep of the
 // step and its L2 round trip is hidden underneath it; r3g_poll_finish checks the epochs afterwards and only spins if a CTA is late.
 __device__ __forceinline__ void r3g_poll_issue(const unsigned long long* buf, int b, int G, unsigned long long& a0, unsigned long long& a1) {
@@ -1364,9 +889,8 @@ struct b200_gmres {
   GmresState* d_state;
   GmresState* h_state;  // pinned
   unsigned* d_bar;      // resident engine: error flag (+ legacy barrier counter)
-  unsigned long long* d_slots;  // resident engine: LL publication slots [2][160][2]
+  unsigned long long* d_slots;  // resident engine: four rotating exchange tables (R3_BUF_WORDS each)
   unsigned ll_epoch;
-  int dbg_on;
   b200_linop *Pl, *Pr;   // borrowed preconditioners (apply the inverse)
   double *pt1, *pt2;     // scratch vectors for preconditioned solves (allocated on first use)
 };
@@ -1594,7 +1118,7 @@ int32_t b200_gmres_create(b200_ctx* ctx, int64_t n, const b200_gmres_opts* opts,
   gm->kcap = 0; gm->d_Vptrs = nullptr; gm->vptr_cap = 0;
   gm->d_h = gm->d_hacc = gm->d_R = gm->d_cs = gm->d_sn = gm->d_z = gm->d_y = gm->d_partial = gm->d_gsub = nullptr;
   gm->d_hraw = nullptr; gm->hraw_cap = 0;
-  gm->d_bar = nullptr; gm->d_slots = nullptr; gm->ll_epoch = 0; gm->dbg_on = 0; gm->Pl = gm->Pr = nullptr; gm->pt1 = gm->pt2 = nullptr;
+  gm->d_bar = nullptr; gm->d_slots = nullptr; gm->ll_epoch = 0; gm->Pl = gm->Pr = nullptr; gm->pt1 = gm->pt2 = nullptr;
   // streaming grid: 4 CTAs of 256 threads per SM, fewer for small n (at least 512 rows per CTA)
   int64_t g = std::min<int64_t>((int64_t)ctx->sm_count * 4, std::max<int64_t>(1, n / 512));
   gm->G = (int)g;
@@ -1606,8 +1130,8 @@ int32_t b200_gmres_create(b200_ctx* ctx, int64_t n, const b200_gmres_opts* opts,
   CUDA_TRY(ctx, cudaMalloc(&gm->d_state, sizeof(GmresState)));
   CUDA_TRY(ctx, cudaMallocHost(&gm->h_state, sizeof(GmresState)));
   CUDA_TRY(ctx, cudaMalloc(&gm->d_bar, 4 * sizeof(unsigned)));
-  CUDA_TRY(ctx, cudaMalloc(&gm->d_slots, sizeof(unsigned long long) * 4 * LL_MAXG * LL_MAXG));
-  CUDA_TRY(ctx, cudaMemsetAsync(gm->d_slots, 0, sizeof(unsigned long long) * 4 * LL_MAXG * LL_MAXG, ctx->stream));
+  CUDA_TRY(ctx, cudaMalloc(&gm->d_slots, sizeof(unsigned long long) * 4 * R3_BUF_WORDS));
+  CUDA_TRY(ctx, cudaMemsetAsync(gm->d_slots, 0, sizeof(unsigned long long) * 4 * R3_BUF_WORDS, ctx->stream));
   CUDA_TRY(ctx, cudaMemsetAsync(gm->d_bar, 0, 4 * sizeof(unsigned), ctx->stream));
   CUDA_TRY(ctx, cudaFuncSetAttribute(update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * (GM_KCAP + 64))));
   CUDA_TRY(ctx, cudaFuncSetAttribute(backsolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * (GM_KCAP + 64))));
@@ -1689,15 +1213,6 @@ int32_t b200_gmres_keep_hessenberg(b200_gmres* gm, int64_t capacity) {
   if (capacity > 0) CUDA_TRY(ctx, cudaMalloc(&gm->d_hraw, sizeof(double) * capacity));
   return B200_OK;
 }
-// test hook: phase timers of the resident kernel (cycles summed over steps, CTA 0): wait, dot, gather, update, steps
-int32_t b200_gmres_debug(b200_gmres* gm, int32_t enable, double* out_host, int32_t count) {
-  B200_DEVICE_GUARD(gm ? gm->ctx : nullptr);
-  b200_ctx* ctx = gm->ctx;
-  if (out_host && count > 0) B200_TRY(b200_memcpy_d2h(ctx, out_host, gm->d_norm_partial2, sizeof(double) * count));
-  gm->dbg_on = enable;
-  CUDA_TRY(ctx, cudaMemsetAsync(gm->d_norm_partial2, 0, sizeof(double) * 1024, ctx->stream));
-  return B200_OK;
-}
 int32_t b200_gmres_get_hessenberg(b200_gmres* gm, double* out_host, int64_t count) {
   B200_DEVICE_GUARD(gm ? gm->ctx : nullptr);
   b200_ctx* ctx = gm->ctx;
@@ -1720,13 +1235,9 @@ int32_t b200_gmres_solve(b200_gmres* gm, b200_linop* op, const double* b, double
   const bool host_op = op->kind == LINOP_CALLBACK || (op->kind == LINOP_PROBLEM && op->prob->kind == B200_PROB_CALLBACK) ||
                        (gm->Pl && gm->Pl->kind == LINOP_CALLBACK) || (gm->Pr && gm->Pr->kind == LINOP_CALLBACK);
   const int check_every = host_op ? 1 : (o.check_every > 0 ? o.check_every : 8);
-  // Gram-Schmidt block: -1 => as many vectors as fit in ~64 MB (half of the 126 MB L2), at most JT; 0 => unblocked
-  int blk = o.block;
-  if (blk < 0) blk = (int)std::min<int64_t>(JT, std::max<int64_t>(1, ((int64_t)64 << 20) / (8 * n)));
-  if (blk > JT) blk = JT;
-  if (orth == B200_ORTH_MGS) blk = 0;
-  // resident engine: built-in Brusselator operator with the exact JVP, even cell count, one CTA per SM holds its rows
-  bool resident = false, resident3 = false, r3g = false;
+  // resident engine: built-in Brusselator operator with the exact JVP (or an assembled sparse Jacobian), even cell count, one
+  // CTA per SM holds its rows: <= 54 rows per thread and two shared-memory stages + the register stage's annex must fit
+  bool resident = false;
   int rs_G = 0, rs_cpc = 0, rs_passes = (orth == B200_ORTH_CGS2) ? 2 : 1;
   int64_t rs_NC = 0;
   size_t rs_smem = 0;
@@ -1743,20 +1254,14 @@ int32_t b200_gmres_solve(b200_gmres* gm, b200_linop* op, const double* b, double
     int64_t cpc = (rs_NC + rs_G - 1) / rs_G;
     cpc = (cpc + 1) & ~(int64_t)1;
     rs_cpc = (int)cpc;
-    rs_smem = sizeof(double) * 4 * (size_t)rs_cpc;  // two stages of 2 * cpc rows
-    const bool fits = (rs_NC % 2 == 0) && (2 * cpc <= (int64_t)RS_RR * RS_THREADS) && (rs_smem + 1024 <= ctx->smem_optin);
+    rs_smem = sizeof(double) * 4 * (size_t)rs_cpc + R3_ANNEX_BYTES;  // two stages of 2 * cpc rows + the annex of the register stage
+    const bool fits = (rs_NC % 2 == 0) && rs_G <= 159 && (2 * cpc <= (int64_t)R3_ROWS * R3_THREADS) && (rs_smem + 2048 <= ctx->smem_optin);
     const bool wanted = (o.engine == B200_ENGINE_RESIDENT) || (o.engine == B200_ENGINE_AUTO && n >= 200000);
     if (fits && wanted) {
       resident = true;
-      static const int r3env = getenv("B200_RS3") ? atoi(getenv("B200_RS3")) : 2;  // A/B runs: 0 two-stage kernel, 1 round-1 three-stage kernel, 2 r3g
-      resident3 = r3env != 0 && (2 * cpc <= (int64_t)R3_ROWS * R3_THREADS) && (rs_smem + R3_ANNEX_BYTES + 2048 <= ctx->smem_optin);
-      if (resident3) rs_smem += R3_ANNEX_BYTES;
-      CUDA_TRY(ctx, cudaFuncSetAttribute(resident_arnoldi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem));
-      CUDA_TRY(ctx, cudaFuncSetAttribute(resident3_arnoldi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem));
       CUDA_TRY(ctx, cudaFuncSetAttribute(resident3g_arnoldi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem));
-      r3g = resident3 && r3env >= 2;
     } else if (o.engine == B200_ENGINE_RESIDENT) {
-      return ctx->fail(B200_ERR_UNSUPPORTED, "resident GMRES engine: problem does not fit (needs an even cell count and <= 7168 cells per SM)", __FILE__, __LINE__);
+      return ctx->fail(B200_ERR_UNSUPPORTED, "resident GMRES engine: problem does not fit (needs an even cell count and at most ~6800 cells per SM)", __FILE__, __LINE__);
     }
   } else if (o.engine == B200_ENGINE_RESIDENT) {
     return ctx->fail(B200_ERR_UNSUPPORTED, "resident GMRES engine needs a built-in Brusselator operator with the exact JVP or an assembled sparse Jacobian", __FILE__, __LINE__);
@@ -1845,11 +1350,9 @@ int32_t b200_gmres_solve(b200_gmres* gm, b200_linop* op, const double* b, double
         RP.k = k; RP.passes = rs_passes; RP.G = rs_G; RP.NC = rs_NC; RP.cpc = rs_cpc;
         RP.V = (const double* const*)gm->d_Vptrs; RP.vnew = gm->V[k];
         if (gm->ll_epoch > 0xfff00000u) {  // epoch space nearly exhausted: start over with clean slots
-          CUDA_TRY(ctx, cudaMemsetAsync(gm->d_slots, 0, sizeof(unsigned long long) * 4 * LL_MAXG * LL_MAXG, ctx->stream));
+          CUDA_TRY(ctx, cudaMemsetAsync(gm->d_slots, 0, sizeof(unsigned long long) * 4 * R3_BUF_WORDS, ctx->stream));
           gm->ll_epoch = 0;
         }
-        RP.dbg = gm->dbg_on ? gm->d_norm_partial2 : nullptr;
-        { static const int li = getenv("B200_RS_LATE") ? atoi(getenv("B200_RS_LATE")) : 0; RP.late_issue = (li == 1) ? 1 : 0; }  // A/B knob of the two-stage kernel: prefetch after the exchange
         RP.slots = gm->d_slots; RP.epoch_base = gm->ll_epoch; RP.err = reinterpret_cast<int*>(gm->d_bar + 1);
         gm->ll_epoch += (unsigned)(rs_passes * k + 2);
         RP.h = gm->d_h; RP.gsub = gm->d_gsub; RP.R = gm->d_R; RP.cs = gm->d_cs; RP.sn = gm->d_sn; RP.z = gm->d_z;
@@ -1857,12 +1360,7 @@ int32_t b200_gmres_solve(b200_gmres* gm, b200_linop* op, const double* b, double
         RP.st = gm->d_state;
         void* args[] = {&RP};
         if (ctx->prof_on) ctx->prof_begin(B200_KID_RESIDENT, (rs_passes * (double)k + 3.0) * Bv);
-        if (r3g)
-          CUDA_TRY(ctx, cudaLaunchCooperativeKernel((const void*)resident3g_arnoldi_kernel, dim3(rs_G), dim3(R3_THREADS), args, rs_smem, ctx->stream));
-        else if (resident3)
-          CUDA_TRY(ctx, cudaLaunchCooperativeKernel((const void*)resident3_arnoldi_kernel, dim3(rs_G), dim3(R3_THREADS), args, rs_smem, ctx->stream));
-        else
-          CUDA_TRY(ctx, cudaLaunchCooperativeKernel((const void*)resident_arnoldi_kernel, dim3(rs_G), dim3(RS_THREADS), args, rs_smem, ctx->stream));
+        CUDA_TRY(ctx, cudaLaunchCooperativeKernel((const void*)resident3g_arnoldi_kernel, dim3(rs_G), dim3(R3_THREADS), args, rs_smem, ctx->stream));
         ctx->launches++;
         if (ctx->prof_on) ctx->prof_end();
       } else {
@@ -1893,24 +1391,13 @@ int32_t b200_gmres_solve(b200_gmres* gm, b200_linop* op, const double* b, double
       } else {
         const size_t shm = sizeof(double) * (k + 32);
         const int passes = (orth == B200_ORTH_CGS2) ? 2 : 1;
-        if (blk > 0 && k > blk) {
-          // L2-blocked Gram-Schmidt: per block one multi-dot sweep (HBM -> L2) and one update sweep (L2 hits)
-          for (int pass = 0; pass < passes; ++pass)
-            for (int c0 = 0; c0 < k; c0 += blk) {
-              const int kb = std::min(blk, k - c0);
-              const bool last = (pass == passes - 1) && (c0 + kb >= k);
-              PLAUNCH(ctx, B200_KID_MULTIDOT, (kb + 1.0) * Bv, (multidot_kernel<true>), G, GM_THREADS, 0, gm->d_state,
-                      (const double* const*)(gm->d_Vptrs + c0), kb, gm->w, n, gm->d_partial);
-              PLAUNCH(ctx, B200_KID_UPDATE, 2.0 * Bv, update_block_kernel, G, GM_THREADS, 0, gm->d_state, (const double* const*)(gm->d_Vptrs + c0), kb,
-                      (const double*)gm->d_partial, pass, gm->d_h + c0, gm->w, n, last ? gm->d_norm_partial : (double*)nullptr);
-            }
-        } else {
-          PLAUNCH(ctx, B200_KID_MULTIDOT, (k + 1.0) * Bv, (multidot_kernel<false>), G, GM_THREADS, 0, gm->d_state, (const double* const*)gm->d_Vptrs, k, gm->w, n, gm->d_partial);
+        {
+          PLAUNCH(ctx, B200_KID_MULTIDOT, (k + 1.0) * Bv, multidot_kernel, G, GM_THREADS, 0, gm->d_state, (const double* const*)gm->d_Vptrs, k, gm->w, n, gm->d_partial);
           LAUNCH(ctx, reduce_h_kernel, (k + 7) / 8, GM_THREADS, 0, gm->d_state, k, G, gm->d_partial, gm->d_h, (double*)nullptr);
           PLAUNCH(ctx, B200_KID_UPDATE, (k + 2.0) * Bv, update_kernel, G, GM_THREADS, shm, gm->d_state, 0, (const double* const*)gm->d_Vptrs, k, gm->d_h, -1.0, gm->w, gm->w, n,
                   gm->d_norm_partial);
           if (orth == B200_ORTH_CGS2) {
-            PLAUNCH(ctx, B200_KID_MULTIDOT, (k + 1.0) * Bv, (multidot_kernel<false>), G, GM_THREADS, 0, gm->d_state, (const double* const*)gm->d_Vptrs, k, gm->w, n, gm->d_partial);
+            PLAUNCH(ctx, B200_KID_MULTIDOT, (k + 1.0) * Bv, multidot_kernel, G, GM_THREADS, 0, gm->d_state, (const double* const*)gm->d_Vptrs, k, gm->w, n, gm->d_partial);
             LAUNCH(ctx, reduce_h_kernel, (k + 7) / 8, GM_THREADS, 0, gm->d_state, k, G, gm->d_partial, gm->d_hacc, gm->d_h);
             PLAUNCH(ctx, B200_KID_UPDATE, (k + 2.0) * Bv, update_kernel, G, GM_THREADS, shm, gm->d_state, 0, (const double* const*)gm->d_Vptrs, k, gm->d_hacc, -1.0, gm->w,
                     gm->w, n, gm->d_norm_partial);
@@ -1941,8 +1428,6 @@ int32_t b200_gmres_solve(b200_gmres* gm, b200_linop* op, const double* b, double
     //   CGS (2j+2) Bv | CGS2 (4j+4) Bv | MGS (3j+1) Bv (dot pass reads v_{i+1}, update pass reads v_i, w read+written)
     for (int j = 1; j <= k; ++j) {
       double orthb = (orth == B200_ORTH_CGS) ? (2.0 * j + 2.0) : (orth == B200_ORTH_CGS2) ? (4.0 * j + 4.0) : (3.0 * j + 1.0);
-      if (blk > 0 && j > blk && orth != B200_ORTH_MGS)  // blocked: basis crosses HBM once per pass; w is L2 resident
-        orthb = ((orth == B200_ORTH_CGS2) ? 2.0 : 1.0) * (j + 2.0);
       if (resident) bytes += (rs_passes * (double)j + 3.0) * Bv;  // basis once per pass + u, v_k reads + v_{k+1} store
       else bytes += (3.0 + 2.0 + orthb) * Bv;
     }

@@ -13,6 +13,10 @@ def _dp(nls, ctx, f):
     return nls._DeviceProblem(ctx, nls.NonlinearProblem(f, None, (3.4, 1.0, 10.0), ctx=ctx))
 
 
+def _h(x):
+    return x.to_host() if hasattr(x, "to_host") else np.asarray(x)
+
+
 def _apply(nls, ctx, op, x, n):
     y = ctx.zeros(n)
     nls.abi.check(ctx.handle, nls.abi.lib().b200_linop_apply(op, x.ptr, y.ptr))
@@ -75,7 +79,7 @@ def test_newton_with_multigrid_cuts_the_krylov_iterations(nls, ctx):
     ref = nls.solve(prob, nls.NewtonRaphson(linsolve=nls.KrylovJL_GMRES(orth="mgs")), abstol=1e-8)
     sol = nls.solve(prob, nls.NewtonRaphson(linsolve=nls.KrylovJL_GMRES(orth="mgs", precs=nls.Multigrid("right"))), abstol=1e-8)
     assert sol.retcode == ref.retcode == nls.ReturnCode.Success and sol.stats.nsteps == ref.stats.nsteps
-    assert sol.resid_inf < 1e-8 and np.abs(sol.u - ref.u).max() <= 1e-6 * np.abs(ref.u).max()
+    assert sol.resid_inf < 1e-8 and np.abs(_h(sol.u) - _h(ref.u)).max() <= 1e-6 * np.abs(_h(ref.u)).max()
     li, lr = [t.lin_iters for t in sol.trace], [t.lin_iters for t in ref.trace]
     assert max(li) <= 40 and min(lr) >= 5 * max(li), (li, lr)
     # with Eisenstat-Walker forcing on top
@@ -124,13 +128,13 @@ def test_newton_on_sparse_prototype_takes_the_direct_route(nls, ctx, po):
     s = sol.stats
     # one coloured Jacobian + one factorisation + one solve per step; a sparse prototype gives no extra Jacobian at init
     assert (s.nsteps, s.nf, s.njacs, s.nfactors, s.nsolve) == (3, 3, 3, 3, 3) and s.njvp == 0
-    assert np.abs(sol.u - dense.u).max() <= 1e-9 * np.abs(dense.u).max()
+    assert np.abs(_h(sol.u) - _h(dense.u)).max() <= 1e-9 * np.abs(_h(dense.u)).max()
     fn = [t.fnorm_inf for t in sol.trace]
     assert abs(fn[0] - 18.00640584541683) <= 1e-9 * 18.0 and abs(fn[1] - 5.434051731e-4) <= 1e-9      # SURVEY.md §A.4 probe values
     sol_k = nls.solve(nls.NonlinearProblem(fs, u0, (3.4, 1.0, 10.0), ctx=ctx), nls.NewtonRaphson(linsolve=nls.KLUFactorization()), abstol=1e-8)
-    assert np.array_equal(sol_k.u, sol.u)
+    assert np.array_equal(_h(sol_k.u), _h(sol.u))
     tr = nls.solve(nls.NonlinearProblem(fs, u0, (3.4, 1.0, 10.0), ctx=ctx), nls.TrustRegion(), abstol=1e-8)
-    assert tr.retcode == nls.ReturnCode.Success and np.abs(tr.u - dense.u).max() <= 1e-8 * np.abs(dense.u).max()
+    assert tr.retcode == nls.ReturnCode.Success and np.abs(_h(tr.u) - _h(dense.u)).max() <= 1e-8 * np.abs(_h(dense.u)).max()
 
 
 def test_sparse_direct_route_refuses_a_band_that_cannot_fit(nls, ctx):
