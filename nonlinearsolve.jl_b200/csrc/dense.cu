@@ -5,16 +5,15 @@
 // AutoForwardDiff: exact derivatives) and the LinearSolve LU reached through linear_solve.jl:100-117 /
 // NonlinearSolveBaseLinearSolveExt.jl:16-32, 102-111 (copyto!(A, J); lu!; ldiv!).
 //
-// getrf structure (outer block NBO = 128, inner block NBI = 32):
-//   inner panel (32 columns), column by column, every step spread over many CTAs:
-//       pivot_search (arg-max partials)  ->  pivot_apply (1 CTA: final arg-max, ipiv, row swap inside the outer panel,
-//       1/pivot)  ->  column_update (scale + rank-1 update of the inner panel + arg-max partials of the NEXT column fused)
+// getrf structure (outer block NBO = 256 / 512, inner block NBI = 32):
+//   inner panel (32 columns): ONE cooperative kernel (`panel_coop_kernel`): every CTA keeps its rows of the panel in shared
+//       memory for all 32 columns; per column only the arg-max partials and two 32-double rows cross CTAs
 //   after an inner panel: TRSM + GEMM (K = 32) on the remaining columns of the outer panel
 //   after the outer panel: row interchanges applied to the columns left/right of it, block TRSM for U12, and the
-//       trailing update  A22 -= L21 U12  with K = 128 — the GEMM-shaped 2/3 n^3 flops — on the FP64 tensor cores:
-//       `gemm_sub_kernel`, 128 x 128 CTA tiles, 8 warps x (32 x 64) warp tiles of mma.sync.m8n8k4.f64 (DMMA in SASS;
-//       tcgen05 has no FP64 kind), K streamed in chunks of 16 through double-buffered, bank-conflict-free shared memory
-//       with register prefetch of the next chunk.
+//       trailing update  A22 -= L21 U12  with K = NBO — the GEMM-shaped 2/3 n^3 flops — on the FP64 tensor cores
+//       (`gemm_sub_w8_kernel`: mma.sync.m8n8k4.f64 = DMMA.8x8x4 in SASS, the native FP64 MMA shape of sm_100a — m16n8k16
+//       compiles to eight of them; tcgen05 has no FP64 kind).  Look-ahead: the next panel's columns are updated first and
+//       the panel is factored on a second, HIGHEST-PRIORITY stream underneath the rest of the update.
 // Pivot sequence is LAPACK's (first maximum wins), checked bit-exact against the oracle / scipy in the tests.
 #include "common.cuh"
 #include <math.h>
@@ -23,7 +22,7 @@
 namespace cg = cooperative_groups;
 
 namespace {
-constexpr int NBO = 256;  // outer block (GEMM K)
+constexpr int NBO_DEFAULT = 256;  // outer block (GEMM K)
 constexpr int NBI = 32;   // inner panel width
 constexpr int DT = 256;
 constexpr int PS_MAX = 160;  // max CTAs of the panel grids
@@ -262,70 +261,78 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-// K is streamed in chunks of 8 through a 4-stage cp.async ring: three chunks are always in flight underneath the MMAs of
-// the current one, so the ~1 us L2/HBM latency of the operand loads is covered even with only 8 resident warps per SM.
-__global__ void __launch_bounds__(GM_T, 2) gemm_sub_kernel(int64_t M, int64_t N, int K, const double* __restrict__ A, int64_t lda,
-                                                            const double* __restrict__ B, int64_t ldb, double* __restrict__ C, int64_t ldc) {
+// K is streamed in chunks of 8 through a 4-stage cp.async ring: three chunks are always in flight underneath the MMAs of the
+// current one.  CTA = 8 warps (4 x 2), tile 128 (M) x 64 (N), each warp a 32 x 32 sub-tile = 4 x 4 DMMA m8n8k4 accumulator
+// fragments (64 registers): 119 registers per thread -> two CTAs = 16 warps per SM.  The FP64 tensor pipe of this part is fed
+// by warps, not by tile size (measured at n = 32768, whole getrf): 4 warps x (32 x 64) with 2 CTAs/SM (round 1) 1.38 s, the
+// same kernel at 3 CTAs/SM 1.17 s, this layout 1.08 s; a persistent 128 x 128-tile kernel with 16-byte copies and a chunk
+// stream running across tile boundaries — better arithmetic intensity, ONE 8-warp CTA per SM — 1.57 s.
+constexpr int G8_T = 256;
+template <int MINB, int BK, int STAGES>
+__global__ void __launch_bounds__(G8_T, MINB) gemm_sub_w8_kernel(int64_t M, int64_t N, int K, const double* __restrict__ A, int64_t lda,
+                                                                  const double* __restrict__ B, int64_t ldb, double* __restrict__ C, int64_t ldc) {
   extern __shared__ double gsm[];
-  double(*As)[GM_BK][GM_BM + GM_PAD] = reinterpret_cast<double(*)[GM_BK][GM_BM + GM_PAD]>(gsm);                                            // [stage][k][m]
-  double(*Bs)[GM_BK][GM_BN + GM_PAD] = reinterpret_cast<double(*)[GM_BK][GM_BN + GM_PAD]>(gsm + GM_STAGES * GM_BK * (GM_BM + GM_PAD));  // [stage][k][n]
+  double(*As)[BK][GM_BM + GM_PAD] = reinterpret_cast<double(*)[BK][GM_BM + GM_PAD]>(gsm);
+  double(*Bs)[BK][GM_BN + GM_PAD] = reinterpret_cast<double(*)[BK][GM_BN + GM_PAD]>(gsm + STAGES * BK * (GM_BM + GM_PAD));
   const int64_t m0 = (int64_t)blockIdx.x * GM_BM, n0 = (int64_t)blockIdx.y * GM_BN;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = warp * 32;
+  const int wm = (warp & 3) * 32, wn = (warp >> 2) * 32;
   const int g = lane >> 2, t4 = lane & 3;
-  const int bk = tid & 7, bn = tid >> 3;  // B staging: k fastest; thread covers n = bn + 16 q, q = 0..3
-  const bool m_ok = m0 + tid < M;
-  const double* a_src = A + (m_ok ? m0 + tid : 0);
+  const int am = tid & 127, ak = tid >> 7;          // A staging: thread covers k = ak + 2 q, q = 0 .. BK/2-1
+  const int bk = tid & (BK - 1), bn = tid / BK;     // B staging: thread covers n = bn + (256/BK) q, q = 0 .. BK/4-1
+  const bool m_ok = m0 + am < M;
+  const double* a_src = A + (m_ok ? m0 + am : 0);
   auto issue_chunk = [&](int ch) {
-    const int st = ch % GM_STAGES, kc = ch * GM_BK;
+    const int st = ch % STAGES, kc = ch * BK;
 #pragma unroll
-    for (int q = 0; q < GM_BK; ++q) {
-      const bool ok = m_ok && (kc + q < K);
-      cp_async8(&As[st][q][tid], a_src + (int64_t)(ok ? kc + q : 0) * lda, ok ? 8 : 0);
+    for (int q = 0; q < BK / 2; ++q) {
+      const int k = ak + 2 * q;
+      const bool ok = m_ok && (kc + k < K);
+      cp_async8(&As[st][k][am], a_src + (int64_t)(ok ? kc + k : 0) * lda, ok ? 8 : 0);
     }
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int64_t nn = n0 + bn + 16 * q;
+    for (int q = 0; q < BK / 4; ++q) {
+      const int64_t nn = n0 + bn + (G8_T / BK) * q;
       const bool ok = (nn < N) && (kc + bk < K);
-      cp_async8(&Bs[st][bk][bn + 16 * q], B + (ok ? nn * ldb + kc + bk : 0), ok ? 8 : 0);
+      cp_async8(&Bs[st][bk][bn + (G8_T / BK) * q], B + (ok ? nn * ldb + kc + bk : 0), ok ? 8 : 0);
     }
   };
-  double acc[4][8][2];
+  double acc[4][4][2];
 #pragma unroll
   for (int a = 0; a < 4; ++a)
 #pragma unroll
-    for (int b = 0; b < 8; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
-  const int nchunks = (K + GM_BK - 1) / GM_BK;
+    for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+  const int nchunks = (K + BK - 1) / BK;
 #pragma unroll
-  for (int s = 0; s < GM_STAGES - 1; ++s) {
+  for (int s = 0; s < STAGES - 1; ++s) {
     if (s < nchunks) issue_chunk(s);
     cp_async_commit();
   }
   for (int ch = 0; ch < nchunks; ++ch) {
-    cp_async_wait<GM_STAGES - 2>();  // chunk `ch` has landed
-    __syncthreads();                 // ... for every thread, and everyone is done reading stage (ch-1) % STAGES
-    if (ch + GM_STAGES - 1 < nchunks) issue_chunk(ch + GM_STAGES - 1);
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    if (ch + STAGES - 1 < nchunks) issue_chunk(ch + STAGES - 1);
     cp_async_commit();
-    const int st = ch % GM_STAGES;
+    const int st = ch % STAGES;
 #pragma unroll
-    for (int kk = 0; kk < GM_BK; kk += 4) {
-      double af[4], bf[8];
+    for (int kk = 0; kk < BK; kk += 4) {
+      double af[4], bf[4];
 #pragma unroll
       for (int a = 0; a < 4; ++a) af[a] = As[st][kk + t4][wm + a * 8 + g];
 #pragma unroll
-      for (int b = 0; b < 8; ++b) bf[b] = Bs[st][kk + t4][b * 8 + g];
+      for (int b = 0; b < 4; ++b) bf[b] = Bs[st][kk + t4][wn + b * 8 + g];
 #pragma unroll
       for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int b = 0; b < 8; ++b) dmma_m8n8k4(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+        for (int b = 0; b < 4; ++b) dmma_m8n8k4(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
     }
   }
 #pragma unroll
   for (int a = 0; a < 4; ++a)
 #pragma unroll
-    for (int b = 0; b < 8; ++b) {
+    for (int b = 0; b < 4; ++b) {
       const int64_t i = m0 + wm + a * 8 + g;
-      const int64_t j = n0 + b * 8 + 2 * t4;
+      const int64_t j = n0 + wn + b * 8 + 2 * t4;
       if (i < M) {
         if (j < N) C[j * ldc + i] -= acc[a][b][0];
         if (j + 1 < N) C[(j + 1) * ldc + i] -= acc[a][b][1];
@@ -338,8 +345,8 @@ constexpr size_t GEMM_SMEM = sizeof(double) * GM_STAGES * GM_BK * ((GM_BM + GM_P
 int32_t gemm_sub(b200_ctx* ctx, int64_t M, int64_t N, int K, const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc) {
   if (M <= 0 || N <= 0 || K <= 0) return B200_OK;
   dim3 grid((unsigned)((M + GM_BM - 1) / GM_BM), (unsigned)((N + GM_BN - 1) / GM_BN));
-  PLAUNCH(ctx, B200_KID_LU_GEMM, 2.0 * (double)M * (double)N * (double)K /* flops, not bytes */, gemm_sub_kernel, grid, GM_T, GEMM_SMEM, M, N, K, A, lda, B, ldb, C,
-          ldc);
+  PLAUNCH(ctx, B200_KID_LU_GEMM, 2.0 * (double)M * (double)N * (double)K /* flops, not bytes */, (gemm_sub_w8_kernel<2, GM_BK, GM_STAGES>), grid, G8_T, GEMM_SMEM, M, N, K,
+          A, lda, B, ldb, C, ldc);
   return B200_OK;
 }
 
@@ -447,9 +454,13 @@ int32_t b200_getrf(b200_ctx* ctx, int64_t n, double* A, int64_t ld, int64_t* ipi
   PanelScratch* ps = reinterpret_cast<PanelScratch*>(ctx->d_partials + 2 * B200_RED_MAX_BLOCKS);
   CUDA_TRY(ctx, cudaMemsetAsync(ps, 0, sizeof(PanelScratch), ctx->stream));
   CUDA_TRY(ctx, cudaFuncSetAttribute(panel_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-  CUDA_TRY(ctx, cudaFuncSetAttribute(gemm_sub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+  CUDA_TRY(ctx, cudaFuncSetAttribute((gemm_sub_w8_kernel<2, GM_BK, GM_STAGES>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
   if (!ctx->aux_stream) {
-    CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+    // highest priority: while the trailing update's CTAs drain and refill, the block scheduler hands freed SM slots to the
+    // look-ahead panel first, so the (latency-bound, cooperative) panel runs underneath the GEMM instead of after it
+    int prio_lo = 0, prio_hi = 0;
+    CUDA_TRY(ctx, cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    CUDA_TRY(ctx, cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, prio_hi));
     CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_a, cudaEventDisableTiming));
     CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_b, cudaEventDisableTiming));
   }
@@ -491,6 +502,9 @@ int32_t b200_getrf(b200_ctx* ctx, int64_t n, double* A, int64_t ld, int64_t* ipi
     return B200_OK;
   };
 
+  // outer block (the K of the trailing update): 512 for the big factorisations halves the C read-modify-write traffic
+  // (n = 32768: 1.08 s -> 1.02 s; 768 buys nothing more), 256 below
+  const int NBO = n >= 16384 ? 512 : NBO_DEFAULT;  // A/B knob for the outer block
   B200_TRY(factor_panel(0, (int)std::min<int64_t>(NBO, n)));
   for (int64_t k0 = 0; k0 < n; k0 += NBO) {
     const int kbo = (int)std::min<int64_t>(NBO, n - k0);
@@ -514,8 +528,7 @@ int32_t b200_getrf(b200_ctx* ctx, int64_t n, double* A, int64_t ld, int64_t* ipi
     B200_TRY(gemm_sub(ctx, rest, kbn, kbo, A + k0 * ld + k1, ld, A + k1 * ld + k0, ld, A + k1 * ld + k1, ld));
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_a, s_main));
     CUDA_TRY(ctx, cudaStreamWaitEvent(s_panel, ctx->ev_a, 0));
-    static const bool lookahead = getenv("B200_LU_LOOKAHEAD") ? atoi(getenv("B200_LU_LOOKAHEAD")) != 0 : true;
-    ctx->stream = lookahead ? s_panel : s_main;
+    ctx->stream = s_panel;
     int32_t st = factor_panel(k1, kbn);
     ctx->stream = s_main;
     B200_TRY(st);
