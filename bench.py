@@ -164,7 +164,7 @@ def run_reference(args):
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "CPU restatement of the reference NewtonRaphson+GMRES inner loop (oracle/oracle.c); the Julia reference cannot run in this image"}
-    print(json.dumps(line))
+    emit(line)
 
 
 def ensemble_params(K):
@@ -584,12 +584,42 @@ def run_b200(args):
                 line[key] = {"error": "%s: %s" % (type(e).__name__, e)}
             ctx.sync()
             torch.cuda.empty_cache()
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
 
+class _OneLineStdout:
+    """The driver parses ONE JSON line from stdout.  Libraries print there behind our back (NCCL's version banner on the first
+    communicator, whatever NCCL_DEBUG says): route file descriptor 1 to stderr for the whole run and write the line to the
+    real stdout at the end."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, text):
+        sys.stdout.flush()
+        os.write(self.real, (text + "\n").encode())
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.real, 1)
+        os.close(self.real)
+        return False
+
+
+_OUT = None
+
+
+def emit(line):
+    (_OUT.emit if _OUT is not None else print)(json.dumps(line))
+
+
 def main():
+    global _OUT
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -600,10 +630,13 @@ def main():
     ap.add_argument("--no-ensemble", dest="no_ensemble", action="store_true", help="skip the config-5 ensemble leg")
     ap.add_argument("--no-legs", dest="no_legs", action="store_true", help="skip the n80 / lu / sparse_tr / precond legs (configs 2, 4 and the §8f variants)")
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_b200(args)
+    with _OneLineStdout() as out:
+        _OUT = out
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_b200(args)
+        _OUT = None
 
 
 if __name__ == "__main__":

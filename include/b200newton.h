@@ -92,7 +92,10 @@ enum { B200_GLOBALIZATION_NONE = 0, B200_GLOBALIZATION_TRUST_REGION = 1, B200_GL
    `δu_cache` that the reference allocates with `similar(u)` and never writes; the library uses the step just taken, which is
    what the retrospective scheme of the cited paper evaluates. */
 enum { B200_TR_SIMPLE = 0, B200_TR_NLSOLVE = 1, B200_TR_NOCEDAL_WRIGHT = 2, B200_TR_HEI = 3, B200_TR_YUAN = 4, B200_TR_FAN = 5, B200_TR_BASTIN = 6 };
-enum { B200_DESCENT_NEWTON = 0, B200_DESCENT_PSEUDO_TRANSIENT = 1 };
+/* LEVENBERG_MARQUARDT (levenberg_marquardt.jl:36-61): DampedNewtonDescent with the Levenberg-Marquardt damping function
+   (running maximum of diag(J'J), floor min_damping_D) wrapped in GeodesicAcceleration, with LevenbergMarquardtTrustRegion;
+   concrete (dense) Jacobian; the damped system is solved in normal form, (J'J + lambda D'D) v = J'f */
+enum { B200_DESCENT_NEWTON = 0, B200_DESCENT_PSEUDO_TRANSIENT = 1, B200_DESCENT_LEVENBERG_MARQUARDT = 2 };
 /* built-in preconditioners (LinearSolve `precs(A, p)`, large_systems.md:244-316): inverse of the 2x2 species blocks, or one
    geometric-multigrid V-cycle of the Brusselator Jacobian (the tutorial's AlgebraicMultigrid ruge_stuben / smoothed_aggregation) */
 enum { B200_PRECOND_NONE = 0, B200_PRECOND_BLOCK_JACOBI_LEFT = 1, B200_PRECOND_BLOCK_JACOBI_RIGHT = 2,
@@ -181,6 +184,11 @@ typedef struct b200_newton_opts {
   double maxtime;          /* seconds of accumulated step time after which the solve stops with MaxTime (NonlinearSolveBase/src/solve.jl:847-855); <= 0 => none */
   int32_t term_norm;       /* B200_NORM_*: the termination mode's internalnorm */
   int32_t term_max_stalled_steps; /* Safe modes: window of the step-norm stall test; 0 => 32 (the solver default's value), < 0 => test disabled */
+  /* LevenbergMarquardt(; damping_initial = 1, damping_increase_factor = 2, damping_decrease_factor = 3, finite_diff_step_geodesic
+     = 0.1, α_geodesic = 0.75, b_uphill = 1, min_damping_D = 1e-8, disable_geodesic = Val(false)); 0 => the default */
+  double lm_damping_initial, lm_damping_increase, lm_damping_decrease, lm_finite_diff_step, lm_alpha_geodesic, lm_b_uphill, lm_min_damping_D;
+  int32_t lm_disable_geodesic;
+  int32_t reserved0;
 } b200_newton_opts;
 
 typedef struct b200_newton_result {

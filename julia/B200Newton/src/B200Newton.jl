@@ -376,6 +376,8 @@ struct NewtonOpts
     ls_c1::Float64; ls_rho_hi::Float64; ls_rho_lo::Float64; ls_maxiters::Int32; precond::Int32
     descent::Int32; tr_scheme::Int32; pt_alpha_initial::Float64
     maxtime::Float64; term_norm::Int32; term_max_stalled_steps::Int32
+    lm_damping_initial::Float64; lm_damping_increase::Float64; lm_damping_decrease::Float64; lm_finite_diff_step::Float64
+    lm_alpha_geodesic::Float64; lm_b_uphill::Float64; lm_min_damping_D::Float64; lm_disable_geodesic::Int32; reserved0::Int32
 end
 struct NewtonResult
     retcode::Int32; nsteps::Int32; nf::Int32; njacs::Int32; nfactors::Int32; nsolve::Int32; njvp::Int32; ntrace::Int32
@@ -499,7 +501,7 @@ end
 # ------------------------------------------------------------------ whole-solve fast path
 """
     B200NewtonKrylov(; problem, linsolve = :gmres | :dense_lu | :sparse_gmres | :sparse_lu,
-                       globalization = :none | :trust_region | :linesearch, descent = :newton | :pseudo_transient,
+                       globalization = :none | :trust_region | :linesearch, descent = :newton | :pseudo_transient | :levenberg_marquardt,
                        forcing = false, precs = :none | :block_jacobi_left | ... , orth = :mgs)
 
 New `AbstractNonlinearSolveAlgorithm` whose `__solve` runs the entire Newton iteration inside the library
@@ -522,7 +524,7 @@ end
 
 const _LINSOLVE = (gmres = 0, dense_lu = 1, sparse_gmres = 2, sparse_lu = 3)
 const _GLOBALIZATION = (none = 0, trust_region = 1, linesearch = 2)
-const _DESCENT = (newton = 0, pseudo_transient = 1)
+const _DESCENT = (newton = 0, pseudo_transient = 1, levenberg_marquardt = 2)
 const _TR_SCHEMES = (simple = 0, nlsolve = 1, nocedal_wright = 2, hei = 3, yuan = 4, fan = 5, bastin = 6)
 const _PRECS = (none = 0, block_jacobi_left = 1, block_jacobi_right = 2, multigrid_left = 3, multigrid_right = 4)
 const _TERMINATION = (abs_norm_safe_best = 0, abs_norm = 1, abs_norm_safe = 2, norm = 3, rel = 4, rel_norm = 5, abs = 6,

@@ -549,6 +549,24 @@ class PseudoTransient(_FirstOrder):
         self.alpha_initial = float(alpha_initial)
 
 
+class LevenbergMarquardt(_FirstOrder):
+    """LevenbergMarquardt(; damping_initial = 1.0, α_geodesic = 0.75, disable_geodesic = Val(false), damping_increase_factor = 2.0,
+    damping_decrease_factor = 3.0, finite_diff_step_geodesic = 0.1, b_uphill = 1.0, min_damping_D = 1e-8)
+    (levenberg_marquardt.jl:36-61): damped normal equations with the running-maximum diagonal, geodesic acceleration, and the
+    uphill-accepting trust region; concrete dense Jacobian.  The trace's `trust_radius` slot carries the damping λ used by the
+    step, `lin_status` the geodesic-acceleration verdict."""
+    name = "LevenbergMarquardt"
+    descent = abi.DESCENT_LEVENBERG_MARQUARDT
+
+    def __init__(self, damping_initial=1.0, alpha_geodesic=0.75, disable_geodesic=False, damping_increase_factor=2.0, damping_decrease_factor=3.0,
+                 finite_diff_step_geodesic=0.1, b_uphill=1.0, min_damping_D=1e-8, autodiff=None):
+        super().__init__(True, None, autodiff, None, None, None, None)
+        self.lm = dict(lm_damping_initial=damping_initial, lm_alpha_geodesic=alpha_geodesic, lm_damping_increase=damping_increase_factor,
+                       lm_damping_decrease=damping_decrease_factor, lm_finite_diff_step=finite_diff_step_geodesic,
+                       lm_b_uphill=(b_uphill if b_uphill > 0 else -1.0), lm_min_damping_D=min_damping_D)
+        self.disable_geodesic = bool(disable_geodesic)
+
+
 class RadiusUpdateSchemes:
     """RadiusUpdateSchemes.{Simple, NLsolve, NocedalWright, Hei, Yuan, Fan, Bastin}  (trust_region.jl:431-520)."""
     Simple, NLsolve, NocedalWright, Hei, Yuan, Fan, Bastin = (abi.TR_SIMPLE, abi.TR_NLSOLVE, abi.TR_NOCEDAL_WRIGHT, abi.TR_HEI, abi.TR_YUAN, abi.TR_FAN, abi.TR_BASTIN)
@@ -623,6 +641,13 @@ def _build_opts(prob, alg, abstol, reltol, maxiters, termination_condition, stor
     if ls_ is not None:  # has_linesearch (solve.jl:249-273): globalization = Val(:LineSearch)
         o.globalization = abi.GLOB_LINESEARCH
         o.ls_c1, o.ls_rho_hi, o.ls_rho_lo, o.ls_maxiters = float(ls_.c_1), float(ls_.rho_hi), float(ls_.rho_lo), int(ls_.maxiters)
+    if isinstance(alg, LevenbergMarquardt):
+        if sparse:
+            raise TypeError("LevenbergMarquardt is offered on the dense concrete Jacobian")
+        o.linsolve = abi.LINSOLVE_DENSE_LU
+        for k, v in alg.lm.items():
+            setattr(o, k, float(v))
+        o.lm_disable_geodesic = 1 if alg.disable_geodesic else 0
     if isinstance(alg, TrustRegion):
         for k, v in alg.tr.items():
             setattr(o, k, float(v))

@@ -194,6 +194,10 @@ int32_t b200i_mg_setup(b200_mg* mg, const double* u);   // rebuild the coarse op
 int32_t b200i_mg_apply(b200_mg* mg, const double* x, double* y);
 int32_t b200i_mg_levels(b200_mg* mg, int32_t* nlev, int32_t* sizes, int32_t cap);
 int32_t b200i_diag_shift(b200_ctx* ctx, int64_t n, double* A, int64_t ld, double shift);  // A[i,i] += shift
+// column-pivoted Householder QR solve of a (possibly rank-deficient) dense system: the rescue of a singular LU
+int32_t b200i_qrcp_solve(b200_ctx* ctx, int64_t n, double* A, int64_t ld, double* b, double* x, double* work, int32_t* jpvt_dev, int32_t* rank_host);
+int32_t b200i_gram(b200_ctx* ctx, int64_t n, const double* J, int64_t ld, double* C, int64_t ldc);          // C = J' J
+int32_t b200i_lm_damp(b200_ctx* ctx, int64_t n, double* C, int64_t ldc, double* dtd, double lambda);     // dtd = max(dtd, diag C); C += lambda diag(dtd)
 void b200i_sparse_jac_csr(b200_sparse_jac* sj, const int64_t** rowptr, const int64_t** csr_col, const int64_t** csr_map);
 int32_t b200i_residual_norm(b200_problem* prob, const double* u, double* du, double* d_norminf /*device, pre-zeroed*/);
 int32_t b200i_axpy_norm(b200_ctx* ctx, int64_t n, double a, const double* x, double* y, double* d_sumsq /*device, pre-zeroed*/);

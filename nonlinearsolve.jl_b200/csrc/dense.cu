@@ -396,6 +396,204 @@ __global__ void __launch_bounds__(DT) trisolve_update_kernel(int lower, int64_t 
 }  // namespace
 
 namespace {
+// ---- Levenberg-Marquardt normal form (levenberg_marquardt.jl / damped_newton.jl :normal_form): C = J' J, and the diagonal of it
+// C[i, j] = sum_k J[k, i] J[k, j]: both operands are contiguous in k (column-major J), 64 x 64 output tile per CTA, 16 x 16
+// threads with a 4 x 4 register block each.  CUDA-core FP64: LM serves small dense systems, this is not a roofline kernel.
+constexpr int LMT = 64, LMK = 16;
+__global__ void __launch_bounds__(256) gram_kernel(int64_t n, const double* __restrict__ J, int64_t ld, double* __restrict__ C, int64_t ldc) {
+  __shared__ double Ai[LMK][LMT + 1], Aj[LMK][LMT + 1];
+  const int64_t i0 = (int64_t)blockIdx.x * LMT, j0 = (int64_t)blockIdx.y * LMT;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  double acc[4][4] = {};
+  for (int64_t k0 = 0; k0 < n; k0 += LMK) {
+    for (int e = threadIdx.x; e < LMK * LMT; e += 256) {
+      const int k = e % LMK, c = e / LMK;   // k fastest: coalesced down the column
+      const int64_t gk = k0 + k;
+      Ai[k][c] = (gk < n && i0 + c < n) ? J[(i0 + c) * ld + gk] : 0.0;
+      Aj[k][c] = (gk < n && j0 + c < n) ? J[(j0 + c) * ld + gk] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < LMK; ++k) {
+      double a[4], b[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { a[q] = Ai[k][tx + 16 * q]; b[q] = Aj[k][ty + 16 * q]; }
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[p][q] = fma(a[p], b[q], acc[p][q]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int p = 0; p < 4; ++p)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int64_t i = i0 + tx + 16 * p, j = j0 + ty + 16 * q;
+      if (i < n && j < n) C[j * ldc + i] = acc[p][q];
+    }
+}
+// dtd[j] = max(dtd[j], C[j, j])  (update_levenberg_marquardt_diagonal!!) ; C[j, j] += lambda * dtd[j]  (dampen_jacobian!!)
+__global__ void __launch_bounds__(256) lm_damp_kernel(int64_t n, double* __restrict__ C, int64_t ldc, double* __restrict__ dtd, double lambda) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const double d = fmax(dtd[j], C[j * ldc + j]);
+  dtd[j] = d;
+  C[j * ldc + j] += lambda * d;
+}
+}  // namespace
+namespace {
+// ---- Rescue of a singular LU (the reference's default dense solver falls back from a failed LU to a
+// column-pivoted QR, lib/NonlinearSolveBase/src/linear_solve.jl:48-55, ext/NonlinearSolveBaseLinearSolveExt.jl:42-49).
+// Householder QR with column pivoting, unblocked, ONE persistent CTA (32 warps, a warp per trailing column, coalesced down the
+// column): a rescue path for the small dense systems where a singular Jacobian can be met, not a roofline kernel.
+// On exit: R in the upper triangle, the Householder vectors below the diagonal (v_k = 1 implied), tau, jpvt, and the numerical
+// rank (|R_kk| > n eps |R_00|).
+constexpr int QR_T = 1024;
+__global__ void __launch_bounds__(QR_T, 1) qrcp_kernel(int64_t n, double* __restrict__ A, int64_t ld, double* __restrict__ tau, int32_t* __restrict__ jpvt,
+                                                        double* __restrict__ colnorm, int32_t* __restrict__ rank_out) {
+  __shared__ double red_v[32];
+  __shared__ int red_i[32];
+  __shared__ double s_a, s_b;
+  __shared__ int s_p;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int64_t j = tid; j < n; j += QR_T) jpvt[j] = (int32_t)j;
+  __syncthreads();
+  double r00 = 0.0;
+  int rank = 0;
+  for (int64_t k = 0; k < n; ++k) {
+    // squared norms of the trailing parts of columns k .. n-1 (recomputed: downdating loses accuracy exactly where it matters)
+    for (int64_t j = k + warp; j < n; j += 32) {
+      const double* c = A + j * ld;
+      double s = 0.0;
+      for (int64_t i = k + lane; i < n; i += 32) s = fma(c[i], c[i], s);
+      s = warp_sum(s);
+      if (lane == 0) colnorm[j] = s;
+    }
+    __syncthreads();
+    double best = -1.0;
+    int bi = (int)k;
+    for (int64_t j = k + tid; j < n; j += QR_T) { const double v = colnorm[j]; if (v > best) { best = v; bi = (int)j; } }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if (lane == 0) { red_v[warp] = best; red_i[warp] = bi; }
+    __syncthreads();
+    if (warp == 0) {
+      best = red_v[lane]; bi = red_i[lane];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+      }
+      if (lane == 0) { s_p = bi; s_a = best; }
+    }
+    __syncthreads();
+    const int64_t p = s_p;
+    const double cn2 = s_a;
+    if (p != k) {  // swap columns k and p (all rows) and the permutation
+      double *ck = A + k * ld, *cp = A + p * ld;
+      for (int64_t i = tid; i < n; i += QR_T) { const double t = ck[i]; ck[i] = cp[i]; cp[i] = t; }
+      if (tid == 0) { const int32_t t = jpvt[k]; jpvt[k] = jpvt[p]; jpvt[p] = t; }
+    }
+    __syncthreads();
+    // Householder reflector of column k: H = I - tau v v', v = (1, A[k+1:, k] / (alpha - beta)), H x = beta e_1
+    double* ck = A + k * ld;
+    if (tid == 0) {
+      const double alpha = ck[k];
+      const double xn2 = fmax(cn2 - alpha * alpha, 0.0);
+      double beta = 0.0, t = 0.0, scal = 0.0;
+      if (xn2 > 0.0 || alpha != 0.0) {
+        beta = -copysign(sqrt(alpha * alpha + xn2), alpha);
+        t = (beta - alpha) / beta;
+        scal = (xn2 > 0.0) ? 1.0 / (alpha - beta) : 0.0;
+        if (xn2 == 0.0) { beta = alpha; t = 0.0; }
+      }
+      ck[k] = beta;
+      tau[k] = t;
+      s_a = t; s_b = scal;
+    }
+    __syncthreads();
+    const double t = s_a, scal = s_b;
+    for (int64_t i = k + 1 + tid; i < n; i += QR_T) ck[i] *= scal;
+    __syncthreads();
+    if (k == 0) r00 = fabs(ck[0]);
+    if (fabs(ck[k]) > (double)n * 2.220446049250313e-16 * r00) rank = (int)k + 1;
+    // apply H to the trailing columns: w = v' a_j ; a_j -= tau w v     (a warp per column)
+    if (t != 0.0)
+      for (int64_t j = k + 1 + warp; j < n; j += 32) {
+        double* c = A + j * ld;
+        double s = (lane == 0) ? c[k] : 0.0;
+        for (int64_t i = k + 1 + lane; i < n; i += 32) s = fma(ck[i], c[i], s);
+        s = warp_sum(s) * t;
+        if (lane == 0) c[k] -= s;
+        for (int64_t i = k + 1 + lane; i < n; i += 32) c[i] = fma(-s, ck[i], c[i]);
+      }
+    __syncthreads();
+  }
+  if (tid == 0) *rank_out = rank;
+}
+// x = P [R11^-1 (Q' b)(1:r) ; 0]  — the basic least-squares solution of the rank-r system; b is overwritten
+__global__ void __launch_bounds__(QR_T, 1) qrcp_solve_kernel(int64_t n, const double* __restrict__ A, int64_t ld, const double* __restrict__ tau,
+                                                              const int32_t* __restrict__ jpvt, const int32_t* __restrict__ rank_in, double* __restrict__ b,
+                                                              double* __restrict__ x) {
+  __shared__ double red[32];
+  __shared__ double s_s;
+  const int tid = threadIdx.x;
+  const int r = *rank_in;
+  for (int64_t k = 0; k < n; ++k) {  // c = Q' b: reflectors in order
+    const double* ck = A + k * ld;
+    double s = 0.0;
+    for (int64_t i = k + 1 + tid; i < n; i += QR_T) s = fma(ck[i], b[i], s);
+    s = block_sum(s, red);
+    if (tid == 0) { s_s = (s + b[k]) * tau[k]; b[k] -= s_s; }
+    __syncthreads();
+    const double ss = s_s;
+    for (int64_t i = k + 1 + tid; i < n; i += QR_T) b[i] = fma(-ss, ck[i], b[i]);
+    __syncthreads();
+  }
+  for (int64_t k = r - 1; k >= 0; --k) {  // R11 y = c(1:r), column-oriented back substitution in place
+    const double* ck = A + k * ld;
+    if (tid == 0) { s_s = b[k] / ck[k]; b[k] = s_s; }
+    __syncthreads();
+    const double yk = s_s;
+    for (int64_t i = tid; i < k; i += QR_T) b[i] = fma(-ck[i], yk, b[i]);
+    __syncthreads();
+  }
+  for (int64_t k = tid; k < n; k += QR_T) x[jpvt[k]] = (k < r) ? b[k] : 0.0;
+}
+}  // namespace
+int32_t b200i_qrcp_solve(b200_ctx* ctx, int64_t n, double* A, int64_t ld, double* b, double* x, double* work /* >= 2 n doubles */, int32_t* jpvt_dev /* n + 1 */,
+                         int32_t* rank_host) {
+  double* tau = work;
+  double* colnorm = work + n;
+  LAUNCH(ctx, qrcp_kernel, 1, QR_T, 0, n, A, ld, tau, jpvt_dev, colnorm, jpvt_dev + n);
+  LAUNCH(ctx, qrcp_solve_kernel, 1, QR_T, 0, n, (const double*)A, ld, (const double*)tau, (const int32_t*)jpvt_dev, (const int32_t*)(jpvt_dev + n), b, x);
+  CHECK_LAUNCH(ctx);
+  if (rank_host) {
+    CUDA_TRY(ctx, cudaMemcpyAsync(rank_host, jpvt_dev + n, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return B200_OK;
+}
+
+int32_t b200i_gram(b200_ctx* ctx, int64_t n, const double* J, int64_t ld, double* C, int64_t ldc) {
+  dim3 grid((unsigned)((n + LMT - 1) / LMT), (unsigned)((n + LMT - 1) / LMT));
+  LAUNCH(ctx, gram_kernel, grid, 256, 0, n, J, ld, C, ldc);
+  CHECK_LAUNCH(ctx);
+  return B200_OK;
+}
+int32_t b200i_lm_damp(b200_ctx* ctx, int64_t n, double* C, int64_t ldc, double* dtd, double lambda) {
+  LAUNCH(ctx, lm_damp_kernel, (int)((n + 255) / 256), 256, 0, n, C, ldc, dtd, lambda);
+  CHECK_LAUNCH(ctx);
+  return B200_OK;
+}
+
+namespace {
 __global__ void __launch_bounds__(256) diag_shift_kernel(int64_t n, double* __restrict__ A, int64_t ld, double shift) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) A[i * ld + i] += shift;

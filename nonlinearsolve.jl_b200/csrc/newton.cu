@@ -49,10 +49,15 @@ struct b200_newton {
   // dense
   double* Jdense;
   int64_t* ipiv;
+  double* qr_work;    // pivoted-QR rescue of a singular LU (allocated on first use)
+  int32_t* qr_jpvt;
   // sparse
   b200_sparse_jac* sj;
   double* nzval;
   b200_sparse_lu* slu;  // LINSOLVE_SPARSE_LU: band factorisation of the assembled Jacobian
+  // LevenbergMarquardt: J'J + lambda D'D (factored in place), the running diagonal D'D, velocity / acceleration, previous velocity
+  double *lmA, *lm_dtd, *lm_v, *lm_a, *lm_vold, *lm_rhs;
+  double lm_lambda, lm_lambda_factor, lm_norm_v_old, lm_loss_old;
   // state
   TermCache tc;
   b200_newton_result res;
@@ -173,9 +178,11 @@ int32_t b200_newton_destroy(b200_newton* nw) {
   b200_ctx* ctx = nw->ctx;
   cudaStreamSynchronize(ctx->stream);
   double* vecs[] = {nw->u, nw->fu, nw->u_cache, nw->du, nw->xlin, nw->best_u, nw->u_trial, nw->fu_trial, nw->Jdu, nw->JTfu, nw->du_c, nw->c1, nw->c2,
-                    nw->Jdense, nw->nzval};
+                    nw->Jdense, nw->nzval, nw->lmA, nw->lm_dtd, nw->lm_v, nw->lm_a, nw->lm_vold, nw->lm_rhs};
   for (double* v : vecs) if (v) cudaFree(v);
   if (nw->ipiv) cudaFree(nw->ipiv);
+  if (nw->qr_work) cudaFree(nw->qr_work);
+  if (nw->qr_jpvt) cudaFree(nw->qr_jpvt);
   if (nw->gm) b200_gmres_destroy(nw->gm);
   if (nw->mg) b200i_mg_destroy(nw->mg);
   if (nw->sj) b200_sparse_jac_destroy(nw->sj);
@@ -192,8 +199,9 @@ int32_t b200_newton_create(b200_problem* prob, const b200_newton_opts* opts, b20
   B200_REQUIRE(ctx, opts->termination >= B200_TERM_ABS_NORM_SAFE_BEST && opts->termination <= B200_TERM_REL_NORM_SAFE_BEST, "newton_create: unknown termination mode");
   B200_REQUIRE(ctx, opts->term_norm == B200_NORM_INF || opts->term_norm == B200_NORM_L2, "newton_create: unknown termination norm");
   B200_REQUIRE(ctx, opts->term_max_stalled_steps <= 128, "newton_create: term_max_stalled_steps must be <= 128");
-  B200_REQUIRE(ctx, opts->descent == B200_DESCENT_NEWTON || (opts->descent == B200_DESCENT_PSEUDO_TRANSIENT && opts->globalization != B200_GLOBALIZATION_TRUST_REGION),
-               "newton_create: descent must be Newton or PseudoTransient (the latter without a trust region)");
+  B200_REQUIRE(ctx, opts->descent == B200_DESCENT_NEWTON || (opts->descent == B200_DESCENT_PSEUDO_TRANSIENT && opts->globalization != B200_GLOBALIZATION_TRUST_REGION) ||
+                        (opts->descent == B200_DESCENT_LEVENBERG_MARQUARDT && opts->globalization == B200_GLOBALIZATION_NONE && opts->linsolve == B200_LINSOLVE_DENSE_LU),
+               "newton_create: descent must be Newton, PseudoTransient (without a trust region) or LevenbergMarquardt (dense concrete Jacobian, its own trust region)");
   B200_REQUIRE(ctx, opts->precond == B200_PRECOND_NONE ||
                         ((opts->linsolve == B200_LINSOLVE_GMRES || opts->linsolve == B200_LINSOLVE_SPARSE_GMRES) &&
                          (prob->kind == B200_PROB_BRUSS2D || prob->kind == B200_PROB_BRUSS3D)),
@@ -206,6 +214,8 @@ int32_t b200_newton_create(b200_problem* prob, const b200_newton_opts* opts, b20
   nw->maxiters = opts->maxiters > 0 ? opts->maxiters : 1000;
   nw->u = nw->fu = nw->u_cache = nw->du = nw->xlin = nw->best_u = nullptr;
   nw->u_trial = nw->fu_trial = nw->Jdu = nw->JTfu = nw->du_c = nw->c1 = nw->c2 = nullptr;
+  nw->qr_work = nullptr; nw->qr_jpvt = nullptr;
+  nw->lmA = nw->lm_dtd = nw->lm_v = nw->lm_a = nw->lm_vold = nw->lm_rhs = nullptr;
   nw->slu = nullptr; nw->mg = nullptr; nw->gm = nullptr; nw->Jdense = nullptr; nw->ipiv = nullptr; nw->sj = nullptr; nw->nzval = nullptr;
   nw->initialised = 0;
   const int64_t n = nw->n;
@@ -217,6 +227,10 @@ int32_t b200_newton_create(b200_problem* prob, const b200_newton_opts* opts, b20
     A(&nw->u_trial); A(&nw->fu_trial); A(&nw->Jdu); A(&nw->JTfu); A(&nw->du_c); A(&nw->c1); A(&nw->c2);
   }
   if (opts->globalization == B200_GLOBALIZATION_LINESEARCH) { A(&nw->u_trial); A(&nw->fu_trial); A(&nw->Jdu); }
+  if (opts->descent == B200_DESCENT_LEVENBERG_MARQUARDT) {
+    A(&nw->u_trial); A(&nw->fu_trial); A(&nw->Jdu); A(&nw->lm_dtd); A(&nw->lm_v); A(&nw->lm_a); A(&nw->lm_vold); A(&nw->lm_rhs);
+    if (s == B200_OK && cudaMalloc(&nw->lmA, sizeof(double) * n * n) != cudaSuccess) { cudaGetLastError(); s = ctx->fail(B200_ERR_NOMEM, "LevenbergMarquardt: J'J does not fit in device memory", __FILE__, __LINE__); }
+  }
   if (s != B200_OK) { b200_newton_destroy(nw); return s; }
   memset(&nw->op, 0, sizeof(nw->op));
   nw->op.ctx = ctx; nw->op.n = n;
@@ -329,6 +343,15 @@ int32_t b200_newton_reinit(b200_newton* nw, const double* u0_dev) {
     nw->alpha_inv = 1.0 / (o.pt_alpha_initial > 0 ? o.pt_alpha_initial : 1.0e-3);
     B200_TRY(h_nrm2(nw, nw->fu, &nw->pt_res_norm));
   }
+  if (o.descent == B200_DESCENT_LEVENBERG_MARQUARDT) {  // LevenbergMarquardtDampingCache / TrustRegionCache init + reinit!  levenberg_marquardt.jl:71-117, 226-262
+    nw->lm_lambda = o.lm_damping_initial > 0 ? o.lm_damping_initial : 1.0;
+    nw->lm_lambda_factor = o.lm_damping_increase > 0 ? o.lm_damping_increase : 2.0;
+    B200_TRY(b200_fill(ctx, n, o.lm_min_damping_D > 0 ? o.lm_min_damping_D : 1.0e-8, nw->lm_dtd));
+    B200_TRY(b200_copy(ctx, n, nw->u, nw->lm_vold));   // `@bb v = copy(u)`: the previous velocity starts as u0
+    B200_TRY(b200_fill(ctx, n, 0.0, nw->du));
+    nw->lm_norm_v_old = INFINITY;
+    nw->lm_loss_old = INFINITY;
+  }
   nw->op.shift = 0.0;
   nw->eta = o.ew_eta0;
   if (o.forcing == B200_FORCING_EW2) {
@@ -339,7 +362,116 @@ int32_t b200_newton_reinit(b200_newton* nw, const double* u0_dev) {
   return B200_OK;
 }
 
+// One step of LevenbergMarquardt() (levenberg_marquardt.jl; descent/damped_newton.jl :normal_form; descent/geodesic_acceleration.jl:
+// 95-135; step! solve.jl:325-465).  All n-vectors and both n x n matrices stay on the device; the host takes the scalar
+// decisions from a handful of norms / dots.
+static int32_t lm_step(b200_newton* nw) {
+  b200_ctx* ctx = nw->ctx;
+  const int64_t n = nw->n;
+  const b200_newton_opts& o = nw->o;
+  const double inc = o.lm_damping_increase > 0 ? o.lm_damping_increase : 2.0, dec = o.lm_damping_decrease > 0 ? o.lm_damping_decrease : 3.0;
+  const double h = o.lm_finite_diff_step > 0 ? o.lm_finite_diff_step : 0.1, alpha_geo = o.lm_alpha_geodesic > 0 ? o.lm_alpha_geodesic : 0.75;
+  const double b_uphill = o.lm_b_uphill > 0 ? o.lm_b_uphill : (o.lm_b_uphill == 0 ? 1.0 : 0.0);
+  if (nw->make_new_jacobian) {  // J = cache.jac_cache(u)
+    nw->res.njacs += 1;
+    B200_TRY(b200_dense_jac_fill(nw->prob, nw->u, nw->Jdense, n));
+  }
+  // ---- DampedNewtonDescent, normal form: A = J'J + lambda D'D with D'D = running max of diag(J'J); v = -(A^-1 J' f)
+  B200_TRY(b200i_gram(ctx, n, nw->Jdense, n, nw->lmA, n));
+  B200_TRY(b200i_lm_damp(ctx, n, nw->lmA, n, nw->lm_dtd, nw->lm_lambda));
+  int32_t info = 0;
+  nw->res.nfactors += 1;
+  B200_TRY(b200_getrf(ctx, n, nw->lmA, n, nw->ipiv, &info));
+  int descent_ok = 1, tr_ok = 0, accepted = 0;
+  double objective = nw->fnorm_inf, du_norm = 0.0;
+  if (info != 0) {  // the damped normal matrix is singular: LinearSolve failure with a current Jacobian
+    if (nw->make_new_jacobian) { nw->retcode = B200_RC_INTERNAL_LINSOLVE_FAILED; nw->force_stop = 1; return B200_OK; }
+    nw->make_new_jacobian = 1;
+    return lm_step(nw);
+  }
+  B200_TRY(b200_gemv(ctx, 1, n, n, nw->Jdense, n, nw->fu, nw->lm_rhs));          // J' f
+  B200_TRY(b200_copy(ctx, n, nw->lm_rhs, nw->lm_v));
+  nw->res.nsolve += 1;
+  B200_TRY(b200_getrs(ctx, n, 1, nw->lmA, n, nw->ipiv, nw->lm_v, n));
+  B200_TRY(b200_scal(ctx, n, -1.0, nw->lm_v));
+  double norm_v;
+  B200_TRY(h_nrm2(nw, nw->lm_v, &norm_v));
+  if (!o.lm_disable_geodesic) {
+    // geodesic acceleration: fu_cache = (2/h) ((f(u + h v) - f(u)) / h - J v) ; a = -(A^-1 J' fu_cache) with the same factorisation
+    B200_TRY(b200_copy(ctx, n, nw->u, nw->u_trial));
+    B200_TRY(b200_axpy(ctx, n, h, nw->lm_v, nw->u_trial));
+    B200_TRY(b200_residual(nw->prob, nw->u_trial, nw->fu_trial));              // evaluate_f!! inside the descent: NLStats.nf is not bumped
+    B200_TRY(b200_gemv(ctx, 0, n, n, nw->Jdense, n, nw->lm_v, nw->Jdu));        // J v
+    B200_TRY(b200_axpy(ctx, n, -1.0, nw->fu, nw->fu_trial));
+    B200_TRY(b200_axpby(ctx, n, -2.0 / h, nw->Jdu, 2.0 / (h * h), nw->fu_trial));
+    B200_TRY(b200_gemv(ctx, 1, n, n, nw->Jdense, n, nw->fu_trial, nw->lm_a));
+    nw->res.nsolve += 1;
+    B200_TRY(b200_getrs(ctx, n, 1, nw->lmA, n, nw->ipiv, nw->lm_a, n));
+    B200_TRY(b200_scal(ctx, n, -1.0, nw->lm_a));
+    double norm_a;
+    B200_TRY(h_nrm2(nw, nw->lm_a, &norm_a));
+    if (2.0 * norm_a <= norm_v * alpha_geo) {
+      B200_TRY(b200_copy(ctx, n, nw->lm_v, nw->du));
+      B200_TRY(b200_axpy(ctx, n, 0.5, nw->lm_a, nw->du));                       // du = v + a / 2
+    } else {
+      descent_ok = 0;  // the step is not taken; du keeps its previous value (geodesic_acceleration.jl:131-133)
+    }
+  } else {
+    nw->res.nsolve += 0;
+    B200_TRY(b200_copy(ctx, n, nw->lm_v, nw->du));
+  }
+  if (descent_ok) {
+    nw->make_new_jacobian = 1;
+    // ---- LevenbergMarquardtTrustRegion: beta = cos(v, v_old); accept iff (1 - beta)^b_uphill * ||f(u + du)|| <= loss_old
+    double vdot;
+    B200_TRY(h_dot(nw, nw->lm_v, nw->lm_vold, &vdot));
+    const double beta = vdot / (norm_v * nw->lm_norm_v_old);
+    B200_TRY(b200_copy(ctx, n, nw->u, nw->u_trial));
+    B200_TRY(b200_axpy(ctx, n, 1.0, nw->du, nw->u_trial));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_scalars, 0, sizeof(double) * 2, ctx->stream));
+    B200_TRY(b200i_residual_norm(nw->prob, nw->u_trial, nw->fu_trial, ctx->d_scalars));
+    nw->res.nf += 1;
+    B200_TRY(b200i_fetch_scalars(ctx, 1));
+    const double trial_inf = ctx->h_scalars[0];
+    double loss;
+    B200_TRY(h_nrm2(nw, nw->fu_trial, &loss));
+    tr_ok = (pow(1.0 - beta, b_uphill) * loss <= nw->lm_loss_old) ? 1 : 0;     // loss_old is never updated by the reference (stays Inf)
+    if (tr_ok) {
+      nw->lm_norm_v_old = norm_v;
+      B200_TRY(b200_copy(ctx, n, nw->lm_v, nw->lm_vold));
+      B200_TRY(h_nrm2(nw, nw->du, &du_norm));
+      std::swap(nw->u, nw->u_trial);
+      std::swap(nw->fu, nw->fu_trial);
+      objective = trial_inf;
+      accepted = 1;
+    } else {
+      nw->make_new_jacobian = 0;
+    }
+    nw->fnorm_inf = objective;
+    bool new_best = false;
+    TermQuant tq;
+    B200_TRY(term_quantities(nw, nw->fu, nw->u, objective, &tq));
+    if (term_check(nw, tq, du_norm, &new_best)) { nw->retcode = nw->tc.retcode; nw->force_stop = 1; }
+    if (new_best && nw->best_u) CUDA_TRY(ctx, cudaMemcpyAsync(nw->best_u, nw->u, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+  } else {
+    nw->make_new_jacobian = 0;
+  }
+  if (o.store_trace) {
+    b200_trace_rec t;
+    memset(&t, 0, sizeof(t));
+    t.iter = nw->nsteps + 1; t.accepted = accepted; t.fnorm_inf = objective; t.step_norm2 = du_norm; t.trust_radius = nw->lm_lambda;  // the damping USED by this step
+    t.lin_status = descent_ok;
+    nw->trace.push_back(t);
+  }
+  // callback_into_cache! (levenberg_marquardt.jl:176-185): lambda shrinks after a step both the descent and the trust region accepted
+  if (descent_ok && tr_ok) nw->lm_lambda_factor = 1.0 / dec;
+  nw->lm_lambda *= nw->lm_lambda_factor;
+  nw->lm_lambda_factor = inc;
+  return B200_OK;
+}
+
 static int32_t newton_step_inner(b200_newton* nw) {
+  if (nw->o.descent == B200_DESCENT_LEVENBERG_MARQUARDT) return lm_step(nw);
   b200_ctx* ctx = nw->ctx;
   const int64_t n = nw->n;
   const b200_newton_opts& o = nw->o;
@@ -421,6 +553,21 @@ static int32_t newton_step_inner(b200_newton* nw) {
       }
       CUDA_TRY(ctx, cudaMemcpyAsync(nw->xlin, nw->fu, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
       if (lin_success) B200_TRY(b200_getrs(ctx, n, 1, nw->Jdense, n, nw->ipiv, nw->xlin, n));
+      else if (n <= 4096) {
+        // singular LU: LinearSolve's default dense solver falls back to a column-pivoted QR (linear_solve.jl:48-55).  The
+        // factorisation destroyed J: refill it, solve in the least-squares sense (basic solution of the numerical-rank system).
+        B200_TRY(b200_dense_jac_fill(nw->prob, nw->u, nw->Jdense, n));
+        if (o.descent == B200_DESCENT_PSEUDO_TRANSIENT) B200_TRY(b200i_diag_shift(ctx, n, nw->Jdense, n, nw->alpha_inv));
+        if (!nw->qr_work) {
+          CUDA_TRY(ctx, cudaMalloc(&nw->qr_work, sizeof(double) * (3 * n + 2)));
+          CUDA_TRY(ctx, cudaMalloc(&nw->qr_jpvt, sizeof(int32_t) * (n + 2)));
+        }
+        CUDA_TRY(ctx, cudaMemcpyAsync(nw->qr_work + 2 * n, nw->fu, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+        int32_t rank = 0;
+        B200_TRY(b200i_qrcp_solve(ctx, n, nw->Jdense, n, nw->qr_work + 2 * n, nw->xlin, nw->qr_work, nw->qr_jpvt, &rank));
+        nw->have_factor = 0;  // Jdense now holds the QR factors: the next step refactorises whatever happens
+        lin_success = rank > 0 ? 1 : 0;
+      }
     } else {
       // `linu` aliases the du buffer: it is the initial guess only when warm_start is requested
       if (o.gmres.warm_start) CUDA_TRY(ctx, cudaMemcpyAsync(nw->xlin, nw->du, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));

@@ -30,6 +30,11 @@ def cases():
         out.append(dict(base, name="linesearch_N%d_x%g" % (N, scale), globalization="linesearch"))
         if scale <= 10.0:
             out.append(dict(base, name="pseudotransient_N%d_x%g" % (N, scale), descent="pseudo_transient", alpha_initial=1.0, maxiters=200))
+    for scale in (1.0, 5.0, 30.0):   # 5x: two geodesic rejections; 30x: a long accept / reject pattern with the damping doubling and tripling
+        out.append(dict(problem="bruss2d", N=6, u0_scale=scale, name="levenberg_marquardt_N6_x%g" % scale, descent="levenberg_marquardt", abstol=1e-8, reltol=1e-8, maxiters=300))
+    out.append(dict(problem="bruss2d", N=6, u0_scale=10.0, name="levenberg_marquardt_nogeodesic_N6_x10", descent="levenberg_marquardt", disable_geodesic=True, abstol=1e-8,
+                    reltol=1e-8, maxiters=300))
+    out.append(dict(problem="quadratic", n=10, name="levenberg_marquardt_quadratic", descent="levenberg_marquardt", abstol=1e-9, reltol=1e-9))
     out.append(dict(problem="quadratic", n=10, name="pseudotransient_quadratic_alpha10", descent="pseudo_transient", alpha_initial=10.0, abstol=1e-9, reltol=1e-9))
     for m in MODES:
         for norm in ("inf", "l2"):
@@ -46,6 +51,12 @@ def run(case):
         prob = nn.Quadratic(case["n"])
         u0 = np.ones(case["n"])
     term = nn.Termination(mode=case.get("termination", "AbsNormSafeBest"), norm=case.get("term_norm", "inf"), abstol=case["abstol"], reltol=case["reltol"])
+    if case.get("descent") == "levenberg_marquardt":
+        r = nn.solve_lm(prob, u0, disable_geodesic=case.get("disable_geodesic", False), termination=term, maxiters=case.get("maxiters", 1000))
+        u = r.pop("u")
+        r["u_norm2"] = float(np.linalg.norm(u))
+        r["u_first"] = [float(x) for x in u[:4]]
+        return r
     r = nn.solve(prob, u0, globalization=case.get("globalization", "none"), tr_scheme=case.get("tr_scheme", "Simple"), descent=case.get("descent", "newton"),
                  alpha_initial=case.get("alpha_initial", 1e-3), termination=term, maxiters=case.get("maxiters", 1000))
     u = r.pop("u")

@@ -53,6 +53,8 @@ def _compare(name, e, res, trace, u, radius_of=lambda t: t.trust_radius):
 
 
 def _oracle_supported(c):
+    if c.get("descent") == "levenberg_marquardt":
+        return False
     return c.get("termination", "AbsNormSafeBest") in ("AbsNormSafeBest", "AbsNorm", "AbsNormSafe") and c.get("term_norm", "inf") == "inf" and \
         c.get("tr_scheme", "Simple") != "Bastin"
 
@@ -92,6 +94,8 @@ def test_cuda_driver_reproduces_the_numpy_sequences(nls, ctx, d):
     term = getattr(nls, c.get("termination", "AbsNormSafeBest") + "TerminationMode")(norm=c.get("term_norm", "inf"))
     if c.get("globalization") == "trust_region":
         alg = nls.TrustRegion(radius_update_scheme=getattr(nls.RadiusUpdateSchemes, c["tr_scheme"]))
+    elif c.get("descent") == "levenberg_marquardt":
+        alg = nls.LevenbergMarquardt(disable_geodesic=c.get("disable_geodesic", False))
     elif c.get("descent") == "pseudo_transient":
         alg = nls.PseudoTransient(alpha_initial=c["alpha_initial"])
     elif c.get("globalization") == "linesearch":
@@ -103,3 +107,5 @@ def test_cuda_driver_reproduces_the_numpy_sequences(nls, ctx, d):
     class R:
         retcode, nsteps, nf, njacs, nfactors, nsolve = sol.retcode, sol.stats.nsteps, sol.stats.nf, sol.stats.njacs, sol.stats.nfactors, sol.stats.nsolve
     _compare(c["name"], e, R, sol.trace, sol.u)
+    if "descent_ok" in e:   # Levenberg-Marquardt: the geodesic-acceleration verdict of every step (trace slot lin_status)
+        assert [t.lin_status for t in sol.trace] == e["descent_ok"], c["name"]
