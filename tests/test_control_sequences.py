@@ -31,25 +31,25 @@ def test_fixture_is_what_the_generator_produces():
                 assert a["expect"][k] == pytest.approx(v, rel=1e-9, abs=1e-12), (b["case"]["name"], k)
 
 
-def _compare(name, e, res, trace, u, radius_of=lambda t: t.trust_radius):
+def _compare(name, e, res, trace, u, radius_of=lambda t: t.trust_radius, rtol=1e-7):
     assert res.retcode == e["retcode"], name
     assert (res.nsteps, res.nf, res.njacs, res.nfactors, res.nsolve) == (e["nsteps"], e["nf"], e["njacs"], e["nfactors"], e["nsolve"]), name
     assert [t.accepted for t in trace] == e["accepted"], name
     fn = np.array([t.fnorm_inf for t in trace])
     ref = np.array(e["fnorm_inf"])
     big = ref > 1e-6 * ref.max()          # below that the residual is rounding of the last Newton step
-    assert np.allclose(fn[big], ref[big], rtol=1e-7), (name, fn, ref)
+    assert np.allclose(fn[big], ref[big], rtol=rtol), (name, fn, ref)
     rad = np.array([radius_of(t) for t in trace])
     er = np.array(e["radius"])
     # radii that are functions of a residual at rounding level (Yuan: p1 ||J' f||, Fan: p1 ||f||^0.99, SER: ratio of residual
     # norms) inherit its relative noise (a factor of 2 between two correct LU solves): exact to 1e-7 while the residual is
     # resolved, only sanity afterwards
-    assert np.allclose(rad[big], er[big], rtol=1e-7, atol=1e-300), (name, rad, er)
+    assert np.allclose(rad[big], er[big], rtol=rtol, atol=1e-300), (name, rad, er)
     assert np.all(np.isfinite(rad[~big])) and np.all(rad[~big] >= 0.0), (name, rad, er)
     sn = np.array([t.step_norm2 for t in trace])
     rs = np.array(e["step_norm2"])
-    assert np.allclose(sn[big], rs[big], rtol=1e-6), name
-    assert abs(np.linalg.norm(u) - e["u_norm2"]) <= 1e-8 * e["u_norm2"] and np.allclose(u[:4], e["u_first"], rtol=1e-7), name
+    assert np.allclose(sn[big], rs[big], rtol=10 * rtol), name
+    assert abs(np.linalg.norm(u) - e["u_norm2"]) <= 1e-8 * e["u_norm2"] and np.allclose(u[:4], e["u_first"], rtol=max(rtol, 1e-7)), name
 
 
 def _oracle_supported(c):
@@ -106,6 +106,8 @@ def test_cuda_driver_reproduces_the_numpy_sequences(nls, ctx, d):
 
     class R:
         retcode, nsteps, nf, njacs, nfactors, nsolve = sol.retcode, sol.stats.nsteps, sol.stats.nf, sol.stats.njacs, sol.stats.nfactors, sol.stats.nsolve
-    _compare(c["name"], e, R, sol.trace, sol.u)
+    # Levenberg-Marquardt solves the normal equations (condition number squared): every DECISION must agree exactly, the
+    # residual history to 1e-4 (two correct dense solves of J'J + lambda D'D differ by kappa(J)^2 eps per step)
+    _compare(c["name"], e, R, sol.trace, sol.u, rtol=1e-4 if c.get("descent") == "levenberg_marquardt" else 1e-7)
     if "descent_ok" in e:   # Levenberg-Marquardt: the geodesic-acceleration verdict of every step (trace slot lin_status)
         assert [t.lin_status for t in sol.trace] == e["descent_ok"], c["name"]
