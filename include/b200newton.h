@@ -65,7 +65,8 @@ enum {
   B200_RC_INTERNAL_LINESEARCH_FAILED = 8,
   B200_RC_SHRINK_THRESHOLD_EXCEEDED = 9,
   B200_RC_INITIAL_FAILURE = 10,
-  B200_RC_FAILURE = 11
+  B200_RC_FAILURE = 11,
+  B200_RC_CONVERGENCE_FAILURE = 12 /* quasi-Newton: max_resets reached (NonlinearSolveQuasiNewton/src/solve.jl:343-347) */
 };
 
 /* linear (GMRES) solve status; maps to LinearSolve retcodes (Success / MaxIters / Failure) */
@@ -95,7 +96,13 @@ enum { B200_TR_SIMPLE = 0, B200_TR_NLSOLVE = 1, B200_TR_NOCEDAL_WRIGHT = 2, B200
 /* LEVENBERG_MARQUARDT (levenberg_marquardt.jl:36-61): DampedNewtonDescent with the Levenberg-Marquardt damping function
    (running maximum of diag(J'J), floor min_damping_D) wrapped in GeodesicAcceleration, with LevenbergMarquardtTrustRegion;
    concrete (dense) Jacobian; the damped system is solved in normal form, (J'J + lambda D'D) v = J'f */
-enum { B200_DESCENT_NEWTON = 0, B200_DESCENT_PSEUDO_TRANSIENT = 1, B200_DESCENT_LEVENBERG_MARQUARDT = 2 };
+enum { B200_DESCENT_NEWTON = 0, B200_DESCENT_PSEUDO_TRANSIENT = 1, B200_DESCENT_LEVENBERG_MARQUARDT = 2, B200_DESCENT_BROYDEN = 3 };
+/* BROYDEN (NonlinearSolveQuasiNewton/src/broyden.jl:34-51): the quasi-Newton family's Broyden() — NewtonDescent on a
+   STORED INVERSE J^-1 (dense n x n, resident in HBM), rank-one good / bad Broyden update after every step, NoChangeInStateReset
+   (reset_conditions.jl:18-88) re-initialising J^-1, ConvergenceFailure after max_resets.  The step routine is keyed on this field
+   because the option struct is; in the reference it is its own algorithm type, not a descent. */
+enum { B200_QN_INIT_IDENTITY = 0, B200_QN_INIT_TRUE_JACOBIAN = 1 };   /* init_jacobian = Val(:identity) | Val(:true_jacobian) (needs linsolve = DENSE_LU) */
+enum { B200_QN_UPDATE_GOOD_BROYDEN = 0, B200_QN_UPDATE_BAD_BROYDEN = 1 };
 /* built-in preconditioners (LinearSolve `precs(A, p)`, large_systems.md:244-316): inverse of the 2x2 species blocks, or one
    geometric-multigrid V-cycle of the Brusselator Jacobian (the tutorial's AlgebraicMultigrid ruge_stuben / smoothed_aggregation) */
 enum { B200_PRECOND_NONE = 0, B200_PRECOND_BLOCK_JACOBI_LEFT = 1, B200_PRECOND_BLOCK_JACOBI_RIGHT = 2,
@@ -189,6 +196,11 @@ typedef struct b200_newton_opts {
   double lm_damping_initial, lm_damping_increase, lm_damping_decrease, lm_finite_diff_step, lm_alpha_geodesic, lm_b_uphill, lm_min_damping_D;
   int32_t lm_disable_geodesic;
   int32_t reserved0;
+  /* Broyden(; max_resets = 100, reset_tolerance = eps^(3/4), init_jacobian = Val(:identity), alpha = nothing, update_rule =
+     Val(:good_broyden)); qn_alpha <= 0 => 2 ||f|| / max(||u||, 1) (1 when ||f|| < 1e-5), the identity is scaled by it before
+     inversion */
+  int32_t qn_init_jacobian, qn_update_rule, qn_max_resets, reserved1;
+  double qn_reset_tolerance, qn_alpha;
 } b200_newton_opts;
 
 typedef struct b200_newton_result {

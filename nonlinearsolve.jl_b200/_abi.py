@@ -14,9 +14,10 @@ LIB_PATH = os.path.join(_HERE, "libb200newton.so")
 OK, ERR_CUDA, ERR_INVALID, ERR_NOMEM, ERR_UNSUPPORTED, ERR_CALLBACK, ERR_NO_DEVICE = 0, -1, -2, -3, -4, -5, -6
 RC_DEFAULT, RC_SUCCESS, RC_MAXITERS, RC_MAXTIME, RC_STALLED, RC_STALLED_SUCCESS, RC_UNSTABLE = 0, 1, 2, 3, 4, 5, 6
 RC_INTERNAL_LINSOLVE_FAILED, RC_INTERNAL_LINESEARCH_FAILED, RC_SHRINK_THRESHOLD_EXCEEDED, RC_INITIAL_FAILURE, RC_FAILURE = 7, 8, 9, 10, 11
+RC_CONVERGENCE_FAILURE = 12
 RETCODE_NAMES = {0: "Default", 1: "Success", 2: "MaxIters", 3: "MaxTime", 4: "Stalled", 5: "StalledSuccess", 6: "Unstable",
                  7: "InternalLinearSolveFailed", 8: "InternalLineSearchFailed", 9: "ShrinkThresholdExceeded",
-                 10: "InitialFailure", 11: "Failure"}
+                 10: "InitialFailure", 11: "Failure", 12: "ConvergenceFailure"}
 LS_SOLVED, LS_MAXITERS, LS_BREAKDOWN, LS_NONFINITE, LS_OUT_OF_MEMORY = 1, 2, 3, 4, 5
 PROB_BRUSS2D, PROB_BRUSS3D, PROB_QUADRATIC, PROB_TRIDIAG_QUAD, PROB_CALLBACK = 1, 2, 3, 4, 5
 ORTH_MGS, ORTH_CGS, ORTH_CGS2 = 0, 1, 2
@@ -25,7 +26,9 @@ LINSOLVE_GMRES, LINSOLVE_DENSE_LU, LINSOLVE_SPARSE_GMRES, LINSOLVE_SPARSE_LU = 0
 JVP_EXACT, JVP_FINITE_DIFF = 0, 1
 GLOB_NONE, GLOB_TRUST_REGION, GLOB_LINESEARCH = 0, 1, 2
 PRECOND_NONE, PRECOND_BLOCK_JACOBI_LEFT, PRECOND_BLOCK_JACOBI_RIGHT, PRECOND_MULTIGRID_LEFT, PRECOND_MULTIGRID_RIGHT = 0, 1, 2, 3, 4
-DESCENT_NEWTON, DESCENT_PSEUDO_TRANSIENT, DESCENT_LEVENBERG_MARQUARDT = 0, 1, 2
+DESCENT_NEWTON, DESCENT_PSEUDO_TRANSIENT, DESCENT_LEVENBERG_MARQUARDT, DESCENT_BROYDEN = 0, 1, 2, 3
+QN_INIT_IDENTITY, QN_INIT_TRUE_JACOBIAN = 0, 1
+QN_UPDATE_GOOD_BROYDEN, QN_UPDATE_BAD_BROYDEN = 0, 1
 TR_SIMPLE, TR_NLSOLVE, TR_NOCEDAL_WRIGHT, TR_HEI, TR_YUAN, TR_FAN, TR_BASTIN = range(7)
 FORCING_NONE, FORCING_EW2 = 0, 1
 TERM_ABS_NORM_SAFE_BEST, TERM_ABS_NORM, TERM_ABS_NORM_SAFE, TERM_NORM, TERM_REL, TERM_REL_NORM, TERM_ABS, TERM_REL_NORM_SAFE, TERM_REL_NORM_SAFE_BEST = range(9)
@@ -59,7 +62,9 @@ class NewtonOpts(C.Structure):
                 ("pt_alpha_initial", C.c_double), ("maxtime", C.c_double), ("term_norm", C.c_int32), ("term_max_stalled_steps", C.c_int32),
                 ("lm_damping_initial", C.c_double), ("lm_damping_increase", C.c_double), ("lm_damping_decrease", C.c_double), ("lm_finite_diff_step", C.c_double),
                 ("lm_alpha_geodesic", C.c_double), ("lm_b_uphill", C.c_double), ("lm_min_damping_D", C.c_double), ("lm_disable_geodesic", C.c_int32),
-                ("reserved0", C.c_int32)]
+                ("reserved0", C.c_int32),
+                ("qn_init_jacobian", C.c_int32), ("qn_update_rule", C.c_int32), ("qn_max_resets", C.c_int32), ("reserved1", C.c_int32),
+                ("qn_reset_tolerance", C.c_double), ("qn_alpha", C.c_double)]
 
 
 class NewtonResult(C.Structure):

@@ -216,6 +216,7 @@ def _as_device(ctx, x):
 class ReturnCode:
     Default, Success, MaxIters, MaxTime, Stalled, StalledSuccess, Unstable = 0, 1, 2, 3, 4, 5, 6
     InternalLinearSolveFailed, InternalLineSearchFailed, ShrinkThresholdExceeded, InitialFailure, Failure = 7, 8, 9, 10, 11
+    ConvergenceFailure = 12
 
     @staticmethod
     def name(code):
@@ -567,6 +568,28 @@ class LevenbergMarquardt(_FirstOrder):
         self.disable_geodesic = bool(disable_geodesic)
 
 
+class Broyden(_FirstOrder):
+    """Broyden(; max_resets = 100, reset_tolerance = nothing, init_jacobian = Val(:identity), alpha = nothing, update_rule =
+    Val(:good_broyden))  NonlinearSolveQuasiNewton/src/broyden.jl:34-51 — the quasi-Newton family's dense Broyden:
+    NewtonDescent on a stored inverse that stays in HBM, rank-one update per step, NoChangeInStateReset, ConvergenceFailure after
+    `max_resets`.  `init_jacobian`: "identity" | "true_jacobian"; `update_rule`: "good_broyden" | "bad_broyden".  The trace's
+    `lin_status` slot flags the steps before which J^-1 was re-initialised."""
+    name = "Broyden"
+    descent = abi.DESCENT_BROYDEN
+
+    def __init__(self, max_resets=100, reset_tolerance=None, init_jacobian="identity", alpha=None, update_rule="good_broyden", autodiff=None):
+        init_jacobian, update_rule = str(init_jacobian).strip(":"), str(update_rule).strip(":")
+        if init_jacobian not in ("identity", "true_jacobian"):
+            raise ValueError("Unknown `init_jacobian = %r`: identity or true_jacobian" % init_jacobian)
+        if update_rule not in ("good_broyden", "bad_broyden"):
+            raise ValueError("Unknown update rule %r: good_broyden or bad_broyden (the diagonal structure is not offered)" % update_rule)
+        super().__init__(init_jacobian == "true_jacobian", None, autodiff, None, None, None, None)
+        self.qn = dict(qn_init_jacobian=abi.QN_INIT_TRUE_JACOBIAN if init_jacobian == "true_jacobian" else abi.QN_INIT_IDENTITY,
+                       qn_update_rule=abi.QN_UPDATE_BAD_BROYDEN if update_rule == "bad_broyden" else abi.QN_UPDATE_GOOD_BROYDEN,
+                       qn_max_resets=int(max_resets))
+        self.reset_tolerance, self.alpha = reset_tolerance, alpha
+
+
 class RadiusUpdateSchemes:
     """RadiusUpdateSchemes.{Simple, NLsolve, NocedalWright, Hei, Yuan, Fan, Bastin}  (trust_region.jl:431-520)."""
     Simple, NLsolve, NocedalWright, Hei, Yuan, Fan, Bastin = (abi.TR_SIMPLE, abi.TR_NLSOLVE, abi.TR_NOCEDAL_WRIGHT, abi.TR_HEI, abi.TR_YUAN, abi.TR_FAN, abi.TR_BASTIN)
@@ -648,6 +671,15 @@ def _build_opts(prob, alg, abstol, reltol, maxiters, termination_condition, stor
         for k, v in alg.lm.items():
             setattr(o, k, float(v))
         o.lm_disable_geodesic = 1 if alg.disable_geodesic else 0
+    if isinstance(alg, Broyden):
+        if sparse:
+            raise TypeError("Broyden keeps a dense inverse: no sparse prototype")
+        # the stored inverse needs no linear solver; the dense LU is there only to invert the true Jacobian at (re)initialisation
+        o.linsolve = abi.LINSOLVE_DENSE_LU if alg.qn["qn_init_jacobian"] == abi.QN_INIT_TRUE_JACOBIAN else abi.LINSOLVE_GMRES
+        for k, v in alg.qn.items():
+            setattr(o, k, int(v))
+        o.qn_reset_tolerance = float(alg.reset_tolerance) if alg.reset_tolerance is not None else 0.0
+        o.qn_alpha = float(alg.alpha) if alg.alpha is not None else 0.0
     if isinstance(alg, TrustRegion):
         for k, v in alg.tr.items():
             setattr(o, k, float(v))

@@ -57,7 +57,8 @@ struct b200_ctx {
 
 #define B200_RED_MAX_BLOCKS 2048
 enum { RED_DOT = 0, RED_SUMSQ = 1, RED_MAXABS = 2, RED_DIFFSQ = 3, RED_MIN = 4, RED_MAX = 5, RED_NEQ = 6,
-       RED_SUMSQ2 = 7 /* sum (x+y)^2 */, RED_MAXABS2 = 8 /* max |x+y| */, RED_RELVIOL = 9 /* #{ |x| > a |x+y| } */ };
+       RED_SUMSQ2 = 7 /* sum (x+y)^2 */, RED_MAXABS2 = 8 /* max |x+y| */, RED_RELVIOL = 9 /* #{ |x| > a |x+y| } */,
+       RED_COUNT_LE = 10 /* #{ |x| <= a } */, RED_COUNT_DIFF_LE = 11 /* #{ |x - y| <= a } */ };
 
 #define CUDA_TRY(ctx, expr)                                                             \
   do {                                                                                  \
@@ -156,6 +157,31 @@ struct b200_problem {
 struct b200_sparse_jac;
 struct b200_mg;
 
+// ---- mbarrier + TMA bulk copy (cp.async.bulk, 1-D): a single thread starts a copy of `bytes` (multiple of 16, both addresses
+//      16-byte aligned) that completes on an mbarrier; waits are bounded so a fault cannot hang the GPU
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  unsigned done = 0, spins = 0;
+  while (!done) {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(a), "r"(parity) : "memory");
+    if (++spins > (1u << 26)) break;
+  }
+}
+__device__ __forceinline__ void tma_bulk_load(void* smem_dst, const void* gsrc, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+               : "memory");
+}
+
+
+constexpr int32_t B200I_ENS_RC_DEFERRED = -7;  // batched ensemble kernel -> host: redo this trajectory through the general driver (never returned to a caller)
+
 struct b200_linop {
   b200_ctx* ctx;
   int32_t kind;  // 0 problem-jvp, 1 csc, 2 dense, 3 callback, 4 sparse_jac
@@ -174,6 +200,7 @@ struct b200_linop {
   double shift;  // operator is A + shift I
   b200_mg* mg;   // LINOP_MULTIGRID: the hierarchy (owned when owns_mg)
   int32_t owns_mg;
+  int64_t *csr_rowptr, *csr_col, *csr_map;  // LINOP_CSC: row view of the pattern (owned), built once so that y = A x is a deterministic gather
 };
 enum { LINOP_PROBLEM = 0, LINOP_CSC = 1, LINOP_DENSE = 2, LINOP_CALLBACK = 3, LINOP_SPARSE_JAC = 4, LINOP_BLOCK_JACOBI = 5, LINOP_MULTIGRID = 6 };
 
@@ -197,6 +224,8 @@ int32_t b200i_diag_shift(b200_ctx* ctx, int64_t n, double* A, int64_t ld, double
 // column-pivoted Householder QR solve of a (possibly rank-deficient) dense system: the rescue of a singular LU
 int32_t b200i_qrcp_solve(b200_ctx* ctx, int64_t n, double* A, int64_t ld, double* b, double* x, double* work, int32_t* jpvt_dev, int32_t* rank_host);
 int32_t b200i_gram(b200_ctx* ctx, int64_t n, const double* J, int64_t ld, double* C, int64_t ldc);          // C = J' J
+int32_t b200i_ger(b200_ctx* ctx, int64_t n, double* A, int64_t ld, const double* c, const double* w);              // A += c w'
+int32_t b200i_scaled_identity(b200_ctx* ctx, int64_t n, double* A, int64_t ld, double d);                          // A = d I
 int32_t b200i_lm_damp(b200_ctx* ctx, int64_t n, double* C, int64_t ldc, double* dtd, double lambda);     // dtd = max(dtd, diag C); C += lambda diag(dtd)
 void b200i_sparse_jac_csr(b200_sparse_jac* sj, const int64_t** rowptr, const int64_t** csr_col, const int64_t** csr_map);
 int32_t b200i_residual_norm(b200_problem* prob, const double* u, double* du, double* d_norminf /*device, pre-zeroed*/);

@@ -277,6 +277,8 @@ __global__ void __launch_bounds__(EW_THREADS) reduce_stage1(int64_t n, const dou
     else if (MODE == RED_SUMSQ2) { double d = x[i] + y[i]; v = d * d; }
     else if (MODE == RED_MAXABS2) v = abs_nf(x[i] + y[i]);
     else if (MODE == RED_RELVIOL) v = (fabs(x[i]) <= a * fabs(x[i] + y[i])) ? 0.0 : 1.0;  // NaN counts as a violation
+    else if (MODE == RED_COUNT_LE) v = (fabs(x[i]) <= a) ? 1.0 : 0.0;
+    else if (MODE == RED_COUNT_DIFF_LE) v = (fabs(x[i] - y[i]) <= a) ? 1.0 : 0.0;
     else v = x[i];
     acc = red_combine<MODE>(acc, v);
   }
@@ -308,6 +310,8 @@ int32_t b200i_reduce_sum_dev(b200_ctx* ctx, int64_t n, const double* x, const do
     case RED_SUMSQ2: return reduce_dev<RED_SUMSQ2>(ctx, n, x, y, d_out, ctx->d_partials);
     case RED_MAXABS2: return reduce_dev<RED_MAXABS2>(ctx, n, x, y, d_out, ctx->d_partials);
     case RED_RELVIOL: return reduce_dev<RED_RELVIOL>(ctx, n, x, y, d_out, ctx->d_partials, a);
+    case RED_COUNT_LE: return reduce_dev<RED_COUNT_LE>(ctx, n, x, y, d_out, ctx->d_partials, a);
+    case RED_COUNT_DIFF_LE: return reduce_dev<RED_COUNT_DIFF_LE>(ctx, n, x, y, d_out, ctx->d_partials, a);
     case RED_DOT: return reduce_dev<RED_DOT>(ctx, n, x, y, d_out, ctx->d_partials);
     case RED_SUMSQ: return reduce_dev<RED_SUMSQ>(ctx, n, x, y, d_out, ctx->d_partials);
     case RED_MAXABS: return reduce_dev<RED_MAXABS>(ctx, n, x, y, d_out, ctx->d_partials);

@@ -599,6 +599,50 @@ __global__ void __launch_bounds__(256) diag_shift_kernel(int64_t n, double* __re
   if (i < n) A[i * ld + i] += shift;
 }
 }  // namespace
+namespace {
+// ---- quasi-Newton (Broyden) level-2 kernels on the stored inverse: HBM-bound, one pass over the n x n matrix each
+// A[:, j] += c * w[j] for a tile of columns: 16-byte accesses down the column, c kept in registers across GER_CPB columns
+constexpr int GER_T = 256, GER_CPB = 8;
+__global__ void __launch_bounds__(GER_T) ger_kernel(int64_t n, double* __restrict__ A, int64_t ld, const double* __restrict__ c, const double* __restrict__ w) {
+  const int64_t i = ((int64_t)blockIdx.x * GER_T + threadIdx.x) * 2;
+  const int64_t j0 = (int64_t)blockIdx.y * GER_CPB;
+  if (i >= n) return;
+  const bool pair = (i + 1 < n) && ((ld & 1) == 0);
+  const double c0 = c[i], c1 = (i + 1 < n) ? c[i + 1] : 0.0;
+#pragma unroll
+  for (int jj = 0; jj < GER_CPB; ++jj) {
+    const int64_t j = j0 + jj;
+    if (j >= n) break;
+    const double wj = w[j];
+    double* col = A + j * ld + i;
+    if (pair) {
+      double2 a = *reinterpret_cast<double2*>(col);
+      a.x = fma(c0, wj, a.x); a.y = fma(c1, wj, a.y);
+      *reinterpret_cast<double2*>(col) = a;
+    } else {
+      col[0] = fma(c0, wj, col[0]);
+      if (i + 1 < n) col[1] = fma(c1, wj, col[1]);
+    }
+  }
+}
+__global__ void __launch_bounds__(256) scaled_identity_kernel(int64_t n, double* __restrict__ A, int64_t ld, double d) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t j = blockIdx.y;
+  if (i < n) A[j * ld + i] = (i == j) ? d : 0.0;
+}
+}  // namespace
+int32_t b200i_ger(b200_ctx* ctx, int64_t n, double* A, int64_t ld, const double* c, const double* w) {
+  const dim3 grid((unsigned)((n + 2 * GER_T - 1) / (2 * GER_T)), (unsigned)((n + GER_CPB - 1) / GER_CPB));
+  LAUNCH(ctx, ger_kernel, grid, GER_T, 0, n, A, ld, c, w);
+  CHECK_LAUNCH(ctx);
+  return B200_OK;
+}
+int32_t b200i_scaled_identity(b200_ctx* ctx, int64_t n, double* A, int64_t ld, double d) {
+  const dim3 grid((unsigned)((n + 255) / 256), (unsigned)n);
+  LAUNCH(ctx, scaled_identity_kernel, grid, 256, 0, n, A, ld, d);
+  CHECK_LAUNCH(ctx);
+  return B200_OK;
+}
 int32_t b200i_diag_shift(b200_ctx* ctx, int64_t n, double* A, int64_t ld, double shift) {
   LAUNCH(ctx, diag_shift_kernel, (int)((n + 255) / 256), 256, 0, n, A, ld, shift);
   CHECK_LAUNCH(ctx);

@@ -19,9 +19,11 @@
 // Algorithmic HBM bytes per Arnoldi step j: passes * j * Bv (basis) + Bv (store v_{j+1}) + j * 8 (R column), Bv = 8 n.
 #include "common.cuh"
 #include <algorithm>
+#include <cstdlib>
 #include <math.h>
 
 namespace {
+constexpr int ENS_LS_BASIS_FULL = 100;  // internal GMRES stop code: the per-CTA basis slab is full (never leaves this file)
 constexpr int ET = 256;   // threads per CTA
 constexpr int NPT = 8;    // max rows per thread  -> n <= 2048 (N <= 32)
 
@@ -238,7 +240,8 @@ __global__ void __launch_bounds__(ET, 2) ens_newton_kernel(EnsParams P, const do
           int gs = 0;
           if (!(rn == rn) || isinf(rn) || !(hbis == hbis) || isinf(hbis)) gs = B200_LS_NONFINITE;
           else if (rn <= tol) gs = B200_LS_SOLVED;
-          else if (k >= P.itmax || k >= P.kcap) gs = B200_LS_MAXITERS;
+          else if (k >= P.itmax) gs = B200_LS_MAXITERS;
+          else if (k >= P.kcap) gs = ENS_LS_BASIS_FULL;  // basis slab exhausted before itmax: hand the trajectory to the general driver
           else if (hbis <= 1.8189894035458565e-12) gs = B200_LS_BREAKDOWN;
           st.gstatus = gs; st.rnorm = rn; st.inv_h = hbis > 0.0 ? 1.0 / hbis : 0.0;
         }
@@ -257,6 +260,7 @@ __global__ void __launch_bounds__(ET, 2) ens_newton_kernel(EnsParams P, const do
         }
         __syncthreads();
       }
+      if (gstatus == ENS_LS_BASIS_FULL) { retcode = B200I_ENS_RC_DEFERRED; force_stop = 1; break; }
       if (gstatus == B200_LS_NONFINITE) {  // linear solve failed with a current Jacobian (solve.jl:367-372)
         retcode = B200_RC_INTERNAL_LINSOLVE_FAILED;
         force_stop = 1;
@@ -347,6 +351,7 @@ __global__ void __launch_bounds__(ET, 2) ens_newton_kernel(EnsParams P, const do
       for (int r = threadIdx.x; r < n; r += ET) uom[r] = us[r];
     }
     if (threadIdx.x == 0) {
+      if (retcode == B200I_ENS_RC_DEFERRED) atomicAdd(counter + 1, 1);
       resid_inf[m] = objective;
       retcodes[m] = retcode;
       nsteps_out[m] = nsteps;
@@ -369,7 +374,7 @@ int32_t b200i_ens_batched_supported(int32_t N, const b200_newton_opts* o) {
 
 int32_t b200i_ens_batched_solve(b200_ctx* ctx, int32_t N, int32_t nprob, double alpha, const b200_newton_opts* o, const double* u0,
                                 const double* A, const double* B, double* u_out, double* resid_inf, int32_t* retcodes, int32_t* nsteps,
-                                int32_t* njvp, void** workspace, size_t* workspace_bytes) {
+                                int32_t* njvp, void** workspace, size_t* workspace_bytes, int32_t* n_deferred) {
   EnsParams P;
   memset(&P, 0, sizeof(P));
   P.N = N; P.n = 2 * N * N; P.nprob = nprob;
@@ -380,7 +385,11 @@ int32_t b200i_ens_batched_solve(b200_ctx* ctx, int32_t N, int32_t nprob, double 
   P.gm_atol = o->gmres.atol > 0 ? o->gmres.atol : P.abstol;
   P.gm_rtol = o->gmres.rtol > 0 ? o->gmres.rtol : reltol;
   P.itmax = o->gmres.itmax > 0 ? o->gmres.itmax : P.n;
-  P.kcap = std::min(P.n, 512);
+  // per-CTA basis slab: 512 columns unless B200_ENS_BASIS_COLUMNS says otherwise (memory knob: the slab is (kcap + 1) n doubles per
+  // resident CTA).  A trajectory that needs more columns than this is not truncated: it is redone by the general driver.
+  int slab_cols = 512;
+  if (const char* e = getenv("B200_ENS_BASIS_COLUMNS")) { const int v = atoi(e); if (v >= 2) slab_cols = v; }
+  P.kcap = std::min(std::min(P.n, P.itmax), slab_cols);
   P.passes = (o->gmres.orth == B200_ORTH_MGS) ? 1 : 2;  // MGS, or MGS applied twice (reorthogonalisation) for CGS2 / MGS2 requests
   P.term_mode = o->termination;
   P.forcing = o->forcing == B200_FORCING_EW2;
@@ -415,10 +424,15 @@ int32_t b200i_ens_batched_solve(b200_ctx* ctx, int32_t N, int32_t nprob, double 
       forcing[(size_t)i + (size_t)N * j] = (s <= r2) ? 5.0 : 0.0;
     }
   CUDA_TRY(ctx, cudaMemcpyAsync(d_forcing, forcing.data(), sizeof(double) * forcing.size(), cudaMemcpyHostToDevice, ctx->stream));
-  CUDA_TRY(ctx, cudaMemsetAsync(d_counter, 0, sizeof(int), ctx->stream));
+  CUDA_TRY(ctx, cudaMemsetAsync(d_counter, 0, 2 * sizeof(int), ctx->stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // `forcing` is a host temporary
   PLAUNCH(ctx, B200_KID_RESIDENT, 0.0, ens_newton_kernel, grid, ET, smem, P, u0, A, B, (const double*)d_forcing, u_out, resid_inf, retcodes, nsteps,
           njvp, ws, d_counter);
   CHECK_LAUNCH(ctx);
+  // trajectories whose Krylov basis outgrew the per-CTA slab (kcap < min(itmax, n)) come back marked B200I_ENS_RC_DEFERRED
+  int hits = 0;
+  CUDA_TRY(ctx, cudaMemcpyAsync(&hits, d_counter + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  *n_deferred = hits;
   return B200_OK;
 }

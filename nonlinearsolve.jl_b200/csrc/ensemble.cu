@@ -17,14 +17,15 @@
 int32_t b200i_ens_batched_supported(int32_t N, const b200_newton_opts* o);
 int32_t b200i_ens_batched_solve(b200_ctx* ctx, int32_t N, int32_t nprob, double alpha, const b200_newton_opts* o, const double* u0,
                                 const double* A, const double* B, double* u_out, double* resid_inf, int32_t* retcodes, int32_t* nsteps,
-                                int32_t* njvp, void** workspace, size_t* workspace_bytes);
+                                int32_t* njvp, void** workspace, size_t* workspace_bytes, int32_t* n_deferred);
 
 struct b200_ensemble {
   b200_ctx* ctx;
   int32_t N, nprob;
   double alpha;
   b200_newton_opts o;
-  b200_problem* prob;  // sequential engine
+  int32_t batched;     // the one-CTA-per-trajectory kernel covers this option set
+  b200_problem* prob;  // sequential engine (whole ensemble when !batched; deferred trajectories otherwise, created on first use)
   b200_newton* nw;
   void* workspace;     // batched engine
   size_t workspace_bytes;
@@ -69,7 +70,8 @@ int32_t b200_ens_create(b200_ctx* ctx, int32_t N, int32_t nprob_local, double al
   CUDA_TRY(ctx, cudaMalloc(&e->d_ns, sizeof(int32_t) * nprob_local));
   CUDA_TRY(ctx, cudaMalloc(&e->d_nj, sizeof(int32_t) * nprob_local));
   CUDA_TRY(ctx, cudaMalloc(&e->d_res, sizeof(double) * nprob_local));
-  if (!b200i_ens_batched_supported(N, &e->o)) {
+  e->batched = b200i_ens_batched_supported(N, &e->o);
+  if (!e->batched) {
     int32_t s = b200_problem_create_bruss2d(ctx, N, 3.4, 1.0, alpha, &e->prob);
     if (s == B200_OK) s = b200_newton_create(e->prob, &e->o, &e->nw);
     if (s != B200_OK) { b200_ens_destroy(e); return s; }
@@ -89,24 +91,45 @@ int32_t b200_ens_solve(b200_ensemble* e, const double* u0, const double* A, cons
   int32_t* d_rc = retcodes ? retcodes : e->d_rc;
   int32_t* d_ns = nsteps ? nsteps : e->d_ns;
   int32_t* d_nj = njvp ? njvp : e->d_nj;
-  if (!e->nw) {
-    B200_TRY(b200i_ens_batched_solve(ctx, e->N, K, e->alpha, &e->o, u0, A, B, u_out, d_res, d_rc, d_ns, d_nj, &e->workspace,
-                                     &e->workspace_bytes));
-  } else {
-    std::vector<double> hA(K), hB(K);
+  // one trajectory through the general driver (remake(prob; p = ...), reinit, solve): the route for option sets the batched
+  // kernel does not cover, and for trajectories whose Krylov basis outgrew the batched kernel's per-CTA slab
+  auto solve_one = [&](int32_t m, double Am, double Bm) -> int32_t {
+    B200_TRY(b200_problem_set_AB(e->prob, Am, Bm));
+    B200_TRY(b200_newton_reinit(e->nw, u0 + (int64_t)m * n));
+    b200_newton_result r;
+    B200_TRY(b200_newton_solve(e->nw, &r));
+    double* u;
+    B200_TRY(b200_newton_u(e->nw, &u));
+    CUDA_TRY(ctx, cudaMemcpyAsync(u_out + (int64_t)m * n, u, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+    LAUNCH(ctx, ens_store_kernel, 1, 1, 0, m, r.resid_inf, r.retcode, r.nsteps, r.njvp, d_res, d_rc, d_ns, d_nj);
+    CHECK_LAUNCH(ctx);
+    return B200_OK;
+  };
+  std::vector<double> hA, hB;
+  auto fetch_AB = [&]() -> int32_t {
+    hA.resize(K); hB.resize(K);
     B200_TRY(b200_memcpy_d2h(ctx, hA.data(), A, sizeof(double) * K));
     B200_TRY(b200_memcpy_d2h(ctx, hB.data(), B, sizeof(double) * K));
-    for (int32_t m = 0; m < K; ++m) {
-      B200_TRY(b200_problem_set_AB(e->prob, hA[m], hB[m]));  // remake(prob; p = ...)
-      B200_TRY(b200_newton_reinit(e->nw, u0 + (int64_t)m * n));
-      b200_newton_result r;
-      B200_TRY(b200_newton_solve(e->nw, &r));
-      double* u;
-      B200_TRY(b200_newton_u(e->nw, &u));
-      CUDA_TRY(ctx, cudaMemcpyAsync(u_out + (int64_t)m * n, u, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
-      LAUNCH(ctx, ens_store_kernel, 1, 1, 0, m, r.resid_inf, r.retcode, r.nsteps, r.njvp, d_res, d_rc, d_ns, d_nj);
+    return B200_OK;
+  };
+  if (e->batched) {
+    int32_t deferred = 0;
+    B200_TRY(b200i_ens_batched_solve(ctx, e->N, K, e->alpha, &e->o, u0, A, B, u_out, d_res, d_rc, d_ns, d_nj, &e->workspace,
+                                     &e->workspace_bytes, &deferred));
+    if (deferred > 0) {
+      if (!e->nw) {
+        B200_TRY(b200_problem_create_bruss2d(ctx, e->N, 3.4, 1.0, e->alpha, &e->prob));
+        B200_TRY(b200_newton_create(e->prob, &e->o, &e->nw));
+      }
+      std::vector<int32_t> hrc(K);
+      B200_TRY(b200_memcpy_d2h(ctx, hrc.data(), d_rc, sizeof(int32_t) * K));
+      B200_TRY(fetch_AB());
+      for (int32_t m = 0; m < K; ++m)
+        if (hrc[m] == B200I_ENS_RC_DEFERRED) B200_TRY(solve_one(m, hA[m], hB[m]));
     }
-    CHECK_LAUNCH(ctx);
+  } else {
+    B200_TRY(fetch_AB());
+    for (int32_t m = 0; m < K; ++m) B200_TRY(solve_one(m, hA[m], hB[m]));
   }
   if (result) {
     std::vector<double> hres(K);

@@ -362,14 +362,16 @@ __global__ void __launch_bounds__(GM_THREADS) residual_init_kernel(int64_t n, co
   if (threadIdx.x == 0) norm_partial[blockIdx.x] = acc;
 }
 
-// ---- generic operator kernels (b2/b3 plug-in points): CSC scatter SpMV and dense column-major GEMV
-__global__ void __launch_bounds__(GM_THREADS) csc_spmv_kernel(int64_t n, const int64_t* __restrict__ colptr, const int64_t* __restrict__ rowval,
-                                                               const double* __restrict__ nzval, int base, const double* __restrict__ x,
-                                                               double* __restrict__ y) {
-  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n) return;
-  const double xc = x[c];
-  for (int64_t p = colptr[c] - base; p < colptr[c + 1] - base; ++p) atomicAdd(&y[rowval[p] - base], nzval[p] * xc);
+// ---- generic operator kernels (b2/b3 plug-in points): CSC matrix through a row view (deterministic gather: the scatter form
+//      with atomicAdd it replaces summed in a run-dependent order) and dense column-major GEMV
+__global__ void __launch_bounds__(GM_THREADS) csc_rows_spmv_kernel(int64_t n, const int64_t* __restrict__ rowptr, const int64_t* __restrict__ col,
+                                                                    const int64_t* __restrict__ map, const double* __restrict__ nzval,
+                                                                    const double* __restrict__ x, double* __restrict__ y) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  double s = 0.0;
+  for (int64_t e = rowptr[r]; e < rowptr[r + 1]; ++e) s = fma(nzval[map[e]], x[col[e]], s);  // ascending column order
+  y[r] = s;
 }
 __global__ void __launch_bounds__(GM_THREADS) dense_gemv_kernel(int trans, int64_t m, int64_t n, const double* __restrict__ A, int64_t ld,
                                                                  const double* __restrict__ x, double* __restrict__ y) {
@@ -425,46 +427,44 @@ struct ResidentParams {
 // carries 32 data bits and a 32-bit epoch, and 64-bit stores are single transactions, so a reader that sees the expected
 // epoch in every word of an entry has the value — no fence, no atomic, no separate barrier, one L2 round trip.
 constexpr int LL_MAXG = 160;
-__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
-  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
-  unsigned done = 0, spins = 0;
-  while (!done) {
-    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(a), "r"(parity) : "memory");
-    if (++spins > (1u << 26)) break;
-  }
-}
-__device__ __forceinline__ void tma_bulk_load(void* smem_dst, const void* gsrc, unsigned bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)),
-               "l"(gsrc), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
-               : "memory");
-}
-
-// CTA 0, one thread: Hessenberg column -> packed R with the stored Givens rotations, new rotation, residual norm, status
-// (same recurrence as givens_kernel)
-__device__ __forceinline__ void resident_givens_tail(const ResidentParams& P, double hbis, double inv) {
+// CTA 0: Hessenberg column -> packed R with the stored Givens rotations, new rotation, residual norm, status (same recurrence
+// as givens_kernel).  The recurrence is serial in i, so one thread runs it — but on a shared-memory copy of the column and of the
+// stored rotations that the whole CTA stages first (and writes back afterwards): run straight on global memory every iteration
+// waits for an L2 round trip (the stores to R may alias the rotations, so the loads cannot be hoisted), ~0.3 us x k per step,
+// which was 7 % of the N = 100 solve.  `ws` = the stage buffers, free once the sweep is over (cap doubles).
+constexpr int R3T = 256;  // = R3_THREADS (declared below)
+__device__ __forceinline__ void resident_givens_tail(const ResidentParams& P, double hbis, double inv, double* ws, int cap, int tid) {
   const int k = P.k;
-      GmresState* st = P.st;
-    double* Rk = P.R + (int64_t)(k - 1) * k / 2;
-    if (P.hraw) {
-      double* hr = P.hraw + (int64_t)(k - 1) * (k + 2) / 2;
-      for (int i = 0; i < k; ++i) hr[i] = P.h[i];
-      hr[k] = hbis;
+  GmresState* st = P.st;
+  double* Rk = P.R + (int64_t)(k - 1) * k / 2;
+  double* hr = P.hraw ? P.hraw + (int64_t)(k - 1) * (k + 2) / 2 : nullptr;
+  const bool staged = 3 * k <= cap;
+  double *col, *cs, *sn;
+  if (staged) {
+    col = ws; cs = ws + k; sn = ws + 2 * k;
+    for (int i = tid; i < k; i += R3T) {
+      const double h = P.h[i];
+      col[i] = h; cs[i] = P.cs[i]; sn[i] = P.sn[i];
+      if (hr) hr[i] = h;
     }
-    for (int i = 0; i < k; ++i) Rk[i] = P.h[i];
+    __syncthreads();
+  } else {
+    col = Rk; cs = P.cs; sn = P.sn;
+    if (tid == 0) {
+      for (int i = 0; i < k; ++i) { const double h = P.h[i]; Rk[i] = h; if (hr) hr[i] = h; }
+    }
+  }
+  if (tid == 0) {
+    if (hr) hr[k] = hbis;
+    double x = col[0];
     for (int i = 0; i + 1 < k; ++i) {
-      const double rt = P.cs[i] * Rk[i] + P.sn[i] * Rk[i + 1];
-      Rk[i + 1] = P.sn[i] * Rk[i] - P.cs[i] * Rk[i + 1];
-      Rk[i] = rt;
+      const double nx = col[i + 1];
+      col[i] = cs[i] * x + sn[i] * nx;
+      x = sn[i] * x - cs[i] * nx;
     }
     double c, s_, rho;
-    sym_givens(Rk[k - 1], hbis, c, s_, rho);
-    P.cs[k - 1] = c; P.sn[k - 1] = s_; Rk[k - 1] = rho;
+    sym_givens(x, hbis, c, s_, rho);
+    P.cs[k - 1] = c; P.sn[k - 1] = s_; col[k - 1] = rho;
     const double zeta = s_ * P.z[k - 1];
     P.z[k - 1] = c * P.z[k - 1];
     P.z[k] = zeta;
@@ -479,6 +479,11 @@ __device__ __forceinline__ void resident_givens_tail(const ResidentParams& P, do
     else if (k >= st->kmax_cycle) status = -1;
     st->status = status;
   }
+  if (staged) {
+    __syncthreads();
+    for (int i = tid; i < k; i += R3T) Rk[i] = col[i];
+  }
+}
 
 // =====================================================================================================================
 // Three-stage, lag-1 organisation of the resident Arnoldi step (rows of one SM fit 54 per thread at 256 threads): the two
@@ -491,6 +496,7 @@ __device__ __forceinline__ void resident_givens_tail(const ResidentParams& P, do
 // via TMA bulk copies, 2: registers).  Exchange: replicated pull tables (16 replicas, 32-byte entries {a, c} with the epoch
 // in every 64-bit word), one entry per polling thread; four table buffers rotate.
 constexpr int R3_THREADS = 256;
+static_assert(R3T == R3_THREADS, "resident_givens_tail strides by the CTA size");
 constexpr int R3_RP = 27;            // row pairs per thread
 constexpr int R3_ROWS = 2 * R3_RP;   // 54 rows per thread -> at most 13824 rows (6912 cells) per CTA
 constexpr int R3_RPR = 24;           // pairs of the third stage held in registers; the last R3_RP - R3_RPR pairs of each thread
@@ -865,9 +871,9 @@ __global__ void __launch_bounds__(R3_THREADS, 1) resident3g_arnoldi_kernel(Resid
       *reinterpret_cast<double2*>(P.vnew + (int64_t)s * NC + c0 + (lr - s * ncell)) = o;
     }
   }
-  if (b == 0 && tid == 0) {
-    P.gsub[P.k] = (((gcf[0] + gcf[1]) + (gcf[2] + gcf[3])) + gcf[4]) * inv;  // <v_k, v_{k-1}> for every later Arnoldi step
-    resident_givens_tail(P, hbis, inv);
+  if (b == 0) {
+    if (tid == 0) P.gsub[P.k] = (((gcf[0] + gcf[1]) + (gcf[2] + gcf[3])) + gcf[4]) * inv;  // <v_k, v_{k-1}> for every later Arnoldi step
+    resident_givens_tail(P, hbis, inv, rsm, 4 * cpc, tid);
   }
 }
 }  // namespace
@@ -1013,9 +1019,8 @@ static int32_t linop_apply_unshifted(b200_linop* op, const double* x, double* y)
     case LINOP_PROBLEM:
       return op->jvp_mode == B200_JVP_FINITE_DIFF ? b200_jvp_fd(op->prob, op->u, x, y) : b200_jvp(op->prob, op->u, x, y);
     case LINOP_CSC: {
-      CUDA_TRY(ctx, cudaMemsetAsync(y, 0, sizeof(double) * op->n, ctx->stream));
-      LAUNCH(ctx, csc_spmv_kernel, (int)((op->n + GM_THREADS - 1) / GM_THREADS), GM_THREADS, 0, op->n, op->colptr, op->rowval, op->nzval,
-             op->index_base, x, y);
+      LAUNCH(ctx, csc_rows_spmv_kernel, (int)((op->n + GM_THREADS - 1) / GM_THREADS), GM_THREADS, 0, op->n, (const int64_t*)op->csr_rowptr,
+             (const int64_t*)op->csr_col, (const int64_t*)op->csr_map, op->nzval, x, y);
       CHECK_LAUNCH(ctx);
       return B200_OK;
     }
@@ -1062,9 +1067,40 @@ int32_t b200_linop_from_problem(b200_problem* prob, const double* u, int32_t jvp
 int32_t b200_linop_from_csc(b200_ctx* ctx, int64_t n, const int64_t* colptr, const int64_t* rowval, const double* nzval, int32_t base,
                             b200_linop** out) {
   B200_DEVICE_GUARD(ctx);
+  B200_REQUIRE(ctx, n > 0 && colptr && rowval && nzval && out, "linop_from_csc: bad arguments");
+  // row view of the pattern, built once on the host (index arrays only; the values stay where they are and may change)
+  std::vector<int64_t> cp(n + 1);
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpy(cp.data(), colptr, sizeof(int64_t) * (n + 1), cudaMemcpyDeviceToHost));
+  const int64_t nnz = cp[n] - base;
+  B200_REQUIRE(ctx, nnz >= 0, "linop_from_csc: colptr is not a CSC column pointer with this index_base");
+  std::vector<int64_t> rv((size_t)std::max<int64_t>(nnz, 1)), rowptr(n + 1, 0), ccol((size_t)std::max<int64_t>(nnz, 1)), cmap((size_t)std::max<int64_t>(nnz, 1));
+  if (nnz > 0) CUDA_TRY(ctx, cudaMemcpy(rv.data(), rowval, sizeof(int64_t) * nnz, cudaMemcpyDeviceToHost));
+  for (int64_t k = 0; k < nnz; ++k) {
+    const int64_t r = rv[k] - base;
+    if (r < 0 || r >= n) return ctx->fail(B200_ERR_INVALID, "linop_from_csc: row index out of range", __FILE__, __LINE__);
+    rowptr[r + 1]++;
+  }
+  for (int64_t r = 0; r < n; ++r) rowptr[r + 1] += rowptr[r];
+  {
+    std::vector<int64_t> fill(rowptr.begin(), rowptr.end() - 1);
+    for (int64_t c = 0; c < n; ++c)
+      for (int64_t k = cp[c] - base; k < cp[c + 1] - base; ++k) { const int64_t q = fill[rv[k] - base]++; ccol[q] = c; cmap[q] = k; }
+  }
   b200_linop* op = new b200_linop();
   memset(op, 0, sizeof(*op));
   op->ctx = ctx; op->kind = LINOP_CSC; op->n = n; op->colptr = colptr; op->rowval = rowval; op->nzval = nzval; op->index_base = base;
+  bool ok = cudaMalloc(&op->csr_rowptr, sizeof(int64_t) * (n + 1)) == cudaSuccess && cudaMalloc(&op->csr_col, sizeof(int64_t) * std::max<int64_t>(nnz, 1)) == cudaSuccess &&
+            cudaMalloc(&op->csr_map, sizeof(int64_t) * std::max<int64_t>(nnz, 1)) == cudaSuccess;
+  if (ok) ok = cudaMemcpy(op->csr_rowptr, rowptr.data(), sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice) == cudaSuccess &&
+               cudaMemcpy(op->csr_col, ccol.data(), sizeof(int64_t) * nnz, cudaMemcpyHostToDevice) == cudaSuccess &&
+               cudaMemcpy(op->csr_map, cmap.data(), sizeof(int64_t) * nnz, cudaMemcpyHostToDevice) == cudaSuccess;
+  if (!ok) {
+    cudaGetLastError();
+    cudaFree(op->csr_rowptr); cudaFree(op->csr_col); cudaFree(op->csr_map);
+    delete op;
+    return ctx->fail(B200_ERR_NOMEM, "linop_from_csc: cannot allocate the row view", __FILE__, __LINE__);
+  }
   *out = op;
   return B200_OK;
 }
@@ -1093,6 +1129,7 @@ int32_t b200_linop_destroy(b200_linop* op) {
   if (!op) return B200_OK;
   B200_DEVICE_GUARD(op->ctx);
   if (op->mg && op->owns_mg) b200i_mg_destroy(op->mg);
+  if (op->csr_rowptr) { cudaStreamSynchronize(op->ctx->stream); cudaFree(op->csr_rowptr); cudaFree(op->csr_col); cudaFree(op->csr_map); }
   delete op;
   return B200_OK;
 }

@@ -57,6 +57,7 @@ struct b200_newton {
   b200_sparse_lu* slu;  // LINSOLVE_SPARSE_LU: band factorisation of the assembled Jacobian
   // LevenbergMarquardt: J'J + lambda D'D (factored in place), the running diagonal D'D, velocity / acceleration, previous velocity
   double *lmA, *lm_dtd, *lm_v, *lm_a, *lm_vold, *lm_rhs;
+  int qn_since_du, qn_since_dfu, qn_nresets;  // Broyden: NoChangeInStateReset counters, resets so far
   double lm_lambda, lm_lambda_factor, lm_norm_v_old, lm_loss_old;
   // state
   TermCache tc;
@@ -200,8 +201,12 @@ int32_t b200_newton_create(b200_problem* prob, const b200_newton_opts* opts, b20
   B200_REQUIRE(ctx, opts->term_norm == B200_NORM_INF || opts->term_norm == B200_NORM_L2, "newton_create: unknown termination norm");
   B200_REQUIRE(ctx, opts->term_max_stalled_steps <= 128, "newton_create: term_max_stalled_steps must be <= 128");
   B200_REQUIRE(ctx, opts->descent == B200_DESCENT_NEWTON || (opts->descent == B200_DESCENT_PSEUDO_TRANSIENT && opts->globalization != B200_GLOBALIZATION_TRUST_REGION) ||
-                        (opts->descent == B200_DESCENT_LEVENBERG_MARQUARDT && opts->globalization == B200_GLOBALIZATION_NONE && opts->linsolve == B200_LINSOLVE_DENSE_LU),
-               "newton_create: descent must be Newton, PseudoTransient (without a trust region) or LevenbergMarquardt (dense concrete Jacobian, its own trust region)");
+                        (opts->descent == B200_DESCENT_LEVENBERG_MARQUARDT && opts->globalization == B200_GLOBALIZATION_NONE && opts->linsolve == B200_LINSOLVE_DENSE_LU) ||
+                        (opts->descent == B200_DESCENT_BROYDEN && opts->globalization == B200_GLOBALIZATION_NONE && prob->n <= 65535 &&
+                         (opts->qn_init_jacobian == B200_QN_INIT_IDENTITY || (opts->qn_init_jacobian == B200_QN_INIT_TRUE_JACOBIAN && opts->linsolve == B200_LINSOLVE_DENSE_LU)) &&
+                         (opts->qn_update_rule == B200_QN_UPDATE_GOOD_BROYDEN || opts->qn_update_rule == B200_QN_UPDATE_BAD_BROYDEN)),
+               "newton_create: descent must be Newton, PseudoTransient (without a trust region), LevenbergMarquardt (dense concrete Jacobian, its own trust region) or "
+               "Broyden (no globalisation, n <= 65535, init_jacobian = true_jacobian needs the dense LU)");
   B200_REQUIRE(ctx, opts->precond == B200_PRECOND_NONE ||
                         ((opts->linsolve == B200_LINSOLVE_GMRES || opts->linsolve == B200_LINSOLVE_SPARSE_GMRES) &&
                          (prob->kind == B200_PROB_BRUSS2D || prob->kind == B200_PROB_BRUSS3D)),
@@ -230,6 +235,10 @@ int32_t b200_newton_create(b200_problem* prob, const b200_newton_opts* opts, b20
   if (opts->descent == B200_DESCENT_LEVENBERG_MARQUARDT) {
     A(&nw->u_trial); A(&nw->fu_trial); A(&nw->Jdu); A(&nw->lm_dtd); A(&nw->lm_v); A(&nw->lm_a); A(&nw->lm_vold); A(&nw->lm_rhs);
     if (s == B200_OK && cudaMalloc(&nw->lmA, sizeof(double) * n * n) != cudaSuccess) { cudaGetLastError(); s = ctx->fail(B200_ERR_NOMEM, "LevenbergMarquardt: J'J does not fit in device memory", __FILE__, __LINE__); }
+  }
+  if (opts->descent == B200_DESCENT_BROYDEN) {  // the stored inverse and the update rule's / reset condition's vectors share the LM slots
+    A(&nw->lm_dtd); A(&nw->lm_v); A(&nw->lm_a); A(&nw->lm_vold); A(&nw->lm_rhs);
+    if (s == B200_OK && cudaMalloc(&nw->lmA, sizeof(double) * n * n) != cudaSuccess) { cudaGetLastError(); s = ctx->fail(B200_ERR_NOMEM, "Broyden: the stored inverse Jacobian (n x n) does not fit in device memory", __FILE__, __LINE__); }
   }
   if (s != B200_OK) { b200_newton_destroy(nw); return s; }
   memset(&nw->op, 0, sizeof(nw->op));
@@ -352,6 +361,12 @@ int32_t b200_newton_reinit(b200_newton* nw, const double* u0_dev) {
     nw->lm_norm_v_old = INFINITY;
     nw->lm_loss_old = INFINITY;
   }
+  if (o.descent == B200_DESCENT_BROYDEN) {  // BroydenUpdateRuleCache.dfu = copy(fu); NoChangeInStateResetCache.dfu = copy(fu); counters 0
+    B200_TRY(b200_copy(ctx, n, nw->fu, nw->lm_v));
+    B200_TRY(b200_copy(ctx, n, nw->fu, nw->lm_a));
+    B200_TRY(b200_fill(ctx, n, 0.0, nw->du));
+    nw->qn_since_du = nw->qn_since_dfu = nw->qn_nresets = 0;
+  }
   nw->op.shift = 0.0;
   nw->eta = o.ew_eta0;
   if (o.forcing == B200_FORCING_EW2) {
@@ -470,8 +485,131 @@ static int32_t lm_step(b200_newton* nw) {
   return B200_OK;
 }
 
+// One step of Broyden() (NonlinearSolveQuasiNewton/src/solve.jl:293-486, broyden.jl:124-144, reset_conditions.jl:52-88,
+// initialization.jl:78-105).  The stored inverse J^-1 (n x n, column-major) lives in HBM; a step is GEMV-shaped:
+//   du = -(J^-1 f)                               1 pass over J^-1
+//   J^-1 += ((du - J^-1 df) / denom) w'          good Broyden: w = J^-T du, denom = <du, J^-1 df>   -> 2 GEMV + 1 GER = 4 passes
+//                                                bad Broyden : w = df,      denom = ||df||^2        -> 1 GEMV + 1 GER = 3 passes
+// The host takes the scalar decisions (reset counters, max_resets, termination) from a handful of reductions.
+static int32_t broyden_init_inverse(b200_newton* nw) {
+  b200_ctx* ctx = nw->ctx;
+  const int64_t n = nw->n;
+  double* Jinv = nw->lmA;
+  if (nw->o.qn_init_jacobian == B200_QN_INIT_TRUE_JACOBIAN) {  // J^-1 = J \ I through the LU (Utils.linsolve_identity!!)
+    nw->res.njacs += 1;
+    B200_TRY(b200_dense_jac_fill(nw->prob, nw->u, nw->Jdense, n));
+    int32_t info = 0;
+    nw->res.nfactors += 1;
+    B200_TRY(b200_getrf(ctx, n, nw->Jdense, n, nw->ipiv, &info));
+    if (info != 0) { nw->retcode = B200_RC_INTERNAL_LINSOLVE_FAILED; nw->force_stop = 1; return B200_OK; }
+    B200_TRY(b200i_scaled_identity(ctx, n, Jinv, n, 1.0));
+    B200_TRY(b200_getrs(ctx, n, n, nw->Jdense, n, nw->ipiv, Jinv, n));
+    return B200_OK;
+  }
+  double alpha = nw->o.qn_alpha;
+  if (!(alpha > 0)) {  // Utils.initial_jacobian_scaling_alpha(nothing, u, fu, L2): 2 ||f|| / max(||u||, 1); 1 below ||f|| = 1e-5
+    double fn, un;
+    B200_TRY(h_nrm2(nw, nw->fu, &fn));
+    B200_TRY(h_nrm2(nw, nw->u, &un));
+    alpha = (fn < 1.0e-5) ? 1.0 : (2.0 * fn) / std::max(un, 1.0);
+  }
+  return b200i_scaled_identity(ctx, n, Jinv, n, 1.0 / alpha);
+}
+
+static int32_t broyden_count(b200_newton* nw, const double* x, const double* y, double tol, double* out) {
+  b200_ctx* ctx = nw->ctx;
+  B200_TRY(b200i_reduce_sum_dev(ctx, nw->n, x, y, y ? RED_COUNT_DIFF_LE : RED_COUNT_LE, ctx->d_scalars, tol));
+  B200_TRY(b200i_fetch_scalars(ctx, 1));
+  *out = ctx->h_scalars[0];
+  return B200_OK;
+}
+
+static int32_t broyden_step(b200_newton* nw) {
+  b200_ctx* ctx = nw->ctx;
+  const int64_t n = nw->n;
+  const b200_newton_opts& o = nw->o;
+  double *Jinv = nw->lmA, *dfu_rule = nw->lm_v, *dfu_reset = nw->lm_a, *Jd = nw->lm_vold, *w = nw->lm_rhs, *c = nw->lm_dtd;
+  const double tol = o.qn_reset_tolerance > 0 ? o.qn_reset_tolerance : 1.8189894035458565e-12;  // eps^(3/4)
+  const int max_resets = o.qn_max_resets > 0 ? o.qn_max_resets : 100;
+  int reset = 0;
+  if (nw->nsteps == 0) {
+    B200_TRY(broyden_init_inverse(nw));
+    if (nw->force_stop) return B200_OK;
+  } else {
+    // NoChangeInStateReset(nsteps = 3): ANY component of du (then of f - f_prev) at or below the tolerance counts as "no change"
+    double cnt;
+    B200_TRY(broyden_count(nw, nw->du, nullptr, tol, &cnt));
+    if (cnt > 0) {
+      if (++nw->qn_since_du >= 3) { nw->qn_since_du = nw->qn_since_dfu = 0; reset = 1; }
+    } else {
+      nw->qn_since_du = nw->qn_since_dfu = 0;
+    }
+    if (!reset) {
+      B200_TRY(broyden_count(nw, nw->fu, dfu_reset, tol, &cnt));
+      if (cnt > 0) {
+        if (++nw->qn_since_dfu >= 3) { nw->qn_since_dfu = nw->qn_since_du = 0; reset = 1; }
+      } else {
+        nw->qn_since_dfu = nw->qn_since_du = 0;
+      }
+      B200_TRY(b200_copy(ctx, n, nw->fu, dfu_reset));
+    }
+    if (reset) {
+      if (++nw->qn_nresets >= max_resets) { nw->retcode = B200_RC_CONVERGENCE_FAILURE; nw->force_stop = 1; return B200_OK; }
+      B200_TRY(broyden_init_inverse(nw));
+      if (nw->force_stop) return B200_OK;
+    }
+  }
+  // ---- NewtonDescent on the stored inverse: du = -(J^-1 f) ; u += du ; f = f(u)
+  B200_TRY(b200_gemv(ctx, 0, n, n, Jinv, n, nw->fu, nw->du));
+  B200_TRY(b200_scal(ctx, n, -1.0, nw->du));
+  CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_scalars, 0, sizeof(double) * 2, ctx->stream));
+  B200_TRY(b200i_axpy_norm(ctx, n, 1.0, nw->du, nw->u, ctx->d_scalars + 1));
+  B200_TRY(b200i_residual_norm(nw->prob, nw->u, nw->fu, ctx->d_scalars));
+  nw->res.nf += 1;
+  B200_TRY(b200i_fetch_scalars(ctx, 2));
+  const double objective = ctx->h_scalars[0], du_norm = sqrt(ctx->h_scalars[1]);
+  nw->fnorm_inf = objective;
+  nw->bytes += 8.0 * (double)n * (double)n;
+  bool new_best = false;
+  TermQuant tq;
+  B200_TRY(term_quantities(nw, nw->fu, nw->u, objective, &tq));
+  if (term_check(nw, tq, du_norm, &new_best)) { nw->retcode = nw->tc.retcode; nw->force_stop = 1; }
+  if (new_best && nw->best_u) CUDA_TRY(ctx, cudaMemcpyAsync(nw->best_u, nw->u, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+  if (o.store_trace) {
+    b200_trace_rec t;
+    memset(&t, 0, sizeof(t));
+    t.iter = nw->nsteps + 1; t.accepted = 1; t.fnorm_inf = objective; t.step_norm2 = du_norm; t.lin_status = reset;  // lin_status: J^-1 was re-initialised before this step
+    nw->trace.push_back(t);
+  }
+  if (nw->force_stop) return B200_OK;  // the reference skips the update once the step has stopped the solve
+  // ---- update rule
+  B200_TRY(b200_axpby(ctx, n, 1.0, nw->fu, -1.0, dfu_rule));             // dfu = fu - dfu
+  B200_TRY(b200_gemv(ctx, 0, n, n, Jinv, n, dfu_rule, Jd));              // J^-1 dfu
+  double denom;
+  const double* rmul;
+  if (o.qn_update_rule == B200_QN_UPDATE_GOOD_BROYDEN) {
+    B200_TRY(b200_gemv(ctx, 1, n, n, Jinv, n, nw->du, w));               // J^-T du
+    B200_TRY(h_dot(nw, nw->du, Jd, &denom));
+    rmul = w;
+  } else {
+    double nd;
+    B200_TRY(h_nrm2(nw, dfu_rule, &nd));
+    denom = nd * nd;
+    rmul = dfu_rule;
+  }
+  const double inv = 1.0 / (denom == 0.0 ? 1.0e-5 : denom);
+  B200_TRY(b200_copy(ctx, n, nw->du, c));
+  B200_TRY(b200_axpy(ctx, n, -1.0, Jd, c));
+  B200_TRY(b200_scal(ctx, n, inv, c));                                   // (du - J^-1 dfu) / denom
+  B200_TRY(b200i_ger(ctx, n, Jinv, n, c, rmul));                         // J^-1 += c rmul'
+  B200_TRY(b200_copy(ctx, n, nw->fu, dfu_rule));
+  nw->bytes += 8.0 * (double)n * (double)n * (o.qn_update_rule == B200_QN_UPDATE_GOOD_BROYDEN ? 4.0 : 3.0);
+  return B200_OK;
+}
+
 static int32_t newton_step_inner(b200_newton* nw) {
   if (nw->o.descent == B200_DESCENT_LEVENBERG_MARQUARDT) return lm_step(nw);
+  if (nw->o.descent == B200_DESCENT_BROYDEN) return broyden_step(nw);
   b200_ctx* ctx = nw->ctx;
   const int64_t n = nw->n;
   const b200_newton_opts& o = nw->o;

@@ -12,6 +12,7 @@
 #include "common.cuh"
 #include <math.h>
 #include <float.h>
+#include <algorithm>
 
 namespace {
 constexpr int PB_THREADS = 256;
@@ -23,12 +24,32 @@ struct BrussParams {
   double a, A, B;
 };
 
+// Point formulas shared by every Brusselator kernel of this file.  Written with explicit round-to-nearest intrinsics so that the
+// compiler's FMA contraction cannot differ from kernel to kernel: the fused residual+JVP kernel, the halo-tile kernels and the
+// 2D kernel (a z-independent 3D state) then agree bit for bit, which tests/test_gpu_fullsize.py asserts.
 __device__ __forceinline__ void bruss_react(double uc, double vc, double A, double& j00, double& j01, double& j10, double& j11) {
-  const double uv2 = 2.0 * uc * vc, uu = uc * uc;
-  j00 = uv2 - (A + 1.0);
+  const double uv2 = __dmul_rn(__dmul_rn(2.0, uc), vc), uu = __dmul_rn(uc, uc);
+  j00 = __dadd_rn(uv2, -(A + 1.0));
   j01 = uu;
-  j10 = A - uv2;
+  j10 = __dadd_rn(A, -uv2);
   j11 = -uu;
+}
+__device__ __forceinline__ double lap_plane(double im, double ip, double jp, double jm, double c) {
+  return __fma_rn(-4.0, c, __dadd_rn(__dadd_rn(__dadd_rn(im, ip), jp), jm));
+}
+__device__ __forceinline__ double lap_z(double kp, double km, double c) { return __fma_rn(-2.0, c, __dadd_rn(kp, km)); }  // exactly 0 for a z-independent state
+__device__ __forceinline__ void bruss_resid(const BrussParams& P, double lapu, double lapv, double uc, double vc, double fo, double& f0, double& f1) {
+  const double uuv = __dmul_rn(__dmul_rn(uc, uc), vc);
+  f0 = __dadd_rn(__fma_rn(-(P.A + 1.0), uc, __dadd_rn(__fma_rn(P.a, lapu, P.B), uuv)), fo);
+  f1 = __dadd_rn(__fma_rn(P.a, lapv, __dmul_rn(P.A, uc)), -uuv);
+}
+// (J v) at a cell from the Laplacians of the direction and the 2x2 reaction block; TRANSPOSE: J' w
+template <bool TRANSPOSE>
+__device__ __forceinline__ void bruss_tangent(const BrussParams& P, double lapd, double lape, double uc, double vc, double dc, double ec, double& o0, double& o1) {
+  double j00, j01, j10, j11;
+  bruss_react(uc, vc, P.A, j00, j01, j10, j11);
+  o0 = __fma_rn(TRANSPOSE ? j10 : j01, ec, __fma_rn(j00, dc, __dmul_rn(P.a, lapd)));
+  o1 = __fma_rn(j11, ec, __fma_rn(TRANSPOSE ? j01 : j10, dc, __dmul_rn(P.a, lape)));
 }
 
 // ---- 2D: one thread per cell.  n is small for every 2D configuration (N<=128 -> 256 KB), so the whole state is
@@ -50,28 +71,22 @@ __global__ void __launch_bounds__(PB_THREADS) bruss2d_kernel(BrussParams P, cons
     const int cim = im + N * j, cip = ip + N * j, cjp = i + N * jp, cjm = i + N * jm;
     const double uc = u[c], vc = u[c + NC];
     if (MODE & M_RESID) {
-      const double lapu = u[cim] + u[cip] + u[cjp] + u[cjm] - 4.0 * uc;
-      const double lapv = u[cim + NC] + u[cip + NC] + u[cjp + NC] + u[cjm + NC] - 4.0 * vc;
-      const double uuv = uc * uc * vc;
-      const double f0 = P.a * lapu + P.B + uuv - (P.A + 1.0) * uc + forcing[c];
-      const double f1 = P.a * lapv + P.A * uc - uuv;
+      const double lapu = lap_plane(u[cim], u[cip], u[cjp], u[cjm], uc);
+      const double lapv = lap_plane(u[cim + NC], u[cip + NC], u[cjp + NC], u[cjm + NC], vc);
+      double f0, f1;
+      bruss_resid(P, lapu, lapv, uc, vc, forcing[c], f0, f1);
       du[c] = f0;
       du[c + NC] = f1;
       if (MODE & M_NORM) nrm = fmax(abs_nf(f0), abs_nf(f1));
     }
     if (MODE & (M_JVP | M_VJP)) {
       const double dc = d[c], ec = d[c + NC];
-      const double lapd = d[cim] + d[cip] + d[cjp] + d[cjm] - 4.0 * dc;
-      const double lape = d[cim + NC] + d[cip + NC] + d[cjp + NC] + d[cjm + NC] - 4.0 * ec;
-      double j00, j01, j10, j11;
-      bruss_react(uc, vc, P.A, j00, j01, j10, j11);
-      if (MODE & M_JVP) {
-        Jd[c] = P.a * lapd + j00 * dc + j01 * ec;
-        Jd[c + NC] = P.a * lape + j10 * dc + j11 * ec;
-      } else {
-        Jd[c] = P.a * lapd + j00 * dc + j10 * ec;
-        Jd[c + NC] = P.a * lape + j01 * dc + j11 * ec;
-      }
+      const double lapd = lap_plane(d[cim], d[cip], d[cjp], d[cjm], dc);
+      const double lape = lap_plane(d[cim + NC], d[cip + NC], d[cjp + NC], d[cjm + NC], ec);
+      double o0, o1;
+      bruss_tangent<(MODE & M_VJP) != 0>(P, lapd, lape, uc, vc, dc, ec, o0, o1);
+      Jd[c] = o0;
+      Jd[c + NC] = o1;
     }
     if (MODE & M_FD) {  // (f(u + eps d) - f(u)) / eps evaluated in one pass over the shared neighbourhood
       const double eps = *eps_ptr;
@@ -120,28 +135,22 @@ __global__ void __launch_bounds__(PB_THREADS) bruss3d_kernel(BrussParams P, cons
     const int64_t ckm = c + ((k == 0) ? (int64_t)(N - 1) * N2 : -N2), ckp = c + ((k + 1 == N) ? -(int64_t)(N - 1) * N2 : N2);
     const double uc = u[c], vc = u[c + NC];
     if (MODE & M_RESID) {
-      const double lapu = (u[cim] + u[cip] + u[cjp] + u[cjm] - 4.0 * uc) + (u[ckp] + u[ckm] - 2.0 * uc);
-      const double lapv = (u[cim + NC] + u[cip + NC] + u[cjp + NC] + u[cjm + NC] - 4.0 * vc) + (u[ckp + NC] + u[ckm + NC] - 2.0 * vc);
-      const double uuv = uc * uc * vc;
-      const double f0 = P.a * lapu + P.B + uuv - (P.A + 1.0) * uc + forcing[r];
-      const double f1 = P.a * lapv + P.A * uc - uuv;
+      const double lapu = __dadd_rn(lap_plane(u[cim], u[cip], u[cjp], u[cjm], uc), lap_z(u[ckp], u[ckm], uc));
+      const double lapv = __dadd_rn(lap_plane(u[cim + NC], u[cip + NC], u[cjp + NC], u[cjm + NC], vc), lap_z(u[ckp + NC], u[ckm + NC], vc));
+      double f0, f1;
+      bruss_resid(P, lapu, lapv, uc, vc, forcing[r], f0, f1);
       du[c] = f0;
       du[c + NC] = f1;
       if (MODE & M_NORM) nrm = fmax(abs_nf(f0), abs_nf(f1));
     }
     if (MODE & (M_JVP | M_VJP)) {
       const double dc = d[c], ec = d[c + NC];
-      const double lapd = (d[cim] + d[cip] + d[cjp] + d[cjm] - 4.0 * dc) + (d[ckp] + d[ckm] - 2.0 * dc);
-      const double lape = (d[cim + NC] + d[cip + NC] + d[cjp + NC] + d[cjm + NC] - 4.0 * ec) + (d[ckp + NC] + d[ckm + NC] - 2.0 * ec);
-      double j00, j01, j10, j11;
-      bruss_react(uc, vc, P.A, j00, j01, j10, j11);
-      if (MODE & M_JVP) {
-        Jd[c] = P.a * lapd + j00 * dc + j01 * ec;
-        Jd[c + NC] = P.a * lape + j10 * dc + j11 * ec;
-      } else {
-        Jd[c] = P.a * lapd + j00 * dc + j10 * ec;
-        Jd[c + NC] = P.a * lape + j01 * dc + j11 * ec;
-      }
+      const double lapd = __dadd_rn(lap_plane(d[cim], d[cip], d[cjp], d[cjm], dc), lap_z(d[ckp], d[ckm], dc));
+      const double lape = __dadd_rn(lap_plane(d[cim + NC], d[cip + NC], d[cjp + NC], d[cjm + NC], ec), lap_z(d[ckp + NC], d[ckm + NC], ec));
+      double o0, o1;
+      bruss_tangent<(MODE & M_VJP) != 0>(P, lapd, lape, uc, vc, dc, ec, o0, o1);
+      Jd[c] = o0;
+      Jd[c + NC] = o1;
     }
     if (MODE & M_FD) {
       const double eps = *eps_ptr;
@@ -160,6 +169,155 @@ __global__ void __launch_bounds__(PB_THREADS) bruss3d_kernel(BrussParams P, cons
       const double g1 = P.a * lapvp + P.A * up - up * up * vp;
       Jd[c] = (g0 - f0) / eps;
       Jd[c + NC] = (g1 - f1) / eps;
+    }
+  }
+  if (MODE & M_NORM) {
+    nrm = block_max(nrm, red);
+    if (threadIdx.x == 0) atomic_max_nonneg(norm_out, nrm);
+  }
+}
+
+// ---- 3D, bandwidth-critical form (K1 / K2 of SURVEY.md §8a; north_star: shared-memory halo tile, 16-byte accesses along i,
+// fused norm).  At N = 100 a whole kernel moves 32-48 MB — 5-7 us at the HBM peak — so what decides the time is how many
+// bytes are in flight from the first microsecond on, not the arithmetic.  Organisation:
+//   * a plane (i, j) is N^2 contiguous doubles; the unit of work is a PLANE-CHUNK: TS_L = 2 * TS_THREADS consecutive flat plane
+//     positions of one k plane (a thread: two neighbouring cells, one 16-byte access; N even keeps a pair inside one row).
+//     The chunks * N plane-chunks are dealt out in contiguous runs to a ONE-WAVE grid (2 CTAs per SM), so every CTA marches
+//     over ~N * chunks / grid consecutive k planes of one chunk (two marches when its run crosses a chunk boundary);
+//   * a march reads each plane ONCE: planes k-1, k, k+1 of the field whose Laplacian is taken (+ a halo of N positions either
+//     side of the chunk, which carries the j -/+ 1 neighbours and both periodic wraps) sit in a shared-memory RING of R plane
+//     slots filled by TMA bulk copies (one elected thread, mbarrier per slot); R - 3 slots are always in flight ahead of the
+//     compute, so the copy engine streams while the CTA works, with no registers tied up by loads;
+//   * the field that enters through its centre value only (u in the JVP / VJP) rides in the same slot; the forcing plane of
+//     the residual is a per-thread constant;
+//   * outputs go straight to global memory as 16-byte stores; ||f||_inf is folded into the residual's epilogue.
+// HBM traffic: (m + 2) / m of the Laplacian field for a march of m planes (m ~ 6.8 at N = 100 on 296 CTAs: +29 % of ONE of
+// the two or three vectors, served from L2 for the most part since neighbouring CTAs read the same planes at the same time).
+constexpr int TS_THREADS = 256;
+constexpr int TS_L = 2 * TS_THREADS;
+constexpr int TS_MAXR = 8;        // ring slots (at most)
+constexpr int TS_MAXMARCH = 4;    // marches per CTA (a run crosses at most a few chunk boundaries)
+
+struct TsMarch { int chunk, ka, m, l0; };  // planes ka .. ka + m - 1 of `chunk`; its loads are l0 .. l0 + m + 1 (planes ka - 1 .. ka + m)
+
+template <int MODE>
+__global__ void __launch_bounds__(TS_THREADS, 2) bruss3d_ring_kernel(BrussParams P, int R, const double* __restrict__ u, const double* __restrict__ d,
+                                                                      const double* __restrict__ forcing, double* __restrict__ out,
+                                                                      double* __restrict__ norm_out) {
+  extern __shared__ __align__(16) double ts_sm[];
+  __shared__ uint64_t mbar[TS_MAXR];
+  __shared__ TsMarch march[TS_MAXMARCH];
+  __shared__ int nmarch_s, nload_s;
+  __shared__ double red[32];
+  constexpr bool HAS_Y = (MODE & (M_JVP | M_VJP)) != 0;
+  const int N = P.N, N2 = N * N, tid = threadIdx.x;
+  const int64_t NC = (int64_t)N2 * N;
+  const int xrow = TS_L + 2 * N;                       // doubles per species of the Laplacian field in a slot
+  const int slot_doubles = 2 * xrow + (HAS_Y ? 2 * TS_L : 0);
+  const double* __restrict__ X = (MODE & M_RESID) ? u : d;
+  const int chunks = (N2 + TS_L - 1) / TS_L;
+  if (tid == 0) {
+    const int64_t W = (int64_t)chunks * N;
+    int64_t w0 = W * blockIdx.x / gridDim.x;
+    const int64_t w1 = W * (blockIdx.x + 1) / gridDim.x;
+    int nm = 0, l = 0;
+    while (w0 < w1 && nm < TS_MAXMARCH) {
+      const int c = (int)(w0 / N), ka = (int)(w0 - (int64_t)c * N);
+      const int m = (int)min((int64_t)(N - ka), w1 - w0);
+      march[nm] = TsMarch{c, ka, m, l};
+      l += m + 2;
+      w0 += m;
+      ++nm;
+    }
+    nmarch_s = nm; nload_s = l;
+    for (int r = 0; r < R; ++r) mbar_init(&mbar[r], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int nmarch = nmarch_s, nload = nload_s;
+  // ---- producer (thread 0): load l = plane (ka - 1 + l - l0) of its march's chunk into slot l % R
+  auto issue = [&](int l) {
+    int mi = 0;
+    while (mi + 1 < nmarch && l >= march[mi + 1].l0) ++mi;
+    const TsMarch mc = march[mi];
+    int kk = mc.ka - 1 + (l - mc.l0);
+    kk = (kk < 0) ? kk + N : (kk >= N ? kk - N : kk);
+    const int p0 = mc.chunk * TS_L;
+    double* slot = ts_sm + (size_t)(l % R) * slot_doubles;
+    uint64_t* bar = &mbar[l % R];
+    // region [p0 - N, p0 + TS_L + N) of the plane, periodic in the flat plane index: at most one wrap (N2 >= TS_L + 2N)
+    int q0 = p0 - N;
+    if (q0 < 0) q0 += N2;
+    const int len = xrow;
+    const int first = min(len, N2 - q0), second = len - first;
+    const int ylen = HAS_Y ? min(TS_L, N2 - p0) : 0;
+    mbar_expect_tx(bar, (unsigned)(2 * len * 8 + 2 * ylen * 8));
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const double* src = X + s * NC + (int64_t)kk * N2;
+      tma_bulk_load(slot + s * xrow, src + q0, (unsigned)(first * 8), bar);
+      if (second > 0) tma_bulk_load(slot + s * xrow + first, src, (unsigned)(second * 8), bar);
+      if (HAS_Y) tma_bulk_load(slot + 2 * xrow + s * TS_L, u + s * NC + (int64_t)kk * N2 + p0, (unsigned)(ylen * 8), bar);
+    }
+  };
+  int next_load = 0;
+  if (tid == 0)
+    for (; next_load < min(nload, R); ++next_load) issue(next_load);
+  double nrm = 0.0;
+  for (int mi = 0; mi < nmarch; ++mi) {
+    const TsMarch mc = march[mi];
+    const int p = mc.chunk * TS_L + 2 * tid;
+    const bool valid = p < N2;
+    int i = 0;
+    double2 fo = {0.0, 0.0};
+    if (valid) {
+      const int j = p / N;
+      i = p - j * N;
+      if (MODE & M_RESID) fo = *reinterpret_cast<const double2*>(forcing + p);
+    }
+    for (int jj = 0; jj < mc.m; ++jj) {
+      const int l = mc.l0 + jj;  // loads l, l + 1, l + 2 = planes k - 1, k, k + 1
+      const int k = mc.ka + jj;
+      if (jj == 0) { mbar_wait(&mbar[l % R], (unsigned)((l / R) & 1)); mbar_wait(&mbar[(l + 1) % R], (unsigned)(((l + 1) / R) & 1)); }
+      mbar_wait(&mbar[(l + 2) % R], (unsigned)(((l + 2) / R) & 1));
+      if (valid) {
+        const double* sm_ = ts_sm + (size_t)(l % R) * slot_doubles;
+        const double* sc_ = ts_sm + (size_t)((l + 1) % R) * slot_doubles;
+        const double* sp_ = ts_sm + (size_t)((l + 2) % R) * slot_doubles;
+        double2 lap[2], xc[2];
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          const double* row = sc_ + s * xrow + N + 2 * tid;  // row[0], row[1]: this thread's cells
+          const double2 c2 = *reinterpret_cast<const double2*>(row);
+          const double2 km = *reinterpret_cast<const double2*>(sm_ + s * xrow + N + 2 * tid);
+          const double2 kp = *reinterpret_cast<const double2*>(sp_ + s * xrow + N + 2 * tid);
+          const double2 jm = *reinterpret_cast<const double2*>(row - N), jp = *reinterpret_cast<const double2*>(row + N);
+          const double left = (i == 0) ? row[N - 1] : row[-1];
+          const double right = (i + 2 == N) ? row[2 - N] : row[2];
+          lap[s].x = __dadd_rn(lap_plane(left, c2.y, jp.x, jm.x, c2.x), lap_z(kp.x, km.x, c2.x));
+          lap[s].y = __dadd_rn(lap_plane(c2.x, right, jp.y, jm.y, c2.y), lap_z(kp.y, km.y, c2.y));
+          xc[s] = c2;
+        }
+        double2 o0, o1;
+        if (MODE & M_RESID) {
+          bruss_resid(P, lap[0].x, lap[1].x, xc[0].x, xc[1].x, fo.x, o0.x, o1.x);
+          bruss_resid(P, lap[0].y, lap[1].y, xc[0].y, xc[1].y, fo.y, o0.y, o1.y);
+          if (MODE & M_NORM) nrm = fmax(nrm, fmax(fmax(abs_nf(o0.x), abs_nf(o0.y)), fmax(abs_nf(o1.x), abs_nf(o1.y))));
+        } else {
+          const double2 y0 = *reinterpret_cast<const double2*>(sc_ + 2 * xrow + 2 * tid);
+          const double2 y1 = *reinterpret_cast<const double2*>(sc_ + 2 * xrow + TS_L + 2 * tid);
+          bruss_tangent<(MODE & M_VJP) != 0>(P, lap[0].x, lap[1].x, y0.x, y1.x, xc[0].x, xc[1].x, o0.x, o1.x);
+          bruss_tangent<(MODE & M_VJP) != 0>(P, lap[0].y, lap[1].y, y0.y, y1.y, xc[0].y, xc[1].y, o0.y, o1.y);
+        }
+        const int64_t plane = (int64_t)k * N2;
+        *reinterpret_cast<double2*>(out + plane + p) = o0;
+        *reinterpret_cast<double2*>(out + NC + plane + p) = o1;
+      }
+      __syncthreads();  // every reader is done with load l (and, at the end of a march, with l + 1 and l + 2)
+      if (tid == 0) {
+        const int released = (jj + 1 == mc.m) ? l + 3 : l + 1;
+        for (; next_load < min(nload, released + R); ++next_load) issue(next_load);
+      }
     }
   }
   if (MODE & M_NORM) {
@@ -252,7 +410,25 @@ int32_t launch_bruss(b200_problem* p, const double* u, const double* d, double* 
   if (p->kind == B200_PROB_BRUSS2D) {
     PLAUNCH(ctx, kid, pbytes, (bruss2d_kernel<MODE>), grid_for((int64_t)p->N * p->N), PB_THREADS, 0, P, u, d, forcing, du, Jd, norm_out, eps);
   } else {
-    PLAUNCH(ctx, kid, pbytes, (bruss3d_kernel<MODE>), grid_for((int64_t)p->N * p->N * p->N), PB_THREADS, 0, P, u, d, forcing, du, Jd, norm_out, eps);
+    constexpr bool tiled = MODE == M_RESID || MODE == (M_RESID | M_NORM) || MODE == M_JVP || MODE == M_VJP;
+    const int N = p->N, N2 = N * N;
+    bool done = false;
+    if constexpr (tiled) if ((N % 2 == 0) && N2 >= TS_L + 2 * N) {
+      constexpr bool has_y = (MODE & (M_JVP | M_VJP)) != 0;
+      const size_t slot = sizeof(double) * (2 * (size_t)(TS_L + 2 * N) + (has_y ? 2 * TS_L : 0));
+      const int R = (int)std::min<size_t>(TS_MAXR, (size_t)(100 * 1024) / slot);  // two CTAs per SM share the 227 KB
+      const int chunks = (N2 + TS_L - 1) / TS_L;
+      const int64_t W = (int64_t)chunks * N;
+      // one wave, two CTAs per SM; every CTA gets a run of >= 2 planes and crosses at most TS_MAXMARCH - 1 chunk boundaries
+      const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(2 * (int64_t)ctx->sm_count, W / 2));
+      if (R >= 4 && (W + grid - 1) / grid <= (int64_t)(TS_MAXMARCH - 1) * N) {
+        const size_t smem = slot * R;
+        CUDA_TRY(ctx, cudaFuncSetAttribute(bruss3d_ring_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PLAUNCH(ctx, kid, pbytes, (bruss3d_ring_kernel<MODE>), grid, TS_THREADS, smem, P, R, u, d, forcing, (MODE & M_RESID) ? du : Jd, norm_out);
+        done = true;
+      }
+    }
+    if (!done) PLAUNCH(ctx, kid, pbytes, (bruss3d_kernel<MODE>), grid_for((int64_t)p->N * p->N * p->N), PB_THREADS, 0, P, u, d, forcing, du, Jd, norm_out, eps);
   }
   CHECK_LAUNCH(ctx);
   return B200_OK;

@@ -470,6 +470,7 @@ void orc_gmres(const orc_linop* op, const double* b, double* x, const b200_gmres
       double zeta = sn[k - 1] * z[k - 1];
       z[k - 1] = cs[k - 1] * z[k - 1];
       rNorm = fabs(zeta);
+      if ((k % 200) == 0 && getenv("ORC_PROGRESS")) fprintf(stderr, "[oracle]   gmres k %d rnorm %.6e (tol %.6e)\n", (int)k, rNorm, eps_tol);
       nr += k;
       nonfinite = !(rNorm == rNorm) || isinf(rNorm) || !(Hbis == Hbis);
       solved = rNorm <= eps_tol;
@@ -906,6 +907,7 @@ void orc_newton_solve(const orc_problem* p, const double* u0, const b200_newton_
       v_copy(n, du, xlin);
       orc_gmres(&op, fu, xlin, &gopts, &gs, NULL, 0);
       res->njvp += gs.nmatvec;
+      if (getenv("ORC_PROGRESS")) fprintf(stderr, "[oracle] newton step %d: gmres status %d iters %d rnorm %.6e tol %.6e\n", (int)nsteps, (int)gs.status, (int)gs.iters, gs.rnorm, gs.tol);
       if (gs.status == B200_LS_NONFINITE || gs.status == B200_LS_OUT_OF_MEMORY) lin_success = 0; /* retcode Failure */
     }
     if (!lin_success) { /* solve.jl:367-382 */

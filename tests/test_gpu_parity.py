@@ -53,14 +53,16 @@ def test_vector_ops(nls, ctx):
         nls.abi.check(ctx.handle, nls.abi.lib().b200_extrema(ctx.handle, n, dx.ptr, C.byref(mn), C.byref(mx)))
         assert (mn.value, mx.value) == (x.min(), x.max())
         eq = C.c_int32()
-        nls.abi.check(ctx.handle, nls.abi.lib().b200_equal(ctx.handle, n, dx.ptr, dx.copy().ptr, C.byref(eq)))
+        dx2 = dx.copy()  # held in a name: a temporary would be freed before the call reads it
+        nls.abi.check(ctx.handle, nls.abi.lib().b200_equal(ctx.handle, n, dx.ptr, dx2.ptr, C.byref(eq)))
         assert eq.value == 1
     xn = np.array([1.0, np.nan, 3.0])
     assert not np.isfinite(ctx.to_device(xn).norm(np.inf))  # non-finite propagates (termination_conditions.jl:256)
 
 
 # ----------------------------------------------------------------------------- residual / JVP / VJP (a1, a2)
-@pytest.mark.parametrize("kind,N", [("bruss2d", 8), ("bruss2d", 32), ("bruss2d", 33), ("bruss3d", 6), ("bruss3d", 16), ("bruss3d", 19)])
+@pytest.mark.parametrize("kind,N", [("bruss2d", 8), ("bruss2d", 32), ("bruss2d", 33), ("bruss3d", 6), ("bruss3d", 16), ("bruss3d", 19),
+                                     ("bruss3d", 24), ("bruss3d", 26), ("bruss3d", 50)])  # N >= 24, even: the halo-tile kernels (26: ragged last chunk)
 def test_residual_jvp_vjp(nls, ctx, po, kind, N):
     dp, P, _ = make(nls, ctx, po, kind, N=N)
     rng = np.random.default_rng(N)
@@ -138,10 +140,22 @@ def test_gmres_vs_oracle(nls, ctx, po, orth):
     assert abs(st.iters - so.iters) <= 1  # reduction order may move the stopping test by one step at the margin
     assert abs(st.rnorm0 - so.rnorm0) <= 1e-12 * so.rnorm0
     assert close(x.to_host(), xo, 1e-7)
-    k = min(st.iters, so.iters, 40)  # early Hessenberg columns agree tightly; later ones drift with rounding
-    cnt = k * (k + 3) // 2
+    # EVERY Hessenberg column both runs produced, column by column (k + 1 entries each, relative to the column's largest
+    # entry): the first 40 to 1e-8, all but the last six to 1e-6.  The last columns of a solve driven to rtol 1e-10 are built
+    # from vectors whose norm before normalisation is ~1e-7 of the operator's scale — rounding differences between two
+    # reduction orders are amplified by that factor there (measured: 1e-8 six columns before the end, 1e-5 .. 1e-4 in the
+    # last one), so they get 1e-3
+    k = min(st.iters, so.iters)
     hg = gm.hessenberg(st.iters)
-    assert np.abs(hg[:cnt] - ho[:cnt]).max() <= 1e-8 * np.abs(ho[:cnt]).max()
+    off, dev = 0, []
+    for j in range(1, k + 1):
+        sl = slice(off, off + j + 1)
+        off += j + 1
+        dev.append(np.abs(hg[sl] - ho[sl]).max() / np.abs(ho[sl]).max())
+    dev = np.array(dev)
+    assert dev[:40].max() <= 1e-8, dev[:40].max()
+    assert dev[:k - 6].max() <= 1e-6, (dev[:k - 6].max(), int(dev[:k - 6].argmax()))
+    assert dev.max() <= 1e-3, (dev.max(), int(dev.argmax()))
     # true residual honours the tolerance
     r = b - P.jvp(u, x.to_host())
     assert np.linalg.norm(r) <= 1.05 * (1e-10 + 1e-10 * st.rnorm0) + 1e-9 * st.rnorm0
@@ -398,8 +412,8 @@ def test_ensemble_batched_vs_oracle(nls, ctx, po, N, K, orth):
     assert np.array_equal(cache.rc.to_host(), rco) and np.array_equal(cache.ns.to_host(), nso)
     assert np.abs(u - uo).max() <= RTOL_ROOT * np.abs(uo).max()
     assert cache.resid.to_host().max() < 1e-8
-    # iteration counts: same algorithm family, reduction order differs -> within a few Arnoldi steps per solve
-    assert np.abs(cache.nj.to_host() - njo).max() <= 6 * nso.max()
+    # iteration counts: same algorithm, reduction order differs -> each linear solve may stop at most 2 Arnoldi steps apart
+    assert np.all(np.abs(cache.nj.to_host() - njo) <= 2 * nso), np.abs(cache.nj.to_host() - njo).max()
     # residual reported == residual of the returned iterate
     m = K // 2
     Pm = po.OracleProblem.bruss2d(N, A=A[m], B=B[m])

@@ -193,3 +193,29 @@ def test_singular_lu_is_rescued_by_pivoted_qr(nls, ctx):
     u = _h(sol.u)
     keep = np.arange(n) != 7
     assert np.abs(u[keep] - np.sqrt(2.0)).max() < 1e-12 and u[7] == 0.0
+
+
+def test_ensemble_trajectories_that_outgrow_the_basis_slab_are_not_truncated(nls, ctx, po, monkeypatch):
+    """the batched ensemble kernel keeps a fixed number of Krylov columns per CTA.  A trajectory whose linear
+    solve needs more is redone by the general Newton driver (same algorithm, growing basis) instead of stopping GMRES early: with
+    the slab shrunk to 24 columns every trajectory takes that route and the results still match the per-trajectory oracle."""
+    import bench
+    N, K = 16, 12
+    P = po.OracleProblem.bruss2d(N)
+    A, B = bench.ensemble_params(K)
+    u0 = np.tile(P.u0(), (K, 1)) * (1.0 + 0.01 * np.arange(K))[:, None]
+    alg = nls.NewtonRaphson(linsolve=nls.KrylovJL_GMRES(orth="mgs"))
+    uo, ro, rco, nso, njo, reso = po.ensemble_solve(N, u0, A, B, opts=po.default_newton_opts(abstol=1e-8, gmres_orth=po.ORTH_MGS))
+    assert njo.max() / nso.max() > 24          # the linear solves do need more than 24 columns
+    full = nls.EnsembleCache(ctx, N, K, 10.0, alg, abstol=1e-8)
+    rf = full.solve(ctx.to_device(u0.ravel()), ctx.to_device(A), ctx.to_device(B))
+    monkeypatch.setenv("B200_ENS_BASIS_COLUMNS", "24")
+    small = nls.EnsembleCache(ctx, N, K, 10.0, alg, abstol=1e-8)
+    rs = small.solve(ctx.to_device(u0.ravel()), ctx.to_device(A), ctx.to_device(B))
+    monkeypatch.delenv("B200_ENS_BASIS_COLUMNS")
+    assert rs.nsuccess == rf.nsuccess == K == reso.nsuccess
+    assert np.array_equal(small.rc.to_host(), rco) and np.array_equal(small.ns.to_host(), nso)
+    us = small.u_out.to_host().reshape(K, -1)
+    assert np.abs(us - uo).max() <= 1e-6 * np.abs(uo).max()
+    assert np.all(np.abs(small.nj.to_host() - njo) <= 2 * nso)
+    assert small.resid.to_host().max() < 1e-8

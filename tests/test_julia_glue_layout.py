@@ -162,6 +162,8 @@ def test_enum_tables_match_the_header():
     assert table("_TR_SCHEMES") == _c_enum("B200_TR_")
     assert table("_PRECS") == _c_enum("B200_PRECOND_")
     assert table("_TERMINATION") == _c_enum("B200_TERM_")
+    assert table("_QN_INIT") == _c_enum("B200_QN_INIT_")
+    assert table("_QN_UPDATE") == _c_enum("B200_QN_UPDATE_")
     # retcode tuple: one entry per B200_RC_* value, in order
     rc = _c_enum("B200_RC_")
     names = re.search(r"const RETCODES = \((.*?)\)\n", JL, re.S).group(1)

@@ -60,7 +60,7 @@ def test_gpu_radius_schemes_vs_oracle(nls, ctx, po, scheme):
         for tg, t in zip(sol.trace, tro):
             assert tg.accepted == t.accepted
             # Fan / Yuan radii are proportional to ||f(u_trial)|| resp. ||J' f(u_trial)||: rounding-level at convergence -> absolute floor
-            assert abs(tg.trust_radius - t.trust_radius) <= 1e-6 * t.trust_radius + 1e-8
+            assert abs(tg.trust_radius - t.trust_radius) <= 1e-6 * t.trust_radius + 1e-7
     # the reference's anchor on the device
     s2 = nls.solve(nls.NonlinearProblem(nls.QuadraticFunction(1000), np.ones(1000), 2.0, ctx=ctx),
                    nls.TrustRegion(linsolve=nls.KrylovJL_GMRES(), radius_update_scheme=code), abstol=1e-9)
