@@ -24,6 +24,7 @@ struct b200_ctx {
   size_t l2_flush_bytes = 0;
   cudaStream_t aux_stream = nullptr;  // look-ahead panel factorisation of the dense LU
   cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+  unsigned long long* d_lu_xchg = nullptr;  // dense LU panel: flag-in-word exchange tables (dense.cu PX_WORDS)
   // optional per-kernel-family event timing (b200_ctx_profile_*)
   bool prof_on = false;
   struct ProfSlot { double ms = 0, bytes = 0; int64_t launches = 0; } prof[B200_KID_COUNT];
@@ -161,6 +162,9 @@ struct b200_mg;
 //      16-byte aligned) that completes on an mbarrier; waits are bounded so a fault cannot hang the GPU
 __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");

@@ -111,6 +111,7 @@ int32_t b200_ctx_destroy(b200_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->d_partials) cudaFree(ctx->d_partials);
+  if (ctx->d_lu_xchg) cudaFree(ctx->d_lu_xchg);
   if (ctx->d_scalars) cudaFree(ctx->d_scalars);
   if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
   if (ctx->l2_flush) cudaFree(ctx->l2_flush);

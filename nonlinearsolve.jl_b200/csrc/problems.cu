@@ -186,8 +186,9 @@ __global__ void __launch_bounds__(PB_THREADS) bruss3d_kernel(BrussParams P, cons
 //     over ~N * chunks / grid consecutive k planes of one chunk (two marches when its run crosses a chunk boundary);
 //   * a march reads each plane ONCE: planes k-1, k, k+1 of the field whose Laplacian is taken (+ a halo of N positions either
 //     side of the chunk, which carries the j -/+ 1 neighbours and both periodic wraps) sit in a shared-memory RING of R plane
-//     slots filled by TMA bulk copies (one elected thread, mbarrier per slot); R - 3 slots are always in flight ahead of the
-//     compute, so the copy engine streams while the CTA works, with no registers tied up by loads;
+//     slots filled by TMA bulk copies.  A dedicated PRODUCER warp issues them (full / empty mbarrier pair per slot); the eight
+//     consumer warps never meet at a CTA-wide barrier: each waits for the newest plane, computes, and releases the oldest slot.
+//     R - 3 slots are always in flight ahead of the compute, with no registers tied up by loads;
 //   * the field that enters through its centre value only (u in the JVP / VJP) rides in the same slot; the forcing plane of
 //     the residual is a per-thread constant;
 //   * outputs go straight to global memory as 16-byte stores; ||f||_inf is folded into the residual's epilogue.
@@ -200,12 +201,13 @@ constexpr int TS_MAXMARCH = 4;    // marches per CTA (a run crosses at most a fe
 
 struct TsMarch { int chunk, ka, m, l0; };  // planes ka .. ka + m - 1 of `chunk`; its loads are l0 .. l0 + m + 1 (planes ka - 1 .. ka + m)
 
+constexpr int TS_CWARPS = TS_THREADS / 32;  // consumer warps; one more warp is the producer
 template <int MODE>
-__global__ void __launch_bounds__(TS_THREADS, 2) bruss3d_ring_kernel(BrussParams P, int R, const double* __restrict__ u, const double* __restrict__ d,
-                                                                      const double* __restrict__ forcing, double* __restrict__ out,
-                                                                      double* __restrict__ norm_out) {
+__global__ void __launch_bounds__(TS_THREADS + 32, 2) bruss3d_ring_kernel(BrussParams P, int R, const double* __restrict__ u, const double* __restrict__ d,
+                                                                           const double* __restrict__ forcing, double* __restrict__ out,
+                                                                           double* __restrict__ norm_out) {
   extern __shared__ __align__(16) double ts_sm[];
-  __shared__ uint64_t mbar[TS_MAXR];
+  __shared__ uint64_t full[TS_MAXR], empty[TS_MAXR];   // full: the slot's copies have landed; empty: every consumer warp has read it
   __shared__ TsMarch march[TS_MAXMARCH];
   __shared__ int nmarch_s, nload_s;
   __shared__ double red[32];
@@ -216,7 +218,7 @@ __global__ void __launch_bounds__(TS_THREADS, 2) bruss3d_ring_kernel(BrussParams
   const int slot_doubles = 2 * xrow + (HAS_Y ? 2 * TS_L : 0);
   const double* __restrict__ X = (MODE & M_RESID) ? u : d;
   const int chunks = (N2 + TS_L - 1) / TS_L;
-  if (tid == 0) {
+  if (tid == TS_THREADS) {
     const int64_t W = (int64_t)chunks * N;
     int64_t w0 = W * blockIdx.x / gridDim.x;
     const int64_t w1 = W * (blockIdx.x + 1) / gridDim.x;
@@ -230,93 +232,111 @@ __global__ void __launch_bounds__(TS_THREADS, 2) bruss3d_ring_kernel(BrussParams
       ++nm;
     }
     nmarch_s = nm; nload_s = l;
-    for (int r = 0; r < R; ++r) mbar_init(&mbar[r], 1);
+    for (int r = 0; r < R; ++r) { mbar_init(&full[r], 1); mbar_init(&empty[r], TS_CWARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
   const int nmarch = nmarch_s, nload = nload_s;
-  // ---- producer (thread 0): load l = plane (ka - 1 + l - l0) of its march's chunk into slot l % R
-  auto issue = [&](int l) {
-    int mi = 0;
-    while (mi + 1 < nmarch && l >= march[mi + 1].l0) ++mi;
-    const TsMarch mc = march[mi];
-    int kk = mc.ka - 1 + (l - mc.l0);
-    kk = (kk < 0) ? kk + N : (kk >= N ? kk - N : kk);
-    const int p0 = mc.chunk * TS_L;
-    double* slot = ts_sm + (size_t)(l % R) * slot_doubles;
-    uint64_t* bar = &mbar[l % R];
-    // region [p0 - N, p0 + TS_L + N) of the plane, periodic in the flat plane index: at most one wrap (N2 >= TS_L + 2N)
-    int q0 = p0 - N;
-    if (q0 < 0) q0 += N2;
-    const int len = xrow;
-    const int first = min(len, N2 - q0), second = len - first;
-    const int ylen = HAS_Y ? min(TS_L, N2 - p0) : 0;
-    mbar_expect_tx(bar, (unsigned)(2 * len * 8 + 2 * ylen * 8));
-#pragma unroll
-    for (int s = 0; s < 2; ++s) {
-      const double* src = X + s * NC + (int64_t)kk * N2;
-      tma_bulk_load(slot + s * xrow, src + q0, (unsigned)(first * 8), bar);
-      if (second > 0) tma_bulk_load(slot + s * xrow + first, src, (unsigned)(second * 8), bar);
-      if (HAS_Y) tma_bulk_load(slot + 2 * xrow + s * TS_L, u + s * NC + (int64_t)kk * N2 + p0, (unsigned)(ylen * 8), bar);
-    }
-  };
-  int next_load = 0;
-  if (tid == 0)
-    for (; next_load < min(nload, R); ++next_load) issue(next_load);
   double nrm = 0.0;
-  for (int mi = 0; mi < nmarch; ++mi) {
-    const TsMarch mc = march[mi];
-    const int p = mc.chunk * TS_L + 2 * tid;
-    const bool valid = p < N2;
-    int i = 0;
-    double2 fo = {0.0, 0.0};
-    if (valid) {
-      const int j = p / N;
-      i = p - j * N;
-      if (MODE & M_RESID) fo = *reinterpret_cast<const double2*>(forcing + p);
-    }
-    for (int jj = 0; jj < mc.m; ++jj) {
-      const int l = mc.l0 + jj;  // loads l, l + 1, l + 2 = planes k - 1, k, k + 1
-      const int k = mc.ka + jj;
-      if (jj == 0) { mbar_wait(&mbar[l % R], (unsigned)((l / R) & 1)); mbar_wait(&mbar[(l + 1) % R], (unsigned)(((l + 1) / R) & 1)); }
-      mbar_wait(&mbar[(l + 2) % R], (unsigned)(((l + 2) / R) & 1));
-      if (valid) {
-        const double* sm_ = ts_sm + (size_t)(l % R) * slot_doubles;
-        const double* sc_ = ts_sm + (size_t)((l + 1) % R) * slot_doubles;
-        const double* sp_ = ts_sm + (size_t)((l + 2) % R) * slot_doubles;
-        double2 lap[2], xc[2];
+  if (tid >= TS_THREADS) {
+    // ---- producer warp (one lane): load l = plane (ka - 1 + l - l0) of its march's chunk into slot l mod R, as soon as the
+    //      consumers have released the slot's previous occupant
+    if (tid == TS_THREADS) {
+      int slot_i = 0, round = 0, mi = 0;
+      for (int l = 0; l < nload; ++l) {
+        if (round > 0) mbar_wait(&empty[slot_i], (unsigned)((round - 1) & 1));
+        while (mi + 1 < nmarch && l >= march[mi + 1].l0) ++mi;
+        const TsMarch mc = march[mi];
+        int kk = mc.ka - 1 + (l - mc.l0);
+        kk = (kk < 0) ? kk + N : (kk >= N ? kk - N : kk);
+        const int p0 = mc.chunk * TS_L;
+        double* slot = ts_sm + (size_t)slot_i * slot_doubles;
+        uint64_t* bar = &full[slot_i];
+        // region [p0 - N, p0 + TS_L + N) of the plane, periodic in the flat plane index: at most one wrap (N2 >= TS_L + 2N)
+        int q0 = p0 - N;
+        if (q0 < 0) q0 += N2;
+        const int first = min(xrow, N2 - q0), second = xrow - first;
+        const int ylen = HAS_Y ? min(TS_L, N2 - p0) : 0;
+        mbar_expect_tx(bar, (unsigned)(2 * xrow * 8 + 2 * ylen * 8));
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
-          const double* row = sc_ + s * xrow + N + 2 * tid;  // row[0], row[1]: this thread's cells
-          const double2 c2 = *reinterpret_cast<const double2*>(row);
-          const double2 km = *reinterpret_cast<const double2*>(sm_ + s * xrow + N + 2 * tid);
-          const double2 kp = *reinterpret_cast<const double2*>(sp_ + s * xrow + N + 2 * tid);
-          const double2 jm = *reinterpret_cast<const double2*>(row - N), jp = *reinterpret_cast<const double2*>(row + N);
-          const double left = (i == 0) ? row[N - 1] : row[-1];
-          const double right = (i + 2 == N) ? row[2 - N] : row[2];
-          lap[s].x = __dadd_rn(lap_plane(left, c2.y, jp.x, jm.x, c2.x), lap_z(kp.x, km.x, c2.x));
-          lap[s].y = __dadd_rn(lap_plane(c2.x, right, jp.y, jm.y, c2.y), lap_z(kp.y, km.y, c2.y));
-          xc[s] = c2;
+          const double* src = X + s * NC + (int64_t)kk * N2;
+          tma_bulk_load(slot + s * xrow, src + q0, (unsigned)(first * 8), bar);
+          if (second > 0) tma_bulk_load(slot + s * xrow + first, src, (unsigned)(second * 8), bar);
+          if (HAS_Y) tma_bulk_load(slot + 2 * xrow + s * TS_L, u + s * NC + (int64_t)kk * N2 + p0, (unsigned)(ylen * 8), bar);
         }
-        double2 o0, o1;
-        if (MODE & M_RESID) {
-          bruss_resid(P, lap[0].x, lap[1].x, xc[0].x, xc[1].x, fo.x, o0.x, o1.x);
-          bruss_resid(P, lap[0].y, lap[1].y, xc[0].y, xc[1].y, fo.y, o0.y, o1.y);
-          if (MODE & M_NORM) nrm = fmax(nrm, fmax(fmax(abs_nf(o0.x), abs_nf(o0.y)), fmax(abs_nf(o1.x), abs_nf(o1.y))));
-        } else {
-          const double2 y0 = *reinterpret_cast<const double2*>(sc_ + 2 * xrow + 2 * tid);
-          const double2 y1 = *reinterpret_cast<const double2*>(sc_ + 2 * xrow + TS_L + 2 * tid);
-          bruss_tangent<(MODE & M_VJP) != 0>(P, lap[0].x, lap[1].x, y0.x, y1.x, xc[0].x, xc[1].x, o0.x, o1.x);
-          bruss_tangent<(MODE & M_VJP) != 0>(P, lap[0].y, lap[1].y, y0.y, y1.y, xc[0].y, xc[1].y, o0.y, o1.y);
-        }
-        const int64_t plane = (int64_t)k * N2;
-        *reinterpret_cast<double2*>(out + plane + p) = o0;
-        *reinterpret_cast<double2*>(out + NC + plane + p) = o1;
+        if (++slot_i == R) { slot_i = 0; ++round; }
       }
-      __syncthreads();  // every reader is done with load l (and, at the end of a march, with l + 1 and l + 2)
-      if (tid == 0) {
-        const int released = (jj + 1 == mc.m) ? l + 3 : l + 1;
-        for (; next_load < min(nload, released + R); ++next_load) issue(next_load);
+    }
+  } else {
+    // ---- consumer warps: no CTA-wide barrier in the march — a warp waits for the newest plane, computes, and hands the oldest
+    //      slot back to the producer
+    const int lane = tid & 31;
+    for (int mi = 0; mi < nmarch; ++mi) {
+      const TsMarch mc = march[mi];
+      const int p = mc.chunk * TS_L + 2 * tid;
+      const bool valid = p < N2;
+      int ileft = -1, iright = 2;  // offsets of the i - 1 / i + 2 neighbours from this thread's pair (periodic in the row)
+      double2 fo = {0.0, 0.0};
+      if (valid) {
+        const int j = p / N, i = p - j * N;
+        if (i == 0) ileft = N - 1;
+        if (i + 2 == N) iright = 2 - N;
+        if (MODE & M_RESID) fo = *reinterpret_cast<const double2*>(forcing + p);
+      }
+      // ring positions of loads l0, l0 + 1, l0 + 2 (slot, phase parity), advanced incrementally: no division in the march
+      int sm_i = mc.l0 % R, pm = (mc.l0 / R) & 1;
+      int sc_i = sm_i + 1, pc = pm;
+      if (sc_i == R) { sc_i = 0; pc ^= 1; }
+      int sp_i = sc_i + 1, pp = pc;
+      if (sp_i == R) { sp_i = 0; pp ^= 1; }
+      mbar_wait(&full[sm_i], (unsigned)pm);
+      mbar_wait(&full[sc_i], (unsigned)pc);
+      const double* xoff = ts_sm + N + 2 * tid;
+      for (int jj = 0; jj < mc.m; ++jj) {
+        const int k = mc.ka + jj;
+        mbar_wait(&full[sp_i], (unsigned)pp);
+        if (valid) {
+          const double* sm_ = xoff + (size_t)sm_i * slot_doubles;
+          const double* sc_ = xoff + (size_t)sc_i * slot_doubles;
+          const double* sp_ = xoff + (size_t)sp_i * slot_doubles;
+          double2 lap[2], xc[2];
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+            const double* row = sc_ + s * xrow;  // row[0], row[1]: this thread's cells
+            const double2 c2 = *reinterpret_cast<const double2*>(row);
+            const double2 km = *reinterpret_cast<const double2*>(sm_ + s * xrow);
+            const double2 kp = *reinterpret_cast<const double2*>(sp_ + s * xrow);
+            const double2 jm = *reinterpret_cast<const double2*>(row - N), jp = *reinterpret_cast<const double2*>(row + N);
+            const double left = row[ileft];
+            const double right = row[iright];
+            lap[s].x = __dadd_rn(lap_plane(left, c2.y, jp.x, jm.x, c2.x), lap_z(kp.x, km.x, c2.x));
+            lap[s].y = __dadd_rn(lap_plane(c2.x, right, jp.y, jm.y, c2.y), lap_z(kp.y, km.y, c2.y));
+            xc[s] = c2;
+          }
+          double2 o0, o1;
+          if (MODE & M_RESID) {
+            bruss_resid(P, lap[0].x, lap[1].x, xc[0].x, xc[1].x, fo.x, o0.x, o1.x);
+            bruss_resid(P, lap[0].y, lap[1].y, xc[0].y, xc[1].y, fo.y, o0.y, o1.y);
+            if (MODE & M_NORM) nrm = fmax(nrm, fmax(fmax(abs_nf(o0.x), abs_nf(o0.y)), fmax(abs_nf(o1.x), abs_nf(o1.y))));
+          } else {
+            const double* yb = sc_ - N + 2 * xrow;   // the centre-only field of the same slot: [2][TS_L]
+            const double2 y0 = *reinterpret_cast<const double2*>(yb);
+            const double2 y1 = *reinterpret_cast<const double2*>(yb + TS_L);
+            bruss_tangent<(MODE & M_VJP) != 0>(P, lap[0].x, lap[1].x, y0.x, y1.x, xc[0].x, xc[1].x, o0.x, o1.x);
+            bruss_tangent<(MODE & M_VJP) != 0>(P, lap[0].y, lap[1].y, y0.y, y1.y, xc[0].y, xc[1].y, o0.y, o1.y);
+          }
+          double* dst = out + (int64_t)k * N2 + p;
+          *reinterpret_cast<double2*>(dst) = o0;
+          *reinterpret_cast<double2*>(dst + NC) = o1;
+        }
+        __syncwarp();
+        if (lane == 0) {  // this warp is done with the oldest plane (and, at the end of a march, with the other two)
+          mbar_arrive(&empty[sm_i]);
+          if (jj + 1 == mc.m) { mbar_arrive(&empty[sc_i]); mbar_arrive(&empty[sp_i]); }
+        }
+        sm_i = sc_i; sc_i = sp_i;
+        if (++sp_i == R) { sp_i = 0; pp ^= 1; }
       }
     }
   }
@@ -416,15 +436,18 @@ int32_t launch_bruss(b200_problem* p, const double* u, const double* d, double* 
     if constexpr (tiled) if ((N % 2 == 0) && N2 >= TS_L + 2 * N) {
       constexpr bool has_y = (MODE & (M_JVP | M_VJP)) != 0;
       const size_t slot = sizeof(double) * (2 * (size_t)(TS_L + 2 * N) + (has_y ? 2 * TS_L : 0));
-      const int R = (int)std::min<size_t>(TS_MAXR, (size_t)(100 * 1024) / slot);  // two CTAs per SM share the 227 KB
+      // two CTAs per SM share the 227 KB.  Measured at N = 100 (ncu, profiles/r2_stencil_explore.txt): 1 CTA x 16 slots, 2 x 8, 2 x 6,
+      // 2 x 4, 3 x 5, 4 x 4 all land within 10.7 - 13.7 us — the depth of the ring is not what bounds a kernel this short
+      const int R = (int)std::min<size_t>(TS_MAXR, (size_t)(100 * 1024) / slot);
+      const int per_sm = 2;
       const int chunks = (N2 + TS_L - 1) / TS_L;
       const int64_t W = (int64_t)chunks * N;
       // one wave, two CTAs per SM; every CTA gets a run of >= 2 planes and crosses at most TS_MAXMARCH - 1 chunk boundaries
-      const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(2 * (int64_t)ctx->sm_count, W / 2));
+      const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(per_sm * (int64_t)ctx->sm_count, W / 2));
       if (R >= 4 && (W + grid - 1) / grid <= (int64_t)(TS_MAXMARCH - 1) * N) {
         const size_t smem = slot * R;
         CUDA_TRY(ctx, cudaFuncSetAttribute(bruss3d_ring_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        PLAUNCH(ctx, kid, pbytes, (bruss3d_ring_kernel<MODE>), grid, TS_THREADS, smem, P, R, u, d, forcing, (MODE & M_RESID) ? du : Jd, norm_out);
+        PLAUNCH(ctx, kid, pbytes, (bruss3d_ring_kernel<MODE>), grid, TS_THREADS + 32, smem, P, R, u, d, forcing, (MODE & M_RESID) ? du : Jd, norm_out);
         done = true;
       }
     }

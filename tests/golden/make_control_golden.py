@@ -40,6 +40,15 @@ def cases():
         for norm in ("inf", "l2"):
             out.append(dict(problem="bruss2d", N=6, u0_scale=1.0, name="term_%s_%s" % (m, norm), termination=m, term_norm=norm, abstol=1e-7, reltol=1e-9))
     out.append(dict(problem="bruss2d", N=6, u0_scale=1.0, name="maxiters_2", maxiters=2, abstol=1e-12, reltol=1e-12))
+    # Broyden (quasi-Newton): both initialisations, both update rules, a reset, the max_resets exit
+    q = dict(problem="quadratic", n=10, u0_linspace=[0.6, 3.0], descent="broyden", abstol=1e-11, reltol=1e-11, maxiters=200)
+    out.append(dict(q, name="broyden_quadratic_good"))
+    out.append(dict(q, name="broyden_quadratic_bad", update_rule="bad_broyden"))
+    out.append(dict(q, name="broyden_quadratic_true_jacobian_with_reset", init_jacobian="true_jacobian"))
+    out.append(dict(q, name="broyden_quadratic_max_resets", reset_tolerance=0.05, max_resets=1))
+    b = dict(problem="bruss2d", N=6, u0_scale=1.0, descent="broyden", init_jacobian="true_jacobian", abstol=1e-8, reltol=1e-8, maxiters=200)
+    out.append(dict(b, name="broyden_bruss2d_true_jacobian_good"))
+    out.append(dict(b, name="broyden_bruss2d_true_jacobian_bad", update_rule="bad_broyden"))
     return out
 
 
@@ -49,13 +58,21 @@ def run(case):
         u0 = prob.u0() * case["u0_scale"]
     else:
         prob = nn.Quadratic(case["n"])
-        u0 = np.ones(case["n"])
+        u0 = np.linspace(*case["u0_linspace"], case["n"]) if "u0_linspace" in case else np.ones(case["n"])
     term = nn.Termination(mode=case.get("termination", "AbsNormSafeBest"), norm=case.get("term_norm", "inf"), abstol=case["abstol"], reltol=case["reltol"])
     if case.get("descent") == "levenberg_marquardt":
         r = nn.solve_lm(prob, u0, disable_geodesic=case.get("disable_geodesic", False), termination=term, maxiters=case.get("maxiters", 1000))
         u = r.pop("u")
         r["u_norm2"] = float(np.linalg.norm(u))
         r["u_first"] = [float(x) for x in u[:4]]
+        return r
+    if case.get("descent") == "broyden":
+        r = nn.solve_broyden(prob, u0, init_jacobian=case.get("init_jacobian", "identity"), update_rule=case.get("update_rule", "good_broyden"),
+                             max_resets=case.get("max_resets", 100), reset_tolerance=case.get("reset_tolerance"), termination=term, maxiters=case.get("maxiters", 1000))
+        u = r.pop("u")
+        r["u_norm2"] = float(np.linalg.norm(u))
+        r["u_first"] = [float(x) for x in u[:4]]
+        r["reset"] = [int(x) for x in r["reset"]]
         return r
     r = nn.solve(prob, u0, globalization=case.get("globalization", "none"), tr_scheme=case.get("tr_scheme", "Simple"), descent=case.get("descent", "newton"),
                  alpha_initial=case.get("alpha_initial", 1e-3), termination=term, maxiters=case.get("maxiters", 1000))

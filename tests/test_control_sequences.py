@@ -53,7 +53,7 @@ def _compare(name, e, res, trace, u, radius_of=lambda t: t.trust_radius, rtol=1e
 
 
 def _oracle_supported(c):
-    if c.get("descent") == "levenberg_marquardt":
+    if c.get("descent") in ("levenberg_marquardt", "broyden"):
         return False
     return c.get("termination", "AbsNormSafeBest") in ("AbsNormSafeBest", "AbsNorm", "AbsNormSafe") and c.get("term_norm", "inf") == "inf" and \
         c.get("tr_scheme", "Simple") != "Bastin"
@@ -89,13 +89,16 @@ def test_cuda_driver_reproduces_the_numpy_sequences(nls, ctx, d):
         p = (3.4, 1.0, 10.0)
     else:
         f = nls.QuadraticFunction(c["n"])
-        u0 = np.ones(c["n"])
+        u0 = np.linspace(*c["u0_linspace"], c["n"]) if "u0_linspace" in c else np.ones(c["n"])
         p = 2.0
     term = getattr(nls, c.get("termination", "AbsNormSafeBest") + "TerminationMode")(norm=c.get("term_norm", "inf"))
     if c.get("globalization") == "trust_region":
         alg = nls.TrustRegion(radius_update_scheme=getattr(nls.RadiusUpdateSchemes, c["tr_scheme"]))
     elif c.get("descent") == "levenberg_marquardt":
         alg = nls.LevenbergMarquardt(disable_geodesic=c.get("disable_geodesic", False))
+    elif c.get("descent") == "broyden":
+        alg = nls.Broyden(init_jacobian=c.get("init_jacobian", "identity"), update_rule=c.get("update_rule", "good_broyden"), max_resets=c.get("max_resets", 100),
+                          reset_tolerance=c.get("reset_tolerance"))
     elif c.get("descent") == "pseudo_transient":
         alg = nls.PseudoTransient(alpha_initial=c["alpha_initial"])
     elif c.get("globalization") == "linesearch":
@@ -109,5 +112,7 @@ def test_cuda_driver_reproduces_the_numpy_sequences(nls, ctx, d):
     # Levenberg-Marquardt solves the normal equations (condition number squared): every DECISION must agree exactly, the
     # residual history to 1e-4 (two correct dense solves of J'J + lambda D'D differ by kappa(J)^2 eps per step)
     _compare(c["name"], e, R, sol.trace, sol.u, rtol=1e-4 if c.get("descent") == "levenberg_marquardt" else 1e-7)
+    if "reset" in e:        # Broyden: the steps before which the stored inverse was re-initialised (trace slot lin_status)
+        assert [t.lin_status for t in sol.trace] == e["reset"][:len(sol.trace)], c["name"]
     if "descent_ok" in e:   # Levenberg-Marquardt: the geodesic-acceleration verdict of every step (trace slot lin_status)
         assert [t.lin_status for t in sol.trace] == e["descent_ok"], c["name"]

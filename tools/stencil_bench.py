@@ -44,5 +44,17 @@ for N in [int(a) for a in sys.argv[1:]] or [100, 80]:
         wall_us = (time.perf_counter() - t0) * 1e6 / reps
         res[name] = {"bytes": nb * Bv, "event_us": round(ev_us, 2), "event_gbs": round(nb * Bv / ev_us / 1e3, 1), "event_frac": round(nb * Bv / ev_us / 1e3 / PEAK, 3),
                      "batch_wall_us": round(wall_us, 2), "batch_gbs": round(nb * Bv / wall_us / 1e3, 1)}
+    # the ceiling for kernels this short: the library's plain copy kernel (2 Bv of traffic) through the same harness
+    import ctypes as C
+    cp = lambda s: nls.abi.check(ctx.handle, nls.abi.lib().b200_copy(ctx.handle, C.c_int64(n), us[s].ptr, os_[s].ptr))  # noqa: E731
+    for s in range(SETS):
+        cp(s)
+    ctx.sync()
+    t0 = time.perf_counter()
+    for r in range(5 * SETS):
+        cp(r % SETS)
+    ctx.sync()
+    wall_us = (time.perf_counter() - t0) * 1e6 / (5 * SETS)
+    res["copy_2Bv"] = {"bytes": 2 * Bv, "batch_wall_us": round(wall_us, 2), "batch_gbs": round(2 * Bv / wall_us / 1e3, 1)}
     out["N%d" % N] = res
 print(json.dumps(out, indent=1))
