@@ -575,7 +575,7 @@ def run_b200(args):
             "clocks": clk,
             "ensemble": ens,
             "resid_inf": sol.resid_inf, "retcode": nls.ReturnCode.name(sol.retcode)}
-    if not args.no_legs:  # the other BASELINE configurations, each in a few seconds (rank 0, after the headline's timed regions)
+    if not args.no_legs and world == 1:  # the other BASELINE configurations, each in a few seconds (N = 1 only, after the headline's timed regions)
         for key, fn in (("n80", lambda: leg_n80(nls, torch, ctx, args.orth, peak)), ("lu", lambda: leg_lu(nls, torch, ctx)),
                         ("sparse_tr", lambda: leg_sparse_tr(nls, torch, ctx, args.orth, peak)), ("precond", lambda: leg_precond(nls, torch, ctx))):
             try:

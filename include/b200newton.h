@@ -101,7 +101,10 @@ enum { B200_DESCENT_NEWTON = 0, B200_DESCENT_PSEUDO_TRANSIENT = 1, B200_DESCENT_
    STORED INVERSE J^-1 (dense n x n, resident in HBM), rank-one good / bad Broyden update after every step, NoChangeInStateReset
    (reset_conditions.jl:18-88) re-initialising J^-1, ConvergenceFailure after max_resets.  The step routine is keyed on this field
    because the option struct is; in the reference it is its own algorithm type, not a descent. */
-enum { B200_QN_INIT_IDENTITY = 0, B200_QN_INIT_TRUE_JACOBIAN = 1 };   /* init_jacobian = Val(:identity) | Val(:true_jacobian) (needs linsolve = DENSE_LU) */
+enum { B200_QN_INIT_IDENTITY = 0, B200_QN_INIT_TRUE_JACOBIAN = 1, B200_QN_INIT_LOW_RANK = 2 };
+/* init_jacobian = Val(:identity) | Val(:true_jacobian) (needs linsolve = DENSE_LU); LOW_RANK = LimitedMemoryBroyden(; threshold)
+   (lbroyden.jl:20-35, initialization.jl:139-298): J^-1 = alpha I + U V' with the last `qn_threshold` rank-one updates kept in two
+   n x threshold arrays (circular), any n */
 enum { B200_QN_UPDATE_GOOD_BROYDEN = 0, B200_QN_UPDATE_BAD_BROYDEN = 1 };
 /* built-in preconditioners (LinearSolve `precs(A, p)`, large_systems.md:244-316): inverse of the 2x2 species blocks, or one
    geometric-multigrid V-cycle of the Brusselator Jacobian (the tutorial's AlgebraicMultigrid ruge_stuben / smoothed_aggregation) */
@@ -199,7 +202,7 @@ typedef struct b200_newton_opts {
   /* Broyden(; max_resets = 100, reset_tolerance = eps^(3/4), init_jacobian = Val(:identity), alpha = nothing, update_rule =
      Val(:good_broyden)); qn_alpha <= 0 => 2 ||f|| / max(||u||, 1) (1 when ||f|| < 1e-5), the identity is scaled by it before
      inversion */
-  int32_t qn_init_jacobian, qn_update_rule, qn_max_resets, reserved1;
+  int32_t qn_init_jacobian, qn_update_rule, qn_max_resets, qn_threshold; /* qn_threshold: LOW_RANK only; 0 => 10 */
   double qn_reset_tolerance, qn_alpha;
 } b200_newton_opts;
 

@@ -379,7 +379,7 @@ struct NewtonOpts
     maxtime::Float64; term_norm::Int32; term_max_stalled_steps::Int32
     lm_damping_initial::Float64; lm_damping_increase::Float64; lm_damping_decrease::Float64; lm_finite_diff_step::Float64
     lm_alpha_geodesic::Float64; lm_b_uphill::Float64; lm_min_damping_D::Float64; lm_disable_geodesic::Int32; reserved0::Int32
-    qn_init_jacobian::Int32; qn_update_rule::Int32; qn_max_resets::Int32; reserved1::Int32
+    qn_init_jacobian::Int32; qn_update_rule::Int32; qn_max_resets::Int32; qn_threshold::Int32
     qn_reset_tolerance::Float64; qn_alpha::Float64
 end
 struct NewtonResult
@@ -524,7 +524,8 @@ Base.@kwdef struct B200NewtonKrylov <: NonlinearSolveBase.AbstractNonlinearSolve
     orth::Symbol = :mgs
     termination::Symbol = :abs_norm_safe_best
     termination_norm::Symbol = :inf      # internalnorm of the termination mode: :inf (maximum(abs, .)) or :l2
-    init_jacobian::Symbol = :identity    # descent = :broyden — Broyden(; init_jacobian = Val(:identity) | Val(:true_jacobian))
+    init_jacobian::Symbol = :identity    # descent = :broyden — Broyden(; init_jacobian = Val(:identity) | Val(:true_jacobian)); :low_rank = LimitedMemoryBroyden
+    threshold::Int = 10                  #                      LimitedMemoryBroyden(; threshold = Val(10))
     update_rule::Symbol = :good_broyden  #                      Broyden(; update_rule = Val(:good_broyden) | Val(:bad_broyden))
     max_resets::Int = 100
 end
@@ -532,7 +533,7 @@ end
 const _LINSOLVE = (gmres = 0, dense_lu = 1, sparse_gmres = 2, sparse_lu = 3)
 const _GLOBALIZATION = (none = 0, trust_region = 1, linesearch = 2)
 const _DESCENT = (newton = 0, pseudo_transient = 1, levenberg_marquardt = 2, broyden = 3)
-const _QN_INIT = (identity = 0, true_jacobian = 1)
+const _QN_INIT = (identity = 0, true_jacobian = 1, low_rank = 2)
 const _QN_UPDATE = (good_broyden = 0, bad_broyden = 1)
 const _TR_SCHEMES = (simple = 0, nlsolve = 1, nocedal_wright = 2, hei = 3, yuan = 4, fan = 5, bastin = 6)
 const _PRECS = (none = 0, block_jacobi_left = 1, block_jacobi_right = 2, multigrid_left = 3, multigrid_right = 4)
@@ -549,7 +550,7 @@ function newton_opts(alg::B200NewtonKrylov; abstol = nothing, reltol = nothing, 
         tr_scheme = getfield(_TR_SCHEMES, alg.radius_update_scheme), pt_alpha_initial = alg.alpha_initial,
         termination = getfield(_TERMINATION, alg.termination), term_norm = alg.termination_norm === :l2 ? 1 : 0,
         qn_init_jacobian = getfield(_QN_INIT, alg.init_jacobian), qn_update_rule = getfield(_QN_UPDATE, alg.update_rule),
-        qn_max_resets = alg.max_resets)
+        qn_max_resets = alg.max_resets, qn_threshold = alg.threshold)
 end
 
 function SciMLBase.__solve(prob::SciMLBase.NonlinearProblem, alg::B200NewtonKrylov, args...;

@@ -27,7 +27,7 @@ JVP_EXACT, JVP_FINITE_DIFF = 0, 1
 GLOB_NONE, GLOB_TRUST_REGION, GLOB_LINESEARCH = 0, 1, 2
 PRECOND_NONE, PRECOND_BLOCK_JACOBI_LEFT, PRECOND_BLOCK_JACOBI_RIGHT, PRECOND_MULTIGRID_LEFT, PRECOND_MULTIGRID_RIGHT = 0, 1, 2, 3, 4
 DESCENT_NEWTON, DESCENT_PSEUDO_TRANSIENT, DESCENT_LEVENBERG_MARQUARDT, DESCENT_BROYDEN = 0, 1, 2, 3
-QN_INIT_IDENTITY, QN_INIT_TRUE_JACOBIAN = 0, 1
+QN_INIT_IDENTITY, QN_INIT_TRUE_JACOBIAN, QN_INIT_LOW_RANK = 0, 1, 2
 QN_UPDATE_GOOD_BROYDEN, QN_UPDATE_BAD_BROYDEN = 0, 1
 TR_SIMPLE, TR_NLSOLVE, TR_NOCEDAL_WRIGHT, TR_HEI, TR_YUAN, TR_FAN, TR_BASTIN = range(7)
 FORCING_NONE, FORCING_EW2 = 0, 1
@@ -63,7 +63,7 @@ class NewtonOpts(C.Structure):
                 ("lm_damping_initial", C.c_double), ("lm_damping_increase", C.c_double), ("lm_damping_decrease", C.c_double), ("lm_finite_diff_step", C.c_double),
                 ("lm_alpha_geodesic", C.c_double), ("lm_b_uphill", C.c_double), ("lm_min_damping_D", C.c_double), ("lm_disable_geodesic", C.c_int32),
                 ("reserved0", C.c_int32),
-                ("qn_init_jacobian", C.c_int32), ("qn_update_rule", C.c_int32), ("qn_max_resets", C.c_int32), ("reserved1", C.c_int32),
+                ("qn_init_jacobian", C.c_int32), ("qn_update_rule", C.c_int32), ("qn_max_resets", C.c_int32), ("qn_threshold", C.c_int32),
                 ("qn_reset_tolerance", C.c_double), ("qn_alpha", C.c_double)]
 
 

@@ -590,6 +590,18 @@ class Broyden(_FirstOrder):
         self.reset_tolerance, self.alpha = reset_tolerance, alpha
 
 
+class LimitedMemoryBroyden(Broyden):
+    """LimitedMemoryBroyden(; max_resets = 3, threshold = Val(10), reset_tolerance = nothing, alpha = nothing)
+    NonlinearSolveQuasiNewton/src/lbroyden.jl:20-35 — good Broyden on J^-1 = alpha I + U V' with the last `threshold` updates kept
+    (two n x threshold arrays): the member of the family that scales to the 2*10^6-unknown systems."""
+    name = "LimitedMemoryBroyden"
+
+    def __init__(self, max_resets=3, threshold=10, reset_tolerance=None, alpha=None):
+        super().__init__(max_resets=max_resets, reset_tolerance=reset_tolerance, init_jacobian="identity", alpha=alpha)
+        self.qn["qn_init_jacobian"] = abi.QN_INIT_LOW_RANK
+        self.qn["qn_threshold"] = int(threshold)
+
+
 class RadiusUpdateSchemes:
     """RadiusUpdateSchemes.{Simple, NLsolve, NocedalWright, Hei, Yuan, Fan, Bastin}  (trust_region.jl:431-520)."""
     Simple, NLsolve, NocedalWright, Hei, Yuan, Fan, Bastin = (abi.TR_SIMPLE, abi.TR_NLSOLVE, abi.TR_NOCEDAL_WRIGHT, abi.TR_HEI, abi.TR_YUAN, abi.TR_FAN, abi.TR_BASTIN)

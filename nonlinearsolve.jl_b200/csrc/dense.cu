@@ -301,6 +301,77 @@ __global__ void __launch_bounds__(DT) trsm_kernel(double* __restrict__ A, int64_
     if (r < kb) col[r] = x[r];
 }
 
+// U12 = L11^{-1} A12 for a whole outer panel in ONE launch: a CTA owns U12_NCB columns of A12 and keeps its kbo x U12_NCB tile in
+// shared memory through all kbo / 32 block steps (warp-cooperative solve of the 32 x 32 unit-lower diagonal block — lanes are
+// rows, the solved entries travel by shuffle — then the rows below are updated with the solved block read back as 16-byte
+// broadcasts).  Replaces 31 dependent launches per outer step (16 solves of 32 rows + 15 updates), which had become pure launch
+// latency: 0.73 ms per step even when A12 was 3 500 columns wide (profiles/r2_lu_timeline.txt).  FP64 FMA-bound: kbo^2 / 2 per column.
+constexpr int U12_NCB = 16, U12_T = 256;
+__global__ void __launch_bounds__(U12_T, 2) u12_fused_kernel(double* __restrict__ A, int64_t ld, int64_t k0, int kbo, int64_t k1, int64_t rest) {
+  extern __shared__ double xs[];                 // [U12_NCB][kbo] column-major tile of A12
+  __shared__ double Ld[NBI][NBI + 1];            // current diagonal block of L11 (strictly lower part used)
+  __shared__ __align__(16) double xb[NBI][U12_NCB];  // the block just solved, row-major: one row = the 16 column values
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t c0 = k1 + (int64_t)blockIdx.x * U12_NCB;
+  const int nc = (int)min((int64_t)U12_NCB, k1 + rest - c0);
+  for (int idx = tid; idx < kbo * U12_NCB; idx += U12_T) {
+    const int c = idx / kbo, r = idx - c * kbo;
+    xs[idx] = (c < nc) ? A[(c0 + c) * ld + k0 + r] : 0.0;
+  }
+  __syncthreads();
+  for (int b0 = 0; b0 < kbo; b0 += NBI) {
+    const int kb = min(NBI, kbo - b0);
+    for (int idx = tid; idx < kb * kb; idx += U12_T) {
+      const int r = idx % kb, q = idx / kb;
+      Ld[r][q] = A[(k0 + b0 + q) * ld + k0 + b0 + r];
+    }
+    __syncthreads();
+    // ---- solve the diagonal block: warp w takes columns w, w + 8; lane = row; x_i is final after step i - 1
+    for (int cc = warp; cc < U12_NCB; cc += U12_T / 32) {
+      double x = (lane < kb) ? xs[cc * kbo + b0 + lane] : 0.0;
+      for (int i = 0; i + 1 < kb; ++i) {
+        const double xi = __shfl_sync(0xffffffffu, x, i);
+        if (lane > i && lane < kb) x = fma(-Ld[lane][i], xi, x);
+      }
+      if (lane < kb) { xs[cc * kbo + b0 + lane] = x; xb[lane][cc] = x; }
+    }
+    __syncthreads();
+    // ---- rows below the block: x[r, :] -= L[r, b0 : b0 + kb] * xb
+    const int nb = kbo - b0 - kb;
+    for (int r = tid; r < nb; r += U12_T) {
+      const int rr = b0 + kb + r;
+      double acc[U12_NCB];
+#pragma unroll
+      for (int c = 0; c < U12_NCB; ++c) acc[c] = xs[c * kbo + rr];
+      const double* Lrow = A + (k0 + b0) * ld + k0 + rr;   // L[rr][b0 + q] = Lrow[q * ld]
+      for (int q0 = 0; q0 < kb; q0 += 8) {
+        double l[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) l[q] = (q0 + q < kb) ? Lrow[(int64_t)(q0 + q) * ld] : 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          if (q0 + q < kb) {
+            const double2* xr = reinterpret_cast<const double2*>(xb[q0 + q]);
+#pragma unroll
+            for (int c = 0; c < U12_NCB; c += 2) {
+              const double2 v = xr[c >> 1];
+              acc[c] = fma(-l[q], v.x, acc[c]);
+              acc[c + 1] = fma(-l[q], v.y, acc[c + 1]);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < U12_NCB; ++c) xs[c * kbo + rr] = acc[c];
+    }
+    __syncthreads();
+  }
+  for (int idx = tid; idx < kbo * U12_NCB; idx += U12_T) {
+    const int c = idx / kbo, r = idx - c * kbo;
+    if (c < nc) A[(c0 + c) * ld + k0 + r] = xs[idx];
+  }
+}
+
 // ------------------------------------------------------------------ C -= A * B on the FP64 tensor cores
 // A: M x K (lda), B: K x N (ldb), C: M x N (ldc), all column-major.  CTA = 4 warps, tile 128 (M) x 64 (N), each warp a
 // 32 x 64 sub-tile = 4 x 8 DMMA m8n8k4 accumulator fragments; K streamed in chunks of 8 through double-buffered shared
@@ -775,6 +846,7 @@ int32_t b200_getrf(b200_ctx* ctx, int64_t n, double* A, int64_t ld, int64_t* ipi
   CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_lu_xchg, 0, sizeof(unsigned long long) * PX_WORDS, ctx->stream));  // epochs are column numbers: valid for one factorisation
   CUDA_TRY(ctx, cudaFuncSetAttribute(panel_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   CUDA_TRY(ctx, cudaFuncSetAttribute((gemm_sub_w8_kernel<2, GM_BK, GM_STAGES>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+  CUDA_TRY(ctx, cudaFuncSetAttribute(u12_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 512 * U12_NCB)));
   if (!ctx->aux_stream) {
     // highest priority: while the trailing update's CTAs drain and refill, the block scheduler hands freed SM slots to the
     // look-ahead panel first, so the (latency-bound, cooperative) panel runs underneath the GEMM instead of after it
@@ -841,23 +913,10 @@ int32_t b200_getrf(b200_ctx* ctx, int64_t n, double* A, int64_t ld, int64_t* ipi
     mark();  // 0b: interchanges done
     const int64_t rest = n - k1;
     if (rest <= 0) break;
-    // ---- U12 = L11^{-1} A12, recursively: solve the top half, update the bottom half with ONE GEMM of K = half, solve the bottom
-    //      half.  Same 16 leaf solves of 32 rows as a left-to-right sweep, but the 15 updates have K = 256, 128, 128, 64 ... instead of
-    //      16 updates of K = 32: 3.75x less read-modify-write traffic on A12 (round 2: this stage was 7 % of the factorisation).
+    // ---- U12 = L11^{-1} A12: one fused launch (column blocks of 16 stay in shared memory through all 16 block steps)
     {
-      struct Rec {
-        static int32_t run(b200_ctx* ctx, double* A, int64_t ld, int64_t r0, int kb, int64_t k1, int64_t rest) {
-          if (kb <= NBI) {
-            PLAUNCH(ctx, B200_KID_LU_OTHER, 0.0, trsm_kernel, (int)((rest + DT - 1) / DT), DT, 0, A, ld, r0, kb, k1, rest);
-            return B200_OK;
-          }
-          const int h = ((kb / 2 + NBI - 1) / NBI) * NBI;
-          B200_TRY(run(ctx, A, ld, r0, h, k1, rest));
-          B200_TRY(gemm_sub(ctx, kb - h, rest, h, A + r0 * ld + (r0 + h), ld, A + k1 * ld + r0, ld, A + k1 * ld + (r0 + h), ld));
-          return run(ctx, A, ld, r0 + h, kb - h, k1, rest);
-        }
-      };
-      B200_TRY(Rec::run(ctx, A, ld, k0, kbo, k1, rest));
+      const size_t smem = sizeof(double) * (size_t)kbo * U12_NCB;
+      PLAUNCH(ctx, B200_KID_LU_OTHER, 0.0, u12_fused_kernel, (int)((rest + U12_NCB - 1) / U12_NCB), U12_T, smem, A, ld, k0, kbo, k1, rest);
     }
     // ---- trailing update on the FP64 tensor cores, with look-ahead: first the columns of the NEXT panel, whose
     //      factorisation (latency-bound, few SMs) then runs on a second stream underneath the rest of the GEMM.

@@ -58,6 +58,9 @@ struct b200_newton {
   // LevenbergMarquardt: J'J + lambda D'D (factored in place), the running diagonal D'D, velocity / acceleration, previous velocity
   double *lmA, *lm_dtd, *lm_v, *lm_a, *lm_vold, *lm_rhs;
   int qn_since_du, qn_since_dfu, qn_nresets;  // Broyden: NoChangeInStateReset counters, resets so far
+  double *lr_U, *lr_V, *lr_c;                // LimitedMemoryBroyden: J^-1 = lr_alpha I + U V' (n x lr_m each, circular), coefficient scratch
+  int lr_m, lr_idx;
+  double lr_alpha;
   double lm_lambda, lm_lambda_factor, lm_norm_v_old, lm_loss_old;
   // state
   TermCache tc;
@@ -179,7 +182,7 @@ int32_t b200_newton_destroy(b200_newton* nw) {
   b200_ctx* ctx = nw->ctx;
   cudaStreamSynchronize(ctx->stream);
   double* vecs[] = {nw->u, nw->fu, nw->u_cache, nw->du, nw->xlin, nw->best_u, nw->u_trial, nw->fu_trial, nw->Jdu, nw->JTfu, nw->du_c, nw->c1, nw->c2,
-                    nw->Jdense, nw->nzval, nw->lmA, nw->lm_dtd, nw->lm_v, nw->lm_a, nw->lm_vold, nw->lm_rhs};
+                    nw->Jdense, nw->nzval, nw->lmA, nw->lm_dtd, nw->lm_v, nw->lm_a, nw->lm_vold, nw->lm_rhs, nw->lr_U, nw->lr_V, nw->lr_c};
   for (double* v : vecs) if (v) cudaFree(v);
   if (nw->ipiv) cudaFree(nw->ipiv);
   if (nw->qr_work) cudaFree(nw->qr_work);
@@ -202,8 +205,9 @@ int32_t b200_newton_create(b200_problem* prob, const b200_newton_opts* opts, b20
   B200_REQUIRE(ctx, opts->term_max_stalled_steps <= 128, "newton_create: term_max_stalled_steps must be <= 128");
   B200_REQUIRE(ctx, opts->descent == B200_DESCENT_NEWTON || (opts->descent == B200_DESCENT_PSEUDO_TRANSIENT && opts->globalization != B200_GLOBALIZATION_TRUST_REGION) ||
                         (opts->descent == B200_DESCENT_LEVENBERG_MARQUARDT && opts->globalization == B200_GLOBALIZATION_NONE && opts->linsolve == B200_LINSOLVE_DENSE_LU) ||
-                        (opts->descent == B200_DESCENT_BROYDEN && opts->globalization == B200_GLOBALIZATION_NONE && prob->n <= 65535 &&
-                         (opts->qn_init_jacobian == B200_QN_INIT_IDENTITY || (opts->qn_init_jacobian == B200_QN_INIT_TRUE_JACOBIAN && opts->linsolve == B200_LINSOLVE_DENSE_LU)) &&
+                        (opts->descent == B200_DESCENT_BROYDEN && opts->globalization == B200_GLOBALIZATION_NONE && (prob->n <= 65535 || opts->qn_init_jacobian == B200_QN_INIT_LOW_RANK) &&
+                         (opts->qn_init_jacobian == B200_QN_INIT_IDENTITY || opts->qn_init_jacobian == B200_QN_INIT_LOW_RANK ||
+                          (opts->qn_init_jacobian == B200_QN_INIT_TRUE_JACOBIAN && opts->linsolve == B200_LINSOLVE_DENSE_LU)) &&
                          (opts->qn_update_rule == B200_QN_UPDATE_GOOD_BROYDEN || opts->qn_update_rule == B200_QN_UPDATE_BAD_BROYDEN)),
                "newton_create: descent must be Newton, PseudoTransient (without a trust region), LevenbergMarquardt (dense concrete Jacobian, its own trust region) or "
                "Broyden (no globalisation, n <= 65535, init_jacobian = true_jacobian needs the dense LU)");
@@ -221,6 +225,7 @@ int32_t b200_newton_create(b200_problem* prob, const b200_newton_opts* opts, b20
   nw->u_trial = nw->fu_trial = nw->Jdu = nw->JTfu = nw->du_c = nw->c1 = nw->c2 = nullptr;
   nw->qr_work = nullptr; nw->qr_jpvt = nullptr;
   nw->lmA = nw->lm_dtd = nw->lm_v = nw->lm_a = nw->lm_vold = nw->lm_rhs = nullptr;
+  nw->lr_U = nw->lr_V = nw->lr_c = nullptr; nw->lr_m = nw->lr_idx = 0; nw->lr_alpha = 1.0;
   nw->slu = nullptr; nw->mg = nullptr; nw->gm = nullptr; nw->Jdense = nullptr; nw->ipiv = nullptr; nw->sj = nullptr; nw->nzval = nullptr;
   nw->initialised = 0;
   const int64_t n = nw->n;
@@ -238,7 +243,14 @@ int32_t b200_newton_create(b200_problem* prob, const b200_newton_opts* opts, b20
   }
   if (opts->descent == B200_DESCENT_BROYDEN) {  // the stored inverse and the update rule's / reset condition's vectors share the LM slots
     A(&nw->lm_dtd); A(&nw->lm_v); A(&nw->lm_a); A(&nw->lm_vold); A(&nw->lm_rhs);
-    if (s == B200_OK && cudaMalloc(&nw->lmA, sizeof(double) * n * n) != cudaSuccess) { cudaGetLastError(); s = ctx->fail(B200_ERR_NOMEM, "Broyden: the stored inverse Jacobian (n x n) does not fit in device memory", __FILE__, __LINE__); }
+    if (opts->qn_init_jacobian == B200_QN_INIT_LOW_RANK) {
+      nw->lr_m = std::max(1, std::min(opts->qn_threshold > 0 ? opts->qn_threshold : 10, nw->maxiters));  // threshold = min(threshold, maxiters)
+      if (s == B200_OK && (cudaMalloc(&nw->lr_U, sizeof(double) * n * nw->lr_m) != cudaSuccess || cudaMalloc(&nw->lr_V, sizeof(double) * n * nw->lr_m) != cudaSuccess ||
+                           cudaMalloc(&nw->lr_c, sizeof(double) * nw->lr_m) != cudaSuccess)) {
+        cudaGetLastError();
+        s = ctx->fail(B200_ERR_NOMEM, "LimitedMemoryBroyden: the low-rank factors do not fit in device memory", __FILE__, __LINE__);
+      }
+    } else if (s == B200_OK && cudaMalloc(&nw->lmA, sizeof(double) * n * n) != cudaSuccess) { cudaGetLastError(); s = ctx->fail(B200_ERR_NOMEM, "Broyden: the stored inverse Jacobian (n x n) does not fit in device memory", __FILE__, __LINE__); }
   }
   if (s != B200_OK) { b200_newton_destroy(nw); return s; }
   memset(&nw->op, 0, sizeof(nw->op));
@@ -513,7 +525,27 @@ static int32_t broyden_init_inverse(b200_newton* nw) {
     B200_TRY(h_nrm2(nw, nw->u, &un));
     alpha = (fn < 1.0e-5) ? 1.0 : (2.0 * fn) / std::max(un, 1.0);
   }
+  if (nw->o.qn_init_jacobian == B200_QN_INIT_LOW_RANK) {  // BroydenLowRankJacobian: idx = 0, alpha = inv(scaling)   initialization.jl:176-199
+    nw->lr_idx = 0;
+    nw->lr_alpha = 1.0 / alpha;
+    return B200_OK;
+  }
   return b200i_scaled_identity(ctx, n, Jinv, n, 1.0 / alpha);
+}
+
+// y = J^-1 x (transpose = 0) or J^-T x (1): the dense stored inverse, or alpha x + U (V' x) resp. alpha x + V (U' x) for the low-rank form
+static int32_t broyden_apply(b200_newton* nw, int transpose, const double* x, double* y) {
+  b200_ctx* ctx = nw->ctx;
+  const int64_t n = nw->n;
+  if (nw->o.qn_init_jacobian != B200_QN_INIT_LOW_RANK) return b200_gemv(ctx, transpose, n, n, nw->lmA, n, x, y);
+  const int k = std::min(nw->lr_idx, nw->lr_m);
+  if (k > 0) {
+    const double *L = transpose ? nw->lr_V : nw->lr_U, *R = transpose ? nw->lr_U : nw->lr_V;
+    B200_TRY(b200_gemv(ctx, 1, n, k, R, n, x, nw->lr_c));   // c = R' x   (k dot products)
+    B200_TRY(b200_gemv(ctx, 0, n, k, L, n, nw->lr_c, y));   // y = L c
+    return b200_axpy(ctx, n, nw->lr_alpha, x, y);
+  }
+  return b200_axpby(ctx, n, nw->lr_alpha, x, 0.0, y);
 }
 
 static int32_t broyden_count(b200_newton* nw, const double* x, const double* y, double tol, double* out) {
@@ -560,7 +592,7 @@ static int32_t broyden_step(b200_newton* nw) {
     }
   }
   // ---- NewtonDescent on the stored inverse: du = -(J^-1 f) ; u += du ; f = f(u)
-  B200_TRY(b200_gemv(ctx, 0, n, n, Jinv, n, nw->fu, nw->du));
+  B200_TRY(broyden_apply(nw, 0, nw->fu, nw->du));
   B200_TRY(b200_scal(ctx, n, -1.0, nw->du));
   CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_scalars, 0, sizeof(double) * 2, ctx->stream));
   B200_TRY(b200i_axpy_norm(ctx, n, 1.0, nw->du, nw->u, ctx->d_scalars + 1));
@@ -569,7 +601,8 @@ static int32_t broyden_step(b200_newton* nw) {
   B200_TRY(b200i_fetch_scalars(ctx, 2));
   const double objective = ctx->h_scalars[0], du_norm = sqrt(ctx->h_scalars[1]);
   nw->fnorm_inf = objective;
-  nw->bytes += 8.0 * (double)n * (double)n;
+  const double pass_bytes = (o.qn_init_jacobian == B200_QN_INIT_LOW_RANK) ? 16.0 * (double)n * std::min(nw->lr_idx, nw->lr_m) : 8.0 * (double)n * (double)n;  // one product with the stored inverse
+  nw->bytes += pass_bytes;
   bool new_best = false;
   TermQuant tq;
   B200_TRY(term_quantities(nw, nw->fu, nw->u, objective, &tq));
@@ -584,11 +617,11 @@ static int32_t broyden_step(b200_newton* nw) {
   if (nw->force_stop) return B200_OK;  // the reference skips the update once the step has stopped the solve
   // ---- update rule
   B200_TRY(b200_axpby(ctx, n, 1.0, nw->fu, -1.0, dfu_rule));             // dfu = fu - dfu
-  B200_TRY(b200_gemv(ctx, 0, n, n, Jinv, n, dfu_rule, Jd));              // J^-1 dfu
+  B200_TRY(broyden_apply(nw, 0, dfu_rule, Jd));                          // J^-1 dfu
   double denom;
   const double* rmul;
   if (o.qn_update_rule == B200_QN_UPDATE_GOOD_BROYDEN) {
-    B200_TRY(b200_gemv(ctx, 1, n, n, Jinv, n, nw->du, w));               // J^-T du
+    B200_TRY(broyden_apply(nw, 1, nw->du, w));                           // J^-T du
     B200_TRY(h_dot(nw, nw->du, Jd, &denom));
     rmul = w;
   } else {
@@ -601,9 +634,16 @@ static int32_t broyden_step(b200_newton* nw) {
   B200_TRY(b200_copy(ctx, n, nw->du, c));
   B200_TRY(b200_axpy(ctx, n, -1.0, Jd, c));
   B200_TRY(b200_scal(ctx, n, inv, c));                                   // (du - J^-1 dfu) / denom
-  B200_TRY(b200i_ger(ctx, n, Jinv, n, c, rmul));                         // J^-1 += c rmul'
+  if (o.qn_init_jacobian == B200_QN_INIT_LOW_RANK) {                      // mul!(J, u, v', true, true): the pair goes into slot idx mod m
+    const int slot = nw->lr_idx % nw->lr_m;
+    B200_TRY(b200_copy(ctx, n, c, nw->lr_U + (int64_t)slot * n));
+    B200_TRY(b200_copy(ctx, n, rmul, nw->lr_V + (int64_t)slot * n));
+    nw->lr_idx += 1;
+  } else {
+    B200_TRY(b200i_ger(ctx, n, Jinv, n, c, rmul));                       // J^-1 += c rmul'
+  }
   B200_TRY(b200_copy(ctx, n, nw->fu, dfu_rule));
-  nw->bytes += 8.0 * (double)n * (double)n * (o.qn_update_rule == B200_QN_UPDATE_GOOD_BROYDEN ? 4.0 : 3.0);
+  nw->bytes += pass_bytes * (o.qn_update_rule == B200_QN_UPDATE_GOOD_BROYDEN ? 4.0 : 3.0);
   return B200_OK;
 }
 

@@ -49,6 +49,9 @@ def cases():
     b = dict(problem="bruss2d", N=6, u0_scale=1.0, descent="broyden", init_jacobian="true_jacobian", abstol=1e-8, reltol=1e-8, maxiters=200)
     out.append(dict(b, name="broyden_bruss2d_true_jacobian_good"))
     out.append(dict(b, name="broyden_bruss2d_true_jacobian_bad", update_rule="bad_broyden"))
+    # LimitedMemoryBroyden: threshold 10 (the circular buffer wraps), and threshold 3 (every update after the third evicts one)
+    out.append(dict(q, name="lbroyden_quadratic", init_jacobian="low_rank", max_resets=3))
+    out.append(dict(q, name="lbroyden_quadratic_threshold3", init_jacobian="low_rank", threshold=3, max_resets=3, maxiters=60))
     return out
 
 
@@ -68,7 +71,8 @@ def run(case):
         return r
     if case.get("descent") == "broyden":
         r = nn.solve_broyden(prob, u0, init_jacobian=case.get("init_jacobian", "identity"), update_rule=case.get("update_rule", "good_broyden"),
-                             max_resets=case.get("max_resets", 100), reset_tolerance=case.get("reset_tolerance"), termination=term, maxiters=case.get("maxiters", 1000))
+                             max_resets=case.get("max_resets", 100), reset_tolerance=case.get("reset_tolerance"), termination=term, maxiters=case.get("maxiters", 1000),
+                             threshold=case.get("threshold", 10))
         u = r.pop("u")
         r["u_norm2"] = float(np.linalg.norm(u))
         r["u_first"] = [float(x) for x in u[:4]]

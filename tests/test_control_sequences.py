@@ -96,6 +96,8 @@ def test_cuda_driver_reproduces_the_numpy_sequences(nls, ctx, d):
         alg = nls.TrustRegion(radius_update_scheme=getattr(nls.RadiusUpdateSchemes, c["tr_scheme"]))
     elif c.get("descent") == "levenberg_marquardt":
         alg = nls.LevenbergMarquardt(disable_geodesic=c.get("disable_geodesic", False))
+    elif c.get("descent") == "broyden" and c.get("init_jacobian") == "low_rank":
+        alg = nls.LimitedMemoryBroyden(max_resets=c.get("max_resets", 3), threshold=c.get("threshold", 10), reset_tolerance=c.get("reset_tolerance"))
     elif c.get("descent") == "broyden":
         alg = nls.Broyden(init_jacobian=c.get("init_jacobian", "identity"), update_rule=c.get("update_rule", "good_broyden"), max_resets=c.get("max_resets", 100),
                           reset_tolerance=c.get("reset_tolerance"))

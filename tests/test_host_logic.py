@@ -57,6 +57,14 @@ def test_algorithm_options_reach_the_struct(nls):
     o = _opts(nls, nls.NewtonRaphson(linsolve=nls.KrylovJL_GMRES(), forcing=nls.EisenstatWalkerForcing2(), jvp_autodiff=nls.AutoFiniteDiff()),
               termination_condition=nls.AbsNormTerminationMode())
     assert o.forcing == abi.FORCING_EW2 and o.jvp_mode == abi.JVP_FINITE_DIFF and o.termination == nls.AbsNormTerminationMode().code
+    o = _opts(nls, nls.Broyden(init_jacobian="true_jacobian", update_rule="bad_broyden", max_resets=7, reset_tolerance=1e-9, alpha=0.5))
+    assert (o.descent, o.qn_init_jacobian, o.qn_update_rule, o.qn_max_resets, o.qn_reset_tolerance, o.qn_alpha, o.linsolve) == (
+        abi.DESCENT_BROYDEN, abi.QN_INIT_TRUE_JACOBIAN, abi.QN_UPDATE_BAD_BROYDEN, 7, 1e-9, 0.5, abi.LINSOLVE_DENSE_LU)
+    o = _opts(nls, nls.Broyden())
+    assert (o.descent, o.qn_init_jacobian, o.qn_update_rule, o.qn_max_resets, o.qn_reset_tolerance, o.qn_alpha) == (abi.DESCENT_BROYDEN, 0, 0, 100, 0.0, 0.0)
+    assert nls.ReturnCode.name(nls.ReturnCode.ConvergenceFailure) == "ConvergenceFailure"
+    with pytest.raises(ValueError):
+        nls.Broyden(update_rule="diagonal")
     with pytest.raises(TypeError):
         _opts(nls, nls.NewtonRaphson(linsolve=object()))
 
