@@ -392,6 +392,43 @@ __global__ void __launch_bounds__(GM_THREADS) dense_gemv_kernel(int trans, int64
     }
   }
 }
+// y = A' x for a TALL, SKINNY A (m rows >> n <= TG_NC columns: the n x threshold factors of LimitedMemoryBroyden): every CTA takes a
+// row range and all columns in one pass (x read once), partials summed in a fixed order by a second kernel — deterministic, no atomics
+constexpr int TG_NC = 16;
+__global__ void __launch_bounds__(GM_THREADS) tall_gemvt_partial_kernel(int64_t m, int nc, const double* __restrict__ A, int64_t ld, const double* __restrict__ x,
+                                                                         double* __restrict__ partial) {
+  __shared__ double red[GM_THREADS / 32][TG_NC];
+  const int G = gridDim.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t per = (m + G - 1) / G, r0 = (int64_t)blockIdx.x * per, r1 = min(m, r0 + per);
+  double acc[TG_NC];
+#pragma unroll
+  for (int c = 0; c < TG_NC; ++c) acc[c] = 0.0;
+  for (int64_t r = r0 + threadIdx.x; r < r1; r += GM_THREADS) {
+    const double xr = x[r];
+#pragma unroll
+    for (int c = 0; c < TG_NC; ++c)
+      if (c < nc) acc[c] = fma(A[(int64_t)c * ld + r], xr, acc[c]);
+  }
+#pragma unroll
+  for (int c = 0; c < TG_NC; ++c) acc[c] = warp_sum(acc[c]);
+  if (lane == 0) {
+#pragma unroll
+    for (int c = 0; c < TG_NC; ++c) red[wid][c] = acc[c];
+  }
+  __syncthreads();
+  if (threadIdx.x < nc) {
+    double s = 0.0;
+    for (int q = 0; q < GM_THREADS / 32; ++q) s += red[q][threadIdx.x];
+    partial[(int64_t)threadIdx.x * G + blockIdx.x] = s;
+  }
+}
+__global__ void tall_gemvt_final_kernel(int nc, int G, const double* __restrict__ partial, double* __restrict__ y) {
+  const int c = threadIdx.x;
+  if (c >= nc) return;
+  double s = 0.0;
+  for (int g = 0; g < G; ++g) s += partial[(int64_t)c * G + g];
+  y[c] = s;
+}
 // =====================================================================================================================
 // Resident Arnoldi step (engine B200_ENGINE_RESIDENT): ONE cooperative kernel per Arnoldi iteration for the built-in
 // Brusselator operators (or an assembled sparse Jacobian through its CSR view).  One CTA per SM; CTA b owns the cells
@@ -1049,6 +1086,13 @@ int32_t b200_gemv(b200_ctx* ctx, int32_t trans, int64_t m, int64_t n, const doub
   B200_DEVICE_GUARD(ctx);
   if (!trans) {
     LAUNCH(ctx, dense_gemv_kernel, (int)((m + GM_THREADS - 1) / GM_THREADS), GM_THREADS, 0, 0, m, n, A, ld, x, y);
+  } else if (n <= 64 && m >= 32768) {  // tall and skinny: all columns in one pass over the rows, TG_NC columns at a time
+    const int G = (int)std::min<int64_t>(512, (m + 4095) / 4096);
+    for (int64_t c0 = 0; c0 < n; c0 += TG_NC) {
+      const int nc = (int)std::min<int64_t>(TG_NC, n - c0);
+      LAUNCH(ctx, tall_gemvt_partial_kernel, G, GM_THREADS, 0, m, nc, A + c0 * ld, ld, x, ctx->d_partials);
+      LAUNCH(ctx, tall_gemvt_final_kernel, 1, 32, 0, nc, G, (const double*)ctx->d_partials, y + c0);
+    }
   } else {
     LAUNCH(ctx, dense_gemv_kernel, (int)std::min<int64_t>(n, 4096), GM_THREADS, 0, 1, m, n, A, ld, x, y);
   }

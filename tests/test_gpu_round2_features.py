@@ -219,3 +219,23 @@ def test_ensemble_trajectories_that_outgrow_the_basis_slab_are_not_truncated(nls
     assert np.abs(us - uo).max() <= 1e-6 * np.abs(uo).max()
     assert np.all(np.abs(small.nj.to_host() - njo) <= 2 * nso)
     assert small.resid.to_host().max() < 1e-8
+
+
+def test_limited_memory_broyden_at_scale_vs_numpy(nls, ctx):
+    """LimitedMemoryBroyden on 2*10^5 unknowns (the tall-skinny products with the n x threshold factors; threshold 4, so the circular
+    buffer wraps) against the NumPy restatement: same number of steps, residual history and root."""
+    from oracle import newton_numpy as nn
+    n = 200_000
+    u0 = np.linspace(0.6, 3.0, n)
+    # abstol 1e-7: the solve ends (9 steps) before any component of du reaches the reset tolerance eps^(3/4), whose <= test is
+    # decided by the last bit
+    ref = nn.solve_broyden(nn.Quadratic(n, 2.0), u0, init_jacobian="low_rank", threshold=4, max_resets=3, termination=nn.Termination(abstol=1e-7), maxiters=100)
+    sol = nls.solve(nls.NonlinearProblem(nls.QuadraticFunction(n), u0, 2.0, ctx=ctx), nls.LimitedMemoryBroyden(threshold=4), abstol=1e-7, maxiters=100)
+    assert sol.retcode == ref["retcode"] == nls.ReturnCode.Success
+    assert sol.stats.nsteps == ref["nsteps"] and sol.stats.nf == ref["nf"]
+    fn = np.array([t.fnorm_inf for t in sol.trace])
+    big = np.array(ref["fnorm_inf"]) > 1e-6 * max(ref["fnorm_inf"])
+    assert np.allclose(fn[big], np.array(ref["fnorm_inf"])[big], rtol=1e-7)
+    u = sol.u.to_host() if hasattr(sol.u, "to_host") else np.asarray(sol.u)
+    assert ref["nsteps"] == 9 and ref["nresets"] == 0
+    assert np.abs(u - np.sqrt(2.0)).max() < 1e-7 and np.abs(u - ref["u"]).max() < 1e-10
