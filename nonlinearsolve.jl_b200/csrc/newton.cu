@@ -794,9 +794,10 @@ static int32_t newton_step_inner(b200_newton* nw) {
           B200_TRY(b200_axpby(ctx, n, d_cauchy / l_grad, nw->du_c, 0.0, nw->c1));  // c1 = (d_cauchy/l_grad) du_c
           B200_TRY(b200_copy(ctx, n, nw->du, nw->c2));
           B200_TRY(b200_axpy(ctx, n, -1.0, nw->c1, nw->c2));                         // c2 = du_newton - c1
-          double a, b2;
-          B200_TRY(h_dot(nw, nw->c2, nw->c2, &a));
-          B200_TRY(h_dot(nw, nw->c1, nw->c2, &b2));
+          B200_TRY(b200i_reduce_sum_dev(ctx, n, nw->c2, nw->c2, RED_DOT, ctx->d_scalars));
+          B200_TRY(b200i_reduce_sum_dev(ctx, n, nw->c1, nw->c2, RED_DOT, ctx->d_scalars + 1));
+          B200_TRY(b200i_fetch_scalars(ctx, 2));
+          const double a = ctx->h_scalars[0], b2 = ctx->h_scalars[1];
           const double b = 2.0 * b2, c = d_cauchy * d_cauchy - nw->trust_region * nw->trust_region;
           const double aux = std::max(0.0, b * b - 4.0 * a * c);
           const double tau = (-b + sqrt(aux)) / (2.0 * a);
@@ -879,23 +880,27 @@ static int32_t newton_step_inner(b200_newton* nw) {
       CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_scalars, 0, sizeof(double) * 2, ctx->stream));
       B200_TRY(b200i_residual_norm(nw->prob, nw->u_trial, nw->fu_trial, ctx->d_scalars));
       nw->res.nf += 1;
-      B200_TRY(b200i_fetch_scalars(ctx, 1));
-      const double trial_inf = ctx->h_scalars[0];
-      if (dJJd != dJJd) {
+      // the six scalars of the acceptance test are independent: reduced on the device one after the other, fetched ONCE
+      // (round 1 synchronised the host after each of them)
+      const bool need_dJJd = dJJd != dJJd;
+      if (need_dJJd) {
         B200_TRY(b200_jvp(nw->prob, nw->u, nw->du, nw->Jdu));
-        B200_TRY(h_dot(nw, nw->Jdu, nw->Jdu, &dJJd));
+        B200_TRY(b200i_reduce_sum_dev(ctx, n, nw->Jdu, nw->Jdu, RED_DOT, ctx->d_scalars + 1));
       }
       B200_TRY(b200_vjp(nw->prob, nw->u, nw->fu, nw->JTfu));
-      double nt, nc, dg;
-      B200_TRY(h_nrm2(nw, nw->fu_trial, &nt));
-      B200_TRY(h_nrm2(nw, nw->fu, &nc));
-      B200_TRY(h_dot(nw, nw->du, nw->JTfu, &dg));
+      B200_TRY(b200i_reduce_sum_dev(ctx, n, nw->fu_trial, nullptr, RED_SUMSQ, ctx->d_scalars + 2));
+      B200_TRY(b200i_reduce_sum_dev(ctx, n, nw->fu, nullptr, RED_SUMSQ, ctx->d_scalars + 3));
+      B200_TRY(b200i_reduce_sum_dev(ctx, n, nw->du, nw->JTfu, RED_DOT, ctx->d_scalars + 4));
+      B200_TRY(b200i_reduce_sum_dev(ctx, n, nw->du, nullptr, RED_SUMSQ, ctx->d_scalars + 5));
+      B200_TRY(b200i_fetch_scalars(ctx, 6));
+      const double trial_inf = ctx->h_scalars[0];
+      if (need_dJJd) dJJd = ctx->h_scalars[1];
+      const double nt = sqrt(ctx->h_scalars[2]), nc = sqrt(ctx->h_scalars[3]), dg = ctx->h_scalars[4];
       const double num = (nt * nt - nc * nc) / 2.0;
       const double denom = dg + dJJd / 2.0;
       const double rho = num / denom;
       accepted = rho > step_thr;
-      double dun;  // internalnorm(du)
-      B200_TRY(h_nrm2(nw, nw->du, &dun));
+      const double dun = sqrt(ctx->h_scalars[5]);  // internalnorm(du)
       double& tr = nw->trust_region;
       if (sch == B200_TR_SIMPLE) {  // trust_region.jl:431-440
         if (rho < shrink_thr) { tr *= shrink_fac; nw->shrink_counter += 1; }
