@@ -147,6 +147,22 @@ def cpu_sample(N, steps, count, orth="mgs"):
     return times, cores, sample, k0
 
 
+def cpu_single_thread(N, orth="mgs"):
+    """the CPU restatement single-threaded as well (the reference's Brusselator loop and Krylov.jl's BLAS-1 calls on
+    `Array`s are effectively serial): ONE Arnoldi iteration at the mean basis size, best of two."""
+    from oracle import pyoracle as po
+    P = po.OracleProblem.bruss3d(N)
+    u = P.u0(1)
+    k0 = MEAN_BASIS.get(N, max(8, int(3.45 * N)))
+    nthreads = po.get_threads()
+    po.set_threads(1)
+    try:
+        t = min(po.arnoldi_sample(P, u, k0, 1, po.ORTH_MGS if orth == "mgs" else po.ORTH_CGS2) for _ in range(2))
+    finally:
+        po.set_threads(nthreads)
+    return 1.0 / t
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path (oracle port), bounded sample per step."""
     rank = int(os.environ.get("RANK", "0"))
@@ -571,7 +587,8 @@ def run_b200(args):
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches_all),
             "roofline": roofline,
-            "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                             "single_thread_value": cpu_single_thread(N, args.orth) if world == 1 else None},
             "clocks": clk,
             "ensemble": ens,
             "resid_inf": sol.resid_inf, "retcode": nls.ReturnCode.name(sol.retcode)}
