@@ -624,42 +624,70 @@ __device__ __forceinline__ void r3_apply_operator(const ResidentParams& P, const
   const int tid = threadIdx.x;
   const double* vk = P.V[P.k - 1];
   const int N = P.N;
-  const int64_t N2 = (int64_t)N * N, NC = P.NC;
+  const int64_t NC = P.NC;
   const int ncell = cx.ncell, nrow = cx.nrow;
   const int64_t c0 = (int64_t)cx.b * P.cpc;
+  if (P.opkind == 1) {  // assembled sparse matrix through its CSR view: a gather per row
 #pragma unroll
-  for (int qq = 0; qq < R3_ROWS; ++qq) {
-    const int lr = 2 * (tid + R3_THREADS * (qq >> 1)) + (qq & 1);
-    w[qq] = 0.0;
-    if (lr < nrow && P.opkind == 1) {
-      const int s = lr >= ncell;
-      const int64_t r = (int64_t)s * NC + c0 + (lr - s * ncell);
-      double acc = 0.0;
-      for (int64_t e = P.rowptr[r], e1 = P.rowptr[r + 1]; e < e1; ++e) acc = fma(P.nzval[P.csr_map[e]], vk[P.csr_col[e]], acc);
-      w[qq] = acc;
-    } else if (lr < nrow) {
-      const int s = lr >= ncell;
-      const int64_t c = c0 + (lr - s * ncell);
-      int64_t cim, cip, cjm, cjp, ckm = 0, ckp = 0;
-      if (P.dim == 3) {
-        const int kk = (int)(c / N2);
-        const int r = (int)(c - (int64_t)kk * N2);
-        const int j = r / N, i = r - j * N;
-        cim = c + ((i == 0) ? (N - 1) : -1); cip = c + ((i + 1 == N) ? -(N - 1) : 1);
-        cjm = c + ((j == 0) ? (int64_t)(N - 1) * N : -N); cjp = c + ((j + 1 == N) ? -(int64_t)(N - 1) * N : N);
-        ckm = c + ((kk == 0) ? (int64_t)(N - 1) * N2 : -N2); ckp = c + ((kk + 1 == N) ? -(int64_t)(N - 1) * N2 : N2);
-      } else {
-        const int j = (int)(c / N), i = (int)(c - (int64_t)j * N);
-        cim = c + ((i == 0) ? (N - 1) : -1); cip = c + ((i + 1 == N) ? -(N - 1) : 1);
-        cjm = c + ((j == 0) ? (int64_t)(N - 1) * N : -N); cjp = c + ((j + 1 == N) ? -(int64_t)(N - 1) * N : N);
+    for (int qq = 0; qq < R3_ROWS; ++qq) {
+      const int lr = 2 * (tid + R3_THREADS * (qq >> 1)) + (qq & 1);
+      w[qq] = 0.0;
+      if (lr < nrow) {
+        const int s = lr >= ncell;
+        const int64_t r = (int64_t)s * NC + c0 + (lr - s * ncell);
+        double acc = 0.0;
+        for (int64_t e = P.rowptr[r], e1 = P.rowptr[r + 1]; e < e1; ++e) acc = fma(P.nzval[P.csr_map[e]], vk[P.csr_col[e]], acc);
+        w[qq] = acc;
       }
-      const double* x = vk + (int64_t)s * NC;
-      const double xc = x[c];
-      double lap = x[cim] + x[cip] + x[cjp] + x[cjm] - 4.0 * xc;
-      if (P.dim == 3) lap = lap + (x[ckp] + x[ckm] - 2.0 * xc);
-      const double uc = P.u[c], vc = P.u[c + NC], dc = vk[c], ec = vk[c + NC];
-      const double uv2 = 2.0 * uc * vc, uu = uc * uc;
-      w[qq] = s ? (P.a * lap + (P.A - uv2) * dc - uu * ec) : (P.a * lap + (uv2 - (P.A + 1.0)) * dc + uu * ec);
+    }
+    return;
+  }
+  // Built-in Brusselator J(u) v, a PAIR of neighbouring cells per step (the pair never straddles a grid row: the cell count per
+  // CTA and N are even), 16-byte loads for everything but the two i-neighbours outside the pair.  Cell coordinates come from two
+  // multiplications by reciprocals, exact for these ranges ((c + 1/2) / d is never within 2^-21 of an integer, the product's error
+  // is < 2^-40).  Late round 2: this block used an int64 and an int32 division PER ROW — 13 500 instructions per warp executed
+  // once per launch, 3.8 % of the stall samples of a k = 513 launch, ~100 us of every Arnoldi step whatever the basis size.
+  const int N2 = N * N, c0i = (int)c0;
+  const double invN = 1.0 / (double)N, invN2 = 1.0 / (double)N2;
+  const bool d3 = P.dim == 3;
+  const double* __restrict__ uu_ = P.u;
+#pragma unroll
+  for (int q = 0; q < R3_RP; ++q) {
+    const int lr = 2 * (tid + R3_THREADS * q);
+    w[2 * q] = 0.0;
+    w[2 * q + 1] = 0.0;
+    if (lr < nrow) {
+      const int s = lr >= ncell;
+      const int c = c0i + (lr - s * ncell);  // even
+      int i, j, kk = 0;
+      if (d3) {
+        kk = (int)(((double)c + 0.5) * invN2);
+        const int r = c - kk * N2;
+        j = (int)(((double)r + 0.5) * invN);
+        i = r - j * N;
+      } else {
+        j = (int)(((double)c + 0.5) * invN);
+        i = c - j * N;
+      }
+      const double* x = vk + (int64_t)s * NC + c;
+      const double2 xc = *reinterpret_cast<const double2*>(x);
+      const double xl = x[(i == 0) ? (N - 1) : -1];
+      const double xr = x[(i + 2 == N) ? (2 - N) : 2];
+      const int ojm = (j == 0) ? (N - 1) * N : -N, ojp = (j + 1 == N) ? -(N - 1) * N : N;
+      const double2 xjm = *reinterpret_cast<const double2*>(x + ojm), xjp = *reinterpret_cast<const double2*>(x + ojp);
+      double lap0 = xl + xc.y + xjp.x + xjm.x - 4.0 * xc.x;
+      double lap1 = xc.x + xr + xjp.y + xjm.y - 4.0 * xc.y;
+      if (d3) {
+        const int okm = (kk == 0) ? (N - 1) * N2 : -N2, okp = (kk + 1 == N) ? -(N - 1) * N2 : N2;
+        const double2 xkm = *reinterpret_cast<const double2*>(x + okm), xkp = *reinterpret_cast<const double2*>(x + okp);
+        lap0 = lap0 + (xkp.x + xkm.x - 2.0 * xc.x);
+        lap1 = lap1 + (xkp.y + xkm.y - 2.0 * xc.y);
+      }
+      const double2 u2 = *reinterpret_cast<const double2*>(uu_ + c), v2 = *reinterpret_cast<const double2*>(uu_ + NC + c);
+      const double2 d2 = *reinterpret_cast<const double2*>(vk + c), e2 = *reinterpret_cast<const double2*>(vk + NC + c);
+      const double uv0 = 2.0 * u2.x * v2.x, uu0 = u2.x * u2.x, uv1 = 2.0 * u2.y * v2.y, uu1 = u2.y * u2.y;
+      w[2 * q] = s ? (P.a * lap0 + (P.A - uv0) * d2.x - uu0 * e2.x) : (P.a * lap0 + (uv0 - (P.A + 1.0)) * d2.x + uu0 * e2.x);
+      w[2 * q + 1] = s ? (P.a * lap1 + (P.A - uv1) * d2.y - uu1 * e2.y) : (P.a * lap1 + (uv1 - (P.A + 1.0)) * d2.y + uu1 * e2.y);
     }
   }
 }
