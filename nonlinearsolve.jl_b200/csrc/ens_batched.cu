@@ -29,6 +29,7 @@ constexpr int NPT = 8;    // max rows per thread  -> n <= 2048 (N <= 32)
 
 struct EnsParams {
   int N, n, nprob, maxiters, itmax, kcap, passes, term_mode, forcing, ew_safeguard;
+  int walk_di, walk_dj;  // ET mod N, ET div N (row walk of the stencil functions)
   double a, abstol, gm_atol, gm_rtol;
   double ew_eta0, ew_eta_max, ew_gamma, ew_alpha, ew_safeguard_threshold;
   int64_t slab;  // doubles per CTA workspace slab
@@ -71,17 +72,35 @@ __device__ __forceinline__ void sym_givens_e(double a, double b, double& c, doub
   else { const double t = b / a; c = (a > 0 ? 1.0 : -1.0) / sqrt(1.0 + t * t); s = c * t; rho = a / c; }
 }
 
+// Grid coordinates (i, j) and species s of this thread's rows r = tid + ET q without a division per row: one division for q = 0, then
+// the walk r += ET advances (i, j) by (ET mod N, ET div N) with carries; j wrapping past N is the species boundary (r >= N^2).
+#define ENS_ROW_WALK_BEGIN(P, N, NC)                                                      \
+  int rw_s = (int)threadIdx.x >= (NC), rw_j, rw_i;                                         \
+  {                                                                                        \
+    const int c_ = (int)threadIdx.x - rw_s * (NC);                                         \
+    rw_j = c_ / (N);                                                                       \
+    rw_i = c_ - rw_j * (N);                                                                \
+    while (rw_j >= (N)) { rw_j -= (N); ++rw_s; }                                           \
+  }
+#define ENS_ROW_WALK_STEP(q, N)                                                            \
+  if ((q) > 0) {                                                                           \
+    rw_i += P.walk_di; rw_j += P.walk_dj;                                                  \
+    if (rw_i >= (N)) { rw_i -= (N); ++rw_j; }                                              \
+    while (rw_j >= (N)) { rw_j -= (N); ++rw_s; }                                           \
+  }
 // residual rows of this thread from the shared-memory iterate (brusselator_2d_loop, sparsity_tests__item1.jl:13-36)
 __device__ __forceinline__ void ens_residual(const EnsParams& P, double A, double B, const double* __restrict__ us,
                                              const double* __restrict__ forcing, double (&f)[NPT]) {
   const int N = P.N, NC = N * N;
+  ENS_ROW_WALK_BEGIN(P, N, NC)
 #pragma unroll
   for (int q = 0; q < NPT; ++q) {
     const int r = threadIdx.x + ET * q;
     f[q] = 0.0;
+    ENS_ROW_WALK_STEP(q, N)
     if (r < P.n) {
-      const int s = r >= NC, c = r - s * NC;
-      const int i = c % N, j = c / N;
+      const int s = rw_s, c = r - s * NC;
+      const int i = rw_i, j = rw_j;
       const int ip = (i + 1 == N) ? 0 : i + 1, im = (i == 0) ? N - 1 : i - 1;
       const int jp = (j + 1 == N) ? 0 : j + 1, jm = (j == 0) ? N - 1 : j - 1;
       const double* x = us + s * NC;
@@ -96,13 +115,15 @@ __device__ __forceinline__ void ens_residual(const EnsParams& P, double A, doubl
 __device__ __forceinline__ void ens_jvp(const EnsParams& P, double A, const double* __restrict__ us, const double* __restrict__ ds,
                                         double (&w)[NPT]) {
   const int N = P.N, NC = N * N;
+  ENS_ROW_WALK_BEGIN(P, N, NC)
 #pragma unroll
   for (int q = 0; q < NPT; ++q) {
     const int r = threadIdx.x + ET * q;
     w[q] = 0.0;
+    ENS_ROW_WALK_STEP(q, N)
     if (r < P.n) {
-      const int s = r >= NC, c = r - s * NC;
-      const int i = c % N, j = c / N;
+      const int s = rw_s, c = r - s * NC;
+      const int i = rw_i, j = rw_j;
       const int ip = (i + 1 == N) ? 0 : i + 1, im = (i == 0) ? N - 1 : i - 1;
       const int jp = (j + 1 == N) ? 0 : j + 1, jm = (j == 0) ? N - 1 : j - 1;
       const double* x = ds + s * NC;
@@ -378,6 +399,7 @@ int32_t b200i_ens_batched_solve(b200_ctx* ctx, int32_t N, int32_t nprob, double 
   EnsParams P;
   memset(&P, 0, sizeof(P));
   P.N = N; P.n = 2 * N * N; P.nprob = nprob;
+  P.walk_di = ET % N; P.walk_dj = ET / N;
   P.npad = (P.n + 1) & ~1;
   P.maxiters = o->maxiters > 0 ? o->maxiters : 1000;
   P.abstol = o->abstol > 0 ? o->abstol : 3.0e-13;
