@@ -146,7 +146,7 @@ typedef struct b200_gmres_opts {
   int32_t orth;       /* B200_ORTH_* ; MGS = Krylov.jl default (reorthogonalization=false) */
   int32_t warm_start; /* 0: x0 = 0 ; 1: x_inout holds the initial guess */
   int32_t engine;     /* B200_ENGINE_* */
-  int32_t check_every;/* host polls the device status every this many Arnoldi iterations (multi-kernel engine); 0 => 8 */
+  int32_t check_every;/* host polls the device status every this many Arnoldi iterations (multi-kernel engine); 0 => 8 (2 with a preconditioner) */
   int32_t block;      /* reserved, must be 0 (round 1 offered an L2-blocked Gram-Schmidt here: measured 2x slower than the
                          streaming kernels on B200 and removed) */
   double atol;

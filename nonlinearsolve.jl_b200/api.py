@@ -353,7 +353,7 @@ class KrylovJL_GMRES:
 
     needs_concrete_A = False
 
-    def __init__(self, gmres_restart=0, memory=20, itmax=0, orth="cgs2", warm_start=False, atol=None, rtol=None, check_every=8,
+    def __init__(self, gmres_restart=0, memory=20, itmax=0, orth="cgs2", warm_start=False, atol=None, rtol=None, check_every=None,
                  engine="auto", block=0, precs=None):
         # precs: LinearSolve's `precs = (A, p) -> (Pl, Pr)`; here a BlockJacobi(side) descriptor of the built-in preconditioner
         self.precs = precs
@@ -366,7 +366,7 @@ class KrylovJL_GMRES:
         g.orth = {"mgs": abi.ORTH_MGS, "cgs": abi.ORTH_CGS, "cgs2": abi.ORTH_CGS2}[self.orth]
         g.warm_start = 1 if self.warm_start else 0
         g.engine = {"auto": abi.ENGINE_AUTO, "multikernel": abi.ENGINE_MULTIKERNEL, "resident": abi.ENGINE_RESIDENT}[self.engine]
-        g.check_every = int(self.check_every)
+        g.check_every = int(self.check_every) if self.check_every is not None else 0  # 0: the library's default (8; 2 with a preconditioner)
         g.block = int(self.block)
         g.atol = float(self.atol) if self.atol is not None else 0.0
         g.rtol = float(self.rtol) if self.rtol is not None else 0.0

@@ -1214,7 +1214,7 @@ void b200_gmres_opts_default(b200_gmres_opts* o) {
   o->orth = B200_ORTH_CGS2;
   o->warm_start = 0;
   o->engine = B200_ENGINE_AUTO;
-  o->check_every = 8;
+  o->check_every = 0;  // 0 => 8, or 2 when a preconditioner is attached (see b200_gmres_solve)
   o->atol = 0.0;
   o->rtol = 1.4901161193847656e-08;  // sqrt(eps): Krylov.jl default rtol
 }
@@ -1343,7 +1343,9 @@ int32_t b200_gmres_solve(b200_gmres* gm, b200_linop* op, const double* b, double
   // handed the operand of an iteration that a finished solve skipped: poll the device status every iteration for them
   const bool host_op = op->kind == LINOP_CALLBACK || (op->kind == LINOP_PROBLEM && op->prob->kind == B200_PROB_CALLBACK) ||
                        (gm->Pl && gm->Pl->kind == LINOP_CALLBACK) || (gm->Pr && gm->Pr->kind == LINOP_CALLBACK);
-  const int check_every = host_op ? 1 : (o.check_every > 0 ? o.check_every : 8);
+  // with a preconditioner an iteration is expensive (a V-cycle per step) and the basis short: iterations enqueued after
+  // convergence still run the preconditioner's kernels, so the status is polled every other step (default 8 otherwise)
+  const int check_every = host_op ? 1 : (o.check_every > 0 ? o.check_every : ((gm->Pl || gm->Pr) ? 2 : 8));
   // resident engine: built-in Brusselator operator with the exact JVP (or an assembled sparse Jacobian), even cell count, one
   // CTA per SM holds its rows: <= 54 rows per thread and two shared-memory stages + the register stage's annex must fit
   bool resident = false;

@@ -161,6 +161,13 @@ struct b200_mg {
   double omega;
   MgLevel lev[MG_MAX_LEVELS];
   std::vector<double*> owned;
+  // One application = ~60 launches on grids of 10^6 down to ONE cell: 1.7 us of GPU time each, but ~5 us of host time to enqueue —
+  // a preconditioned solve was host-bound (5 100 launches, 56 ms wall for 18 ms of GPU work).  The V-cycle is captured once per
+  // linearisation point into a CUDA graph (fixed input = lev[0].b, fixed result buffer) and replayed with one launch per application.
+  cudaGraphExec_t gexec = nullptr;
+  double* gres = nullptr;       // where the captured cycle leaves its result
+  int64_t glaunches = 0;        // kernel launches inside the captured cycle (for the launch counter)
+  bool graph_unavailable = false;
 };
 
 namespace {
@@ -248,6 +255,7 @@ int32_t b200i_mg_create(b200_problem* prob, b200_mg** out) {
 int32_t b200i_mg_destroy(b200_mg* mg) {
   if (!mg) return B200_OK;
   cudaStreamSynchronize(mg->ctx->stream);
+  if (mg->gexec) cudaGraphExecDestroy(mg->gexec);
   for (double* p : mg->owned) cudaFree(p);
   delete mg;
   return B200_OK;
@@ -263,14 +271,46 @@ int32_t b200i_mg_setup(b200_mg* mg, const double* u) {
     LAUNCH(ctx, mg_restrict_kernel, mg_grid(Cl.NC), MG_THREADS, 0, L.N, Cl.N, L.dim, L.ratio, (const double*)L.state, Cl.state);
   }
   CHECK_LAUNCH(ctx);
+  // the captured cycle has the level states' addresses and values baked in as of its capture: a new linearisation point needs a new one
+  if (mg->gexec) { CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)); cudaGraphExecDestroy(mg->gexec); mg->gexec = nullptr; }
   return B200_OK;
 }
 
 int32_t b200i_mg_apply(b200_mg* mg, const double* x, double* y) {
   b200_ctx* ctx = mg->ctx;
+  const size_t bytes = sizeof(double) * 2 * mg->lev[0].NC;
+  if (!mg->gexec && !mg->graph_unavailable && !ctx->prof_on) {
+    cudaGraph_t graph = nullptr;
+    const int64_t l0 = ctx->launches;
+    double* res = nullptr;
+    if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+      const int32_t rc = mg_vcycle(mg, 0, mg->lev[0].b, &res);
+      const cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+      if (rc == B200_OK && e == cudaSuccess && graph && cudaGraphInstantiate(&mg->gexec, graph, 0) == cudaSuccess) {
+        mg->gres = res;
+        mg->glaunches = ctx->launches - l0;
+      } else {
+        mg->gexec = nullptr;
+        mg->graph_unavailable = true;
+        cudaGetLastError();
+      }
+      if (graph) cudaGraphDestroy(graph);
+      ctx->launches = l0;  // nothing ran yet
+    } else {
+      mg->graph_unavailable = true;
+      cudaGetLastError();
+    }
+  }
+  if (mg->gexec) {
+    CUDA_TRY(ctx, cudaMemcpyAsync(mg->lev[0].b, x, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaGraphLaunch(mg->gexec, ctx->stream));
+    ctx->launches += mg->glaunches;
+    CUDA_TRY(ctx, cudaMemcpyAsync(y, mg->gres, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    return B200_OK;
+  }
   double* res = nullptr;
   B200_TRY(mg_vcycle(mg, 0, x, &res));
-  CUDA_TRY(ctx, cudaMemcpyAsync(y, res, sizeof(double) * 2 * mg->lev[0].NC, cudaMemcpyDeviceToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(y, res, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
   return B200_OK;
 }
 
