@@ -161,8 +161,8 @@ struct b200_mg {
   double omega;
   MgLevel lev[MG_MAX_LEVELS];
   std::vector<double*> owned;
-  // One application = ~60 launches on grids of 10^6 down to ONE cell: 1.7 us of GPU time each, but ~5 us of host time to enqueue —
-  // a preconditioned solve was host-bound (5 100 launches, 56 ms wall for 18 ms of GPU work).  The V-cycle is captured once per
+  // One application = ~60 launches on grids of 10^6 down to ONE cell: a few us of GPU time each (0.44 ms in all), but ~5 us of host
+  // time to enqueue every one — a preconditioned solve was host-bound (5 100 launches per config-3 solve).  The V-cycle is captured once per
   // linearisation point into a CUDA graph (fixed input = lev[0].b, fixed result buffer) and replayed with one launch per application.
   cudaGraphExec_t gexec = nullptr;
   double* gres = nullptr;       // where the captured cycle leaves its result
