@@ -118,3 +118,16 @@ def test_cuda_driver_reproduces_the_numpy_sequences(nls, ctx, d):
         assert [t.lin_status for t in sol.trace] == e["reset"][:len(sol.trace)], c["name"]
     if "descent_ok" in e:   # Levenberg-Marquardt: the geodesic-acceleration verdict of every step (trace slot lin_status)
         assert [t.lin_status for t in sol.trace] == e["descent_ok"], c["name"]
+
+
+def test_broyden_restatement_meets_the_reference_anchor():
+    """NonlinearSolveQuasiNewton/test/core_tests__item1.jl:36-44 and core_tests__item7.jl: Broyden (both initialisations, both full-structure
+    update rules) and LimitedMemoryBroyden on quadratic_f(u) = u.^2 .- 2 from u0 = [1, 1] with abstol 1e-9: successful retcode and
+    maximum(abs, f(u)) < 1e-9 — the anchor the NumPy restatement (and through it the CUDA driver) is pinned on."""
+    from oracle import newton_numpy as nn
+    q = nn.Quadratic(2, 2.0)
+    for kw in (dict(), dict(update_rule="bad_broyden"), dict(init_jacobian="true_jacobian"), dict(init_jacobian="true_jacobian", update_rule="bad_broyden"),
+               dict(init_jacobian="low_rank", max_resets=3)):
+        r = nn.solve_broyden(q, np.ones(2), termination=nn.Termination(abstol=1e-9), **kw)
+        assert r["retcode"] == nn.RC["Success"], kw
+        assert np.max(np.abs(q.f(r["u"]))) < 1e-9 and np.allclose(r["u"], np.sqrt(2.0), atol=1e-9), kw
