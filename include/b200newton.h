@@ -105,7 +105,9 @@ enum { B200_QN_INIT_IDENTITY = 0, B200_QN_INIT_TRUE_JACOBIAN = 1, B200_QN_INIT_L
 /* init_jacobian = Val(:identity) | Val(:true_jacobian) (needs linsolve = DENSE_LU); LOW_RANK = LimitedMemoryBroyden(; threshold)
    (lbroyden.jl:20-35, initialization.jl:139-298): J^-1 = alpha I + U V' with the last `qn_threshold` rank-one updates kept in two
    n x threshold arrays (circular), any n */
-enum { B200_QN_UPDATE_GOOD_BROYDEN = 0, B200_QN_UPDATE_BAD_BROYDEN = 1 };
+enum { B200_QN_UPDATE_GOOD_BROYDEN = 0, B200_QN_UPDATE_BAD_BROYDEN = 1, B200_QN_UPDATE_KLEMENT = 2 };
+/* KLEMENT (klement.jl:30-49, 128-140): Klement() with its default init_jacobian = Val(:identity), i.e. a DIAGONAL approximate Jacobian
+   (an n-vector, any n): du = -f ./ J, J += ((df - J du) ./ (J^2 du^2)) .* du .* J^2, IllConditionedJacobianReset (any zero on the diagonal) */
 /* built-in preconditioners (LinearSolve `precs(A, p)`, large_systems.md:244-316): inverse of the 2x2 species blocks, or one
    geometric-multigrid V-cycle of the Brusselator Jacobian (the tutorial's AlgebraicMultigrid ruge_stuben / smoothed_aggregation) */
 enum { B200_PRECOND_NONE = 0, B200_PRECOND_BLOCK_JACOBI_LEFT = 1, B200_PRECOND_BLOCK_JACOBI_RIGHT = 2,

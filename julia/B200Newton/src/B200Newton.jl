@@ -534,7 +534,7 @@ const _LINSOLVE = (gmres = 0, dense_lu = 1, sparse_gmres = 2, sparse_lu = 3)
 const _GLOBALIZATION = (none = 0, trust_region = 1, linesearch = 2)
 const _DESCENT = (newton = 0, pseudo_transient = 1, levenberg_marquardt = 2, broyden = 3)
 const _QN_INIT = (identity = 0, true_jacobian = 1, low_rank = 2)
-const _QN_UPDATE = (good_broyden = 0, bad_broyden = 1)
+const _QN_UPDATE = (good_broyden = 0, bad_broyden = 1, klement = 2)
 const _TR_SCHEMES = (simple = 0, nlsolve = 1, nocedal_wright = 2, hei = 3, yuan = 4, fan = 5, bastin = 6)
 const _PRECS = (none = 0, block_jacobi_left = 1, block_jacobi_right = 2, multigrid_left = 3, multigrid_right = 4)
 const _TERMINATION = (abs_norm_safe_best = 0, abs_norm = 1, abs_norm_safe = 2, norm = 3, rel = 4, rel_norm = 5, abs = 6,

@@ -602,6 +602,17 @@ class LimitedMemoryBroyden(Broyden):
         self.qn["qn_threshold"] = int(threshold)
 
 
+class Klement(Broyden):
+    """Klement(; max_resets = 100, alpha = nothing, init_jacobian = Val(:identity))  NonlinearSolveQuasiNewton/src/klement.jl:30-49 — with
+    the default initialisation the approximate Jacobian has the DIAGONAL structure: an n-vector, elementwise descent and update, any n.
+    (`init_jacobian = true_jacobian / true_jacobian_diagonal` are not offered.)"""
+    name = "Klement"
+
+    def __init__(self, max_resets=100, alpha=None):
+        super().__init__(max_resets=max_resets, init_jacobian="identity", alpha=alpha)
+        self.qn["qn_update_rule"] = abi.QN_UPDATE_KLEMENT
+
+
 class RadiusUpdateSchemes:
     """RadiusUpdateSchemes.{Simple, NLsolve, NocedalWright, Hei, Yuan, Fan, Bastin}  (trust_region.jl:431-520)."""
     Simple, NLsolve, NocedalWright, Hei, Yuan, Fan, Bastin = (abi.TR_SIMPLE, abi.TR_NLSOLVE, abi.TR_NOCEDAL_WRIGHT, abi.TR_HEI, abi.TR_YUAN, abi.TR_FAN, abi.TR_BASTIN)

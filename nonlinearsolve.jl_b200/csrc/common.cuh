@@ -228,6 +228,8 @@ int32_t b200i_diag_shift(b200_ctx* ctx, int64_t n, double* A, int64_t ld, double
 // column-pivoted Householder QR solve of a (possibly rank-deficient) dense system: the rescue of a singular LU
 int32_t b200i_qrcp_solve(b200_ctx* ctx, int64_t n, double* A, int64_t ld, double* b, double* x, double* work, int32_t* jpvt_dev, int32_t* rank_host);
 int32_t b200i_gram(b200_ctx* ctx, int64_t n, const double* J, int64_t ld, double* C, int64_t ldc);          // C = J' J
+int32_t b200i_klement_descent(b200_ctx* ctx, int64_t n, const double* J, const double* fu, double* du);                       // du = -fu ./ J
+int32_t b200i_klement_update(b200_ctx* ctx, int64_t n, double* J, const double* fu, double* fu_cache, const double* du);       // Klement's diagonal rule; fu_cache = fu
 int32_t b200i_ger(b200_ctx* ctx, int64_t n, double* A, int64_t ld, const double* c, const double* w);              // A += c w'
 int32_t b200i_scaled_identity(b200_ctx* ctx, int64_t n, double* A, int64_t ld, double d);                          // A = d I
 int32_t b200i_lm_damp(b200_ctx* ctx, int64_t n, double* C, int64_t ldc, double* dtd, double lambda);     // dtd = max(dtd, diag C); C += lambda diag(dtd)

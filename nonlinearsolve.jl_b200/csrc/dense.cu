@@ -775,6 +775,39 @@ __global__ void __launch_bounds__(256) scaled_identity_kernel(int64_t n, double*
   if (i < n) A[j * ld + i] = (i == j) ? d : 0.0;
 }
 }  // namespace
+namespace {
+// Klement with a diagonal approximate Jacobian: everything is elementwise
+__global__ void __launch_bounds__(256) klement_descent_kernel(int64_t n, const double* __restrict__ J, const double* __restrict__ fu, double* __restrict__ du) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) du[i] = -(fu[i] / J[i]);   // J \ fu for a Diagonal, then @. du *= -1
+}
+__global__ void __launch_bounds__(256) klement_update_kernel(int64_t n, double* __restrict__ J, const double* __restrict__ fu, double* __restrict__ fu_cache,
+                                                             const double* __restrict__ du) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double j = J[i], d = du[i], f = fu[i];
+  // The numerator f - f_prev - J du cancels to rounding level near the root and is then divided by J^2 du^2 ~ 1e-15: the rule is
+  // ill-conditioned there, and a fused multiply-add in it sends the iteration somewhere else than the reference's unfused
+  // broadcast does (observed: blow-up at the step where the reference converges).  Every operation is therefore rounded
+  // separately, in the broadcast's order:  J += (((f - f_prev) - J du) / D) * du * J^2,  D = J^2 du^2 (1e-5 when zero).
+  const double jj = __dmul_rn(j, j);
+  const double jdu = __dmul_rn(jj, __dmul_rn(d, d));
+  const double num = __dadd_rn(__dadd_rn(f, -fu_cache[i]), -__dmul_rn(j, d));
+  const double t = __dmul_rn(__dmul_rn(__ddiv_rn(num, jdu == 0.0 ? 1.0e-5 : jdu), d), jj);
+  J[i] = __dadd_rn(j, t);
+  fu_cache[i] = f;
+}
+}  // namespace
+int32_t b200i_klement_descent(b200_ctx* ctx, int64_t n, const double* J, const double* fu, double* du) {
+  LAUNCH(ctx, klement_descent_kernel, (int)((n + 255) / 256), 256, 0, n, J, fu, du);
+  CHECK_LAUNCH(ctx);
+  return B200_OK;
+}
+int32_t b200i_klement_update(b200_ctx* ctx, int64_t n, double* J, const double* fu, double* fu_cache, const double* du) {
+  LAUNCH(ctx, klement_update_kernel, (int)((n + 255) / 256), 256, 0, n, J, fu, fu_cache, du);
+  CHECK_LAUNCH(ctx);
+  return B200_OK;
+}
 int32_t b200i_ger(b200_ctx* ctx, int64_t n, double* A, int64_t ld, const double* c, const double* w) {
   const dim3 grid((unsigned)((n + 2 * GER_T - 1) / (2 * GER_T)), (unsigned)((n + GER_CPB - 1) / GER_CPB));
   LAUNCH(ctx, ger_kernel, grid, GER_T, 0, n, A, ld, c, w);

@@ -205,10 +205,12 @@ int32_t b200_newton_create(b200_problem* prob, const b200_newton_opts* opts, b20
   B200_REQUIRE(ctx, opts->term_max_stalled_steps <= 128, "newton_create: term_max_stalled_steps must be <= 128");
   B200_REQUIRE(ctx, opts->descent == B200_DESCENT_NEWTON || (opts->descent == B200_DESCENT_PSEUDO_TRANSIENT && opts->globalization != B200_GLOBALIZATION_TRUST_REGION) ||
                         (opts->descent == B200_DESCENT_LEVENBERG_MARQUARDT && opts->globalization == B200_GLOBALIZATION_NONE && opts->linsolve == B200_LINSOLVE_DENSE_LU) ||
-                        (opts->descent == B200_DESCENT_BROYDEN && opts->globalization == B200_GLOBALIZATION_NONE && (prob->n <= 65535 || opts->qn_init_jacobian == B200_QN_INIT_LOW_RANK) &&
+                        (opts->descent == B200_DESCENT_BROYDEN && opts->globalization == B200_GLOBALIZATION_NONE &&
+                         (prob->n <= 65535 || opts->qn_init_jacobian == B200_QN_INIT_LOW_RANK || opts->qn_update_rule == B200_QN_UPDATE_KLEMENT) &&
                          (opts->qn_init_jacobian == B200_QN_INIT_IDENTITY || opts->qn_init_jacobian == B200_QN_INIT_LOW_RANK ||
                           (opts->qn_init_jacobian == B200_QN_INIT_TRUE_JACOBIAN && opts->linsolve == B200_LINSOLVE_DENSE_LU)) &&
-                         (opts->qn_update_rule == B200_QN_UPDATE_GOOD_BROYDEN || opts->qn_update_rule == B200_QN_UPDATE_BAD_BROYDEN)),
+                         (opts->qn_update_rule == B200_QN_UPDATE_GOOD_BROYDEN || opts->qn_update_rule == B200_QN_UPDATE_BAD_BROYDEN ||
+                          (opts->qn_update_rule == B200_QN_UPDATE_KLEMENT && opts->qn_init_jacobian == B200_QN_INIT_IDENTITY))),
                "newton_create: descent must be Newton, PseudoTransient (without a trust region), LevenbergMarquardt (dense concrete Jacobian, its own trust region) or "
                "Broyden (no globalisation, n <= 65535, init_jacobian = true_jacobian needs the dense LU)");
   B200_REQUIRE(ctx, opts->precond == B200_PRECOND_NONE ||
@@ -243,7 +245,9 @@ int32_t b200_newton_create(b200_problem* prob, const b200_newton_opts* opts, b20
   }
   if (opts->descent == B200_DESCENT_BROYDEN) {  // the stored inverse and the update rule's / reset condition's vectors share the LM slots
     A(&nw->lm_dtd); A(&nw->lm_v); A(&nw->lm_a); A(&nw->lm_vold); A(&nw->lm_rhs);
-    if (opts->qn_init_jacobian == B200_QN_INIT_LOW_RANK) {
+    if (opts->qn_update_rule == B200_QN_UPDATE_KLEMENT) {
+      // diagonal structure: the approximate Jacobian is the n-vector lm_dtd, the rule's residual cache lm_v — nothing n x n
+    } else if (opts->qn_init_jacobian == B200_QN_INIT_LOW_RANK) {
       nw->lr_m = std::max(1, std::min(opts->qn_threshold > 0 ? opts->qn_threshold : 10, nw->maxiters));  // threshold = min(threshold, maxiters)
       if (s == B200_OK && (cudaMalloc(&nw->lr_U, sizeof(double) * n * nw->lr_m) != cudaSuccess || cudaMalloc(&nw->lr_V, sizeof(double) * n * nw->lr_m) != cudaSuccess ||
                            cudaMalloc(&nw->lr_c, sizeof(double) * nw->lr_m) != cudaSuccess)) {
@@ -556,7 +560,64 @@ static int32_t broyden_count(b200_newton* nw, const double* x, const double* y, 
   return B200_OK;
 }
 
+// One step of Klement() with its default diagonal structure (klement.jl:30-49, 128-140; reset_conditions.jl:103-120; solve.jl:293-486):
+// J is an n-vector, so descent, update and the reset test are elementwise kernels and one counting reduction — any n.
+static int32_t klement_step(b200_newton* nw) {
+  b200_ctx* ctx = nw->ctx;
+  const int64_t n = nw->n;
+  const b200_newton_opts& o = nw->o;
+  double *J = nw->lm_dtd, *fu_cache = nw->lm_v;
+  const int max_resets = o.qn_max_resets > 0 ? o.qn_max_resets : 100;
+  auto init_diag = [&]() -> int32_t {
+    double alpha = o.qn_alpha;
+    if (!(alpha > 0)) {
+      double fn, un;
+      B200_TRY(h_nrm2(nw, nw->fu, &fn));
+      B200_TRY(h_nrm2(nw, nw->u, &un));
+      alpha = (fn < 1.0e-5) ? 1.0 : (2.0 * fn) / std::max(un, 1.0);
+    }
+    return b200_fill(ctx, n, alpha, J);   // J = one.(fu) .* alpha, NOT inverted (store_inverse_jacobian = false)
+  };
+  int reset = 0;
+  if (nw->nsteps == 0) {
+    B200_TRY(init_diag());
+  } else {
+    double zeros;  // IllConditionedJacobianReset on a Diagonal: any(iszero, diag(J))
+    B200_TRY(broyden_count(nw, J, nullptr, 0.0, &zeros));
+    if (zeros > 0) {
+      reset = 1;
+      if (++nw->qn_nresets >= max_resets) { nw->retcode = B200_RC_CONVERGENCE_FAILURE; nw->force_stop = 1; return B200_OK; }
+      B200_TRY(init_diag());
+    }
+  }
+  B200_TRY(b200i_klement_descent(ctx, n, J, nw->fu, nw->du));
+  CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_scalars, 0, sizeof(double) * 2, ctx->stream));
+  B200_TRY(b200i_axpy_norm(ctx, n, 1.0, nw->du, nw->u, ctx->d_scalars + 1));
+  B200_TRY(b200i_residual_norm(nw->prob, nw->u, nw->fu, ctx->d_scalars));
+  nw->res.nf += 1;
+  nw->res.nsolve += 1;   // the diagonal system goes through NativeJLLinearSolveCache (linear_solve.jl:130-134): nsolve and nfactors both +1
+  nw->res.nfactors += 1;
+  B200_TRY(b200i_fetch_scalars(ctx, 2));
+  const double objective = ctx->h_scalars[0], du_norm = sqrt(ctx->h_scalars[1]);
+  nw->fnorm_inf = objective;
+  nw->bytes += 8.0 * (double)n * 8.0;
+  bool new_best = false;
+  TermQuant tq;
+  B200_TRY(term_quantities(nw, nw->fu, nw->u, objective, &tq));
+  if (term_check(nw, tq, du_norm, &new_best)) { nw->retcode = nw->tc.retcode; nw->force_stop = 1; }
+  if (new_best && nw->best_u) CUDA_TRY(ctx, cudaMemcpyAsync(nw->best_u, nw->u, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+  if (o.store_trace) {
+    b200_trace_rec t;
+    memset(&t, 0, sizeof(t));
+    t.iter = nw->nsteps + 1; t.accepted = 1; t.fnorm_inf = objective; t.step_norm2 = du_norm; t.lin_status = reset;
+    nw->trace.push_back(t);
+  }
+  if (nw->force_stop) return B200_OK;
+  return b200i_klement_update(ctx, n, J, nw->fu, fu_cache, nw->du);
+}
+
 static int32_t broyden_step(b200_newton* nw) {
+  if (nw->o.qn_update_rule == B200_QN_UPDATE_KLEMENT) return klement_step(nw);
   b200_ctx* ctx = nw->ctx;
   const int64_t n = nw->n;
   const b200_newton_opts& o = nw->o;

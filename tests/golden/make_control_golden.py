@@ -52,6 +52,9 @@ def cases():
     # LimitedMemoryBroyden: threshold 10 (the circular buffer wraps), and threshold 3 (every update after the third evicts one)
     out.append(dict(q, name="lbroyden_quadratic", init_jacobian="low_rank", max_resets=3))
     out.append(dict(q, name="lbroyden_quadratic_threshold3", init_jacobian="low_rank", threshold=3, max_resets=3, maxiters=60))
+    # Klement's diagonal rule divides a numerator that cancels to rounding level by J^2 du^2 ~ 1e-15 once |f| ~ 1e-7: past that point
+    # its iterates depend on the last bit of the residual (a fused multiply-add in f is enough).  The sequence is pinned up to 1e-6.
+    out.append(dict(q, name="klement_quadratic", descent="klement", abstol=1e-6, reltol=1e-6))
     return out
 
 
@@ -65,6 +68,12 @@ def run(case):
     term = nn.Termination(mode=case.get("termination", "AbsNormSafeBest"), norm=case.get("term_norm", "inf"), abstol=case["abstol"], reltol=case["reltol"])
     if case.get("descent") == "levenberg_marquardt":
         r = nn.solve_lm(prob, u0, disable_geodesic=case.get("disable_geodesic", False), termination=term, maxiters=case.get("maxiters", 1000))
+        u = r.pop("u")
+        r["u_norm2"] = float(np.linalg.norm(u))
+        r["u_first"] = [float(x) for x in u[:4]]
+        return r
+    if case.get("descent") == "klement":
+        r = nn.solve_klement(prob, u0, termination=term, maxiters=case.get("maxiters", 1000))
         u = r.pop("u")
         r["u_norm2"] = float(np.linalg.norm(u))
         r["u_first"] = [float(x) for x in u[:4]]

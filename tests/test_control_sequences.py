@@ -53,7 +53,7 @@ def _compare(name, e, res, trace, u, radius_of=lambda t: t.trust_radius, rtol=1e
 
 
 def _oracle_supported(c):
-    if c.get("descent") in ("levenberg_marquardt", "broyden"):
+    if c.get("descent") in ("levenberg_marquardt", "broyden", "klement"):
         return False
     return c.get("termination", "AbsNormSafeBest") in ("AbsNormSafeBest", "AbsNorm", "AbsNormSafe") and c.get("term_norm", "inf") == "inf" and \
         c.get("tr_scheme", "Simple") != "Bastin"
@@ -96,6 +96,8 @@ def test_cuda_driver_reproduces_the_numpy_sequences(nls, ctx, d):
         alg = nls.TrustRegion(radius_update_scheme=getattr(nls.RadiusUpdateSchemes, c["tr_scheme"]))
     elif c.get("descent") == "levenberg_marquardt":
         alg = nls.LevenbergMarquardt(disable_geodesic=c.get("disable_geodesic", False))
+    elif c.get("descent") == "klement":
+        alg = nls.Klement()
     elif c.get("descent") == "broyden" and c.get("init_jacobian") == "low_rank":
         alg = nls.LimitedMemoryBroyden(max_resets=c.get("max_resets", 3), threshold=c.get("threshold", 10), reset_tolerance=c.get("reset_tolerance"))
     elif c.get("descent") == "broyden":
@@ -131,3 +133,5 @@ def test_broyden_restatement_meets_the_reference_anchor():
         r = nn.solve_broyden(q, np.ones(2), termination=nn.Termination(abstol=1e-9), **kw)
         assert r["retcode"] == nn.RC["Success"], kw
         assert np.max(np.abs(q.f(r["u"]))) < 1e-9 and np.allclose(r["u"], np.sqrt(2.0), atol=1e-9), kw
+    r = nn.solve_klement(q, np.ones(2), termination=nn.Termination(abstol=1e-9))   # core_tests__item4.jl: Klement on the same problem
+    assert r["retcode"] == nn.RC["Success"] and np.max(np.abs(q.f(r["u"]))) < 1e-9

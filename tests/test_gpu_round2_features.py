@@ -239,3 +239,22 @@ def test_limited_memory_broyden_at_scale_vs_numpy(nls, ctx):
     u = sol.u.to_host() if hasattr(sol.u, "to_host") else np.asarray(sol.u)
     assert ref["nsteps"] == 9 and ref["nresets"] == 0
     assert np.abs(u - np.sqrt(2.0)).max() < 1e-7 and np.abs(u - ref["u"]).max() < 1e-10
+
+
+def test_klement_diagonal_at_scale_vs_numpy(nls, ctx):
+    """Klement() (default diagonal structure: an n-vector Jacobian, elementwise kernels) on 5*10^5 unknowns against the NumPy restatement.
+    Two families of components (starts 1.0 and 1.8) so that no component converges much earlier than the others: the rule divides a
+    numerator that cancels to rounding level by J^2 du^2 once a component is nearly converged, and from there its iterates depend on
+    the last bit of the residual (a spread of starting values makes even the NumPy run jump, see make_control_golden.py)."""
+    from oracle import newton_numpy as nn
+    n = 500_000
+    u0 = np.where(np.arange(n) % 2 == 0, 1.0, 1.8)
+    ref = nn.solve_klement(nn.Quadratic(n, 2.0), u0, termination=nn.Termination(abstol=1e-6), maxiters=100)
+    sol = nls.solve(nls.NonlinearProblem(nls.QuadraticFunction(n), u0, 2.0, ctx=ctx), nls.Klement(), abstol=1e-6, maxiters=100)
+    assert sol.retcode == ref["retcode"] == nls.ReturnCode.Success
+    s = sol.stats
+    assert (s.nsteps, s.nf, s.nsolve, s.nfactors, s.njacs) == (ref["nsteps"], ref["nf"], ref["nsolve"], ref["nfactors"], ref["njacs"]) and ref["nsteps"] == 6
+    fn = np.array([t.fnorm_inf for t in sol.trace])
+    assert np.allclose(fn[:5], np.array(ref["fnorm_inf"])[:5], rtol=1e-8)
+    u = sol.u.to_host() if hasattr(sol.u, "to_host") else np.asarray(sol.u)
+    assert np.abs(u - np.sqrt(2.0)).max() < 1e-6 and sol.resid_inf <= 1e-6
