@@ -135,3 +135,33 @@ def test_broyden_restatement_meets_the_reference_anchor():
         assert np.max(np.abs(q.f(r["u"]))) < 1e-9 and np.allclose(r["u"], np.sqrt(2.0), atol=1e-9), kw
     r = nn.solve_klement(q, np.ones(2), termination=nn.Termination(abstol=1e-9))   # core_tests__item4.jl: Klement on the same problem
     assert r["retcode"] == nn.RC["Success"] and np.max(np.abs(q.f(r["u"]))) < 1e-9
+
+
+MODES9 = ["Norm", "Rel", "RelNorm", "RelNormSafe", "RelNormSafeBest", "Abs", "AbsNorm", "AbsNormSafe", "AbsNormSafeBest"]
+
+
+@pytest.mark.parametrize("mode", MODES9)
+def test_numpy_restatement_meets_the_termination_condition_anchors(mode):
+    """rootfind_tests__item4 / item7 / item13 / item17.jl and NonlinearSolveQuasiNewton/test/core_tests__item3.jl: for every entry of
+    TERMINATION_CONDITIONS (common/common_rootfind_testing.jl:3-13, maximum(abs, .) as the norm) and the DEFAULT tolerances
+    (eps^(4/5)), NewtonRaphson / TrustRegion / LevenbergMarquardt / PseudoTransient / Broyden on quadratic_f from u0 = [1, 1] end
+    with maximum(abs, f(u)) < 1e-9."""
+    from oracle import newton_numpy as nn
+    q, u0, tol = nn.Quadratic(2, 2.0), np.ones(2), float(np.finfo(float).eps) ** 0.8
+    T = lambda: nn.Termination(mode=mode, norm="inf", abstol=tol, reltol=tol)  # noqa: E731
+    runs = {"NewtonRaphson": nn.solve(q, u0, termination=T()), "TrustRegion": nn.solve(q, u0, globalization="trust_region", termination=T()),
+            "PseudoTransient": nn.solve(q, u0, descent="pseudo_transient", alpha_initial=10.0, termination=T()),
+            "LevenbergMarquardt": nn.solve_lm(q, u0, termination=T()), "Broyden": nn.solve_broyden(q, u0, termination=T())}
+    for name, r in runs.items():
+        assert np.max(np.abs(q.f(r["u"]))) < 1e-9, (name, mode, r["retcode"], r["nsteps"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", MODES9)
+def test_cuda_driver_meets_the_termination_condition_anchors(nls, ctx, mode):
+    """The same anchors through the CUDA driver (default tolerances of the library = the reference's eps^(4/5))."""
+    term = getattr(nls, mode + "TerminationMode")(norm="inf")
+    for alg in (nls.NewtonRaphson(), nls.TrustRegion(), nls.PseudoTransient(alpha_initial=10.0), nls.LevenbergMarquardt(), nls.Broyden()):
+        sol = nls.solve(nls.NonlinearProblem(nls.QuadraticFunction(2), np.ones(2), 2.0, ctx=ctx), alg, termination_condition=term)
+        u = sol.u.to_host() if hasattr(sol.u, "to_host") else np.asarray(sol.u)
+        assert np.max(np.abs(u * u - 2.0)) < 1e-9, (alg.name, mode, nls.ReturnCode.name(sol.retcode), sol.stats.nsteps)
