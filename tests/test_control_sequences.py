@@ -165,3 +165,31 @@ def test_cuda_driver_meets_the_termination_condition_anchors(nls, ctx, mode):
         sol = nls.solve(nls.NonlinearProblem(nls.QuadraticFunction(2), np.ones(2), 2.0, ctx=ctx), alg, termination_condition=term)
         u = sol.u.to_host() if hasattr(sol.u, "to_host") else np.asarray(sol.u)
         assert np.max(np.abs(u * u - 2.0)) < 1e-9, (alg.name, mode, nls.ReturnCode.name(sol.retcode), sol.stats.nsteps)
+
+
+def test_restatements_meet_the_iterator_interface_anchor(po):
+    """nlprob_iterator_interface (common/common_rootfind_testing.jl:47-57; rootfind_tests__item2 / 6 / 11 / 15.jl and
+    NonlinearSolveQuasiNewton/test/core_tests__item2.jl): a continuation over p = range(0.01, 2, length = 200) that re-initialises the
+    cache at the previous root, maxiters 100, abstol 1e-10, must return sqrt.(p) — for the NumPy restatement (NewtonRaphson,
+    TrustRegion, PseudoTransient(alpha_initial = 10), LevenbergMarquardt, Broyden) and for the C oracle (the first three)."""
+    from oracle import newton_numpy as nn
+    ps = np.linspace(0.01, 2.0, 200)
+    algs = {"NewtonRaphson": lambda q, u, T: nn.solve(q, u, termination=T, maxiters=100),
+            "TrustRegion": lambda q, u, T: nn.solve(q, u, globalization="trust_region", termination=T, maxiters=100),
+            "PseudoTransient": lambda q, u, T: nn.solve(q, u, descent="pseudo_transient", alpha_initial=10.0, termination=T, maxiters=100),
+            "LevenbergMarquardt": lambda q, u, T: nn.solve_lm(q, u, termination=T, maxiters=100),
+            "Broyden": lambda q, u, T: nn.solve_broyden(q, u, termination=T, maxiters=100)}
+    for name, run in algs.items():
+        u, sols = np.array([0.5]), []
+        for p in ps:
+            r = run(nn.Quadratic(1, p), u, nn.Termination(abstol=1e-10))
+            u = r["u"]
+            sols.append(u[0])
+        assert np.allclose(sols, np.sqrt(ps), rtol=1.5e-8), name
+    for name, kw in (("NewtonRaphson", {}), ("TrustRegion", dict(globalization=1)), ("PseudoTransient", dict(descent=1, pt_alpha_initial=10.0))):
+        u, sols = np.array([0.5]), []
+        for p in ps:
+            P = po.OracleProblem.quadratic(1, p)
+            u, fu, res, tr = P.newton(u, po.default_newton_opts(abstol=1e-10, linsolve=po.LINSOLVE_DENSE_LU, maxiters=100, **kw))
+            sols.append(u[0])
+        assert np.allclose(sols, np.sqrt(ps), rtol=1.5e-8), "oracle.c " + name
