@@ -193,3 +193,23 @@ def test_restatements_meet_the_iterator_interface_anchor(po):
             u, fu, res, tr = P.newton(u, po.default_newton_opts(abstol=1e-10, linsolve=po.LINSOLVE_DENSE_LU, maxiters=100, **kw))
             sols.append(u[0])
         assert np.allclose(sols, np.sqrt(ps), rtol=1.5e-8), "oracle.c " + name
+
+
+def test_numpy_restatement_meets_the_trust_region_anchors():
+    """rootfind_tests__item8.jl (every RadiusUpdateScheme on quadratic_f from [1, 1], abstol 1e-9: successful retcode, err < 1e-9) and
+    rootfind_tests__item10 / item15.jl (newton_fails from u0 = [-10, -1, 1, 2, 3, 4, 10], p = 0: TrustRegion() and
+    LevenbergMarquardt() succeed with |f| < 1e-9 where an undamped Newton iteration does not)."""
+    from oracle import newton_numpy as nn
+    q = nn.Quadratic(2, 2.0)
+    for scheme in ("Simple", "NocedalWright", "NLsolve", "Hei", "Yuan", "Fan", "Bastin"):
+        r = nn.solve(q, np.ones(2), globalization="trust_region", tr_scheme=scheme, termination=nn.Termination(abstol=1e-9))
+        assert r["retcode"] in (nn.RC["Success"], nn.RC["StalledSuccess"]) and np.max(np.abs(q.f(r["u"]))) < 1e-9, scheme
+    nf = nn.NewtonFails(np.zeros(7))
+    u0 = np.array([-10.0, -1.0, 1.0, 2.0, 3.0, 4.0, 10.0])
+    # the Jacobian restated by the chain rule against central differences
+    h = 1e-6
+    fd = (nf.f(u0 + h) - nf.f(u0 - h)) / (2 * h)
+    assert np.allclose(np.diag(nf.jac(u0)), fd, rtol=1e-6)
+    for name, r in (("TrustRegion", nn.solve(nf, u0, globalization="trust_region", termination=nn.Termination(abstol=1e-9))),
+                    ("LevenbergMarquardt", nn.solve_lm(nf, u0, termination=nn.Termination(abstol=1e-9)))):
+        assert r["retcode"] in (nn.RC["Success"], nn.RC["StalledSuccess"]) and np.all(np.abs(nf.f(r["u"])) < 1e-9), (name, r["retcode"], r["nsteps"])
