@@ -1,8 +1,14 @@
 import os
 import sys
 
-import numpy as np
-import pytest
+# The oracle's OpenMP threads must not spin while they wait: on a GPU box whose host cores are shared with other jobs a spinning team
+# turns every parallel region into a scheduling lottery (one run of the N = 100 parity tests took ten minutes instead of one).
+# Set before anything loads an OpenMP runtime.
+os.environ.setdefault("OMP_WAIT_POLICY", "passive")
+os.environ.setdefault("OMP_PROC_BIND", "false")
+
+import numpy as np  # noqa: E402
+import pytest  # noqa: E402
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
